@@ -1,0 +1,432 @@
+// Tall-skinny FP64 GEMMs of the diaglib hot path on the sm_100a FP64 tensor pipe (DMMA).
+//
+//   gram_tn   : C(p x q)  = A(n x p)^T B(n x q)      reduction over the long dimension n
+//   block_mul : Y(n x q)  = alpha V(n x p) C(p x q) + beta Y
+//
+// Both stream the n-long operands exactly once from HBM through a cp.async (LDGSTS)
+// multi-stage shared-memory ring whose column stride is padded (== 4 mod 16 doubles) so
+// that every DMMA m8n8k4 fragment load is bank-conflict free.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+#include <vector>
+
+namespace dlb {
+
+// =====================================================================================
+// gram_tn
+// =====================================================================================
+namespace {
+
+constexpr int GR_THREADS = 512;
+constexpr int GR_WARPS = GR_THREADS / 32;
+constexpr int GR_KT = 32;          // rows of n per pipeline stage
+constexpr int GR_S = GR_KT + 4;    // padded column stride in shared memory (doubles)
+constexpr int GR_STAGES = 3;
+constexpr int GR_MAXB = 128;       // max p / q handled by one launch
+
+// A warp task is a 2 x 4 block of 8x8 output tiles (16 x 32 elements); bit r*4+c of tmask
+// says whether tile (ti0+r, tj0+c) is computed.  The host balances the tasks over the four
+// SM sub-partitions (warp id mod 4), which matters for the triangular (sym_lower) case.
+struct GramTask {
+  uint8_t ti0, tj0, tmask, pad;
+};
+struct GramSched {
+  GramTask t[GR_WARPS][2];
+};
+
+template <bool ALIGN16>
+__device__ __forceinline__ void gram_load_stage(double* s, const double* __restrict__ M, int64_t ld, int ncols,
+                                                int64_t k0, int64_t n, int tid) {
+  if (ALIGN16) {
+    const int total = ncols * (GR_KT / 2);
+    for (int id = tid; id < total; id += GR_THREADS) {
+      const int col = id / (GR_KT / 2), part = id % (GR_KT / 2);
+      const int64_t row = k0 + part * 2;
+      int64_t rem = (n - row) * 8;
+      const int bytes = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+      const double* src = M + (int64_t)col * ld + (bytes > 0 ? row : 0);
+      cp_async16(s + col * GR_S + part * 2, src, bytes);
+    }
+  } else {
+    const int total = ncols * GR_KT;
+    for (int id = tid; id < total; id += GR_THREADS) {
+      const int col = id / GR_KT, part = id % GR_KT;
+      const int64_t row = k0 + part;
+      const int bytes = row < n ? 8 : 0;
+      const double* src = M + (int64_t)col * ld + (bytes > 0 ? row : 0);
+      cp_async8(s + col * GR_S + part, src, bytes);
+    }
+  }
+}
+
+template <bool ALIGN16>
+__global__ void __launch_bounds__(GR_THREADS, 1)
+gram_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const double* __restrict__ B, int64_t ldb,
+            int q, int same, const __grid_constant__ GramSched sched, double* __restrict__ partial, int PB, int QB) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int stage_doubles = (PB + (same ? 0 : QB)) * GR_S;
+
+  const GramTask t0 = sched.t[warp][0], t1 = sched.t[warp][1];
+  double acc[2][2][4][2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[s][r][c][0] = acc[s][r][c][1] = 0.0;
+
+  const int64_t nchunks = (n + GR_KT - 1) / GR_KT;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t my_chunks = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+
+  auto issue = [&](int64_t local_idx) {
+    if (local_idx < my_chunks) {
+      double* s = smem + (local_idx % GR_STAGES) * stage_doubles;
+      const int64_t k0 = (first + local_idx * stride) * GR_KT;
+      gram_load_stage<ALIGN16>(s, A, lda, p, k0, n, tid);
+      if (!same) gram_load_stage<ALIGN16>(s + PB * GR_S, B, ldb, q, k0, n, tid);
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int s = 0; s < GR_STAGES - 1; ++s) issue(s);
+
+  const int frag_off = (lane >> 2) * GR_S + (lane & 3);
+  for (int64_t it = 0; it < my_chunks; ++it) {
+    cp_async_wait<GR_STAGES - 2>();
+    __syncthreads();
+    issue(it + GR_STAGES - 1);
+    const double* sA = smem + (it % GR_STAGES) * stage_doubles;
+    const double* sB = same ? sA : sA + PB * GR_S;
+#pragma unroll
+    for (int ks = 0; ks < GR_KT / 4; ++ks) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const GramTask t = s == 0 ? t0 : t1;
+        if (t.tmask == 0) continue;
+        const double* pa = sA + (t.ti0 * 8) * GR_S + ks * 4 + frag_off;
+        const double* pb = sB + (t.tj0 * 8) * GR_S + ks * 4 + frag_off;
+        if (t.tmask == 0xFF) {
+          double a[2], b[4];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) a[r] = pa[r * 8 * GR_S];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) b[c] = pb[c * 8 * GR_S];
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dmma884(acc[s][r][c][0], acc[s][r][c][1], a[r], b[c]);
+        } else {
+          double a[2] = {0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+            if (t.tmask & (0xF << (4 * r))) a[r] = pa[r * 8 * GR_S];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (t.tmask & (0x11 << c)) b[c] = pb[c * 8 * GR_S];
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (t.tmask & (1 << (r * 4 + c))) dmma884(acc[s][r][c][0], acc[s][r][c][1], a[r], b[c]);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // per-CTA partial result, PB x QB column-major
+  double* out = partial + (size_t)blockIdx.x * PB * QB;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const GramTask t = s == 0 ? t0 : t1;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (t.tmask & (1 << (r * 4 + c))) {
+          const int i = (t.ti0 + r) * 8 + (lane >> 2);
+          const int j = (t.tj0 + c) * 8 + (lane & 3) * 2;
+          out[i + (size_t)j * PB] = acc[s][r][c][0];
+          out[i + (size_t)(j + 1) * PB] = acc[s][r][c][1];
+        }
+  }
+}
+
+// deterministic (fixed-order) sum of the per-CTA partials; mirrors the lower triangle if sym
+__global__ void gram_reduce_kernel(const double* __restrict__ partial, int ncta, int PB, int QB, int p, int q,
+                                   int sym, double* __restrict__ C, int ldc, double* __restrict__ Ct) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p * q) return;
+  const int i = idx % p, j = idx / p;
+  int si = i, sj = j;
+  if (sym && j > i) { si = j; sj = i; }
+  const double* src = partial + si + (size_t)sj * PB;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const size_t step = (size_t)PB * QB;
+  int c = 0;
+  for (; c + 4 <= ncta; c += 4) {
+    s0 += src[(size_t)c * step];
+    s1 += src[(size_t)(c + 1) * step];
+    s2 += src[(size_t)(c + 2) * step];
+    s3 += src[(size_t)(c + 3) * step];
+  }
+  for (; c < ncta; ++c) s0 += src[(size_t)c * step];
+  const double v = (s0 + s1) + (s2 + s3);
+  C[i + (size_t)j * ldc] = v;
+  if (Ct) Ct[j + (size_t)i * ldc] = v;  // mirror of an off-diagonal block of a symmetric product
+}
+
+// Build a balanced task schedule for a p x q block (tile counts ntp x ntq).
+GramSched make_sched(int ntp, int ntq, bool sym_lower) {
+  struct T { int ti0, tj0, mask, cnt; };
+  std::vector<T> tasks;
+  for (int ti0 = 0; ti0 < ntp; ti0 += 2)
+    for (int tj0 = 0; tj0 < ntq; tj0 += 4) {
+      int mask = 0, cnt = 0;
+      for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 4; ++c) {
+          const int ti = ti0 + r, tj = tj0 + c;
+          if (ti < ntp && tj < ntq && (!sym_lower || tj <= ti)) { mask |= 1 << (r * 4 + c); ++cnt; }
+        }
+      if (cnt) tasks.push_back({ti0, tj0, mask, cnt});
+    }
+  std::stable_sort(tasks.begin(), tasks.end(), [](const T& a, const T& b) { return a.cnt > b.cnt; });
+  GramSched s{};
+  int load_q[4] = {0, 0, 0, 0};
+  int load_w[GR_WARPS] = {0};
+  int nslot[GR_WARPS] = {0};
+  for (const T& t : tasks) {
+    // least-loaded sub-partition that still has a free slot
+    int bq = -1;
+    for (int qd = 0; qd < 4; ++qd) {
+      bool has_free = false;
+      for (int w = qd; w < GR_WARPS; w += 4) has_free |= nslot[w] < 2;
+      if (has_free && (bq < 0 || load_q[qd] < load_q[bq])) bq = qd;
+    }
+    int bw = -1;
+    for (int w = bq; w < GR_WARPS; w += 4)
+      if (nslot[w] < 2 && (bw < 0 || load_w[w] < load_w[bw])) bw = w;
+    s.t[bw][nslot[bw]] = GramTask{(uint8_t)t.ti0, (uint8_t)t.tj0, (uint8_t)t.mask, 0};
+    ++nslot[bw];
+    load_w[bw] += t.cnt;
+    load_q[bq] += t.cnt;
+  }
+  return s;
+}
+
+}  // namespace
+
+size_t gram_scratch_bytes(int p, int q, int num_sms) {
+  const int pb = std::min(p, GR_MAXB), qb = std::min(q, GR_MAXB);
+  const int PB = (pb + 7) / 8 * 8, QB = (qb + 7) / 8 * 8;
+  return (size_t)num_sms * PB * QB * sizeof(double);
+}
+
+void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t lda, int p, const double* B,
+             int64_t ldb, int q, double* C, int ldc, bool sym_lower, double* partial) {
+  if (p <= 0 || q <= 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const bool al16 = aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0);
+  const int64_t nchunks = (n + GR_KT - 1) / GR_KT;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, nchunks));
+  for (int p0 = 0; p0 < p; p0 += GR_MAXB)
+    for (int q0 = 0; q0 < q; q0 += GR_MAXB) {
+      const bool diag_blk = sym_lower && p0 == q0;
+      if (sym_lower && q0 > p0) continue;  // mirrored below
+      const int pb = std::min(GR_MAXB, p - p0), qb = std::min(GR_MAXB, q - q0);
+      const int ntp = (pb + 7) / 8, ntq = (qb + 7) / 8;
+      const int PB = ntp * 8, QB = ntq * 8;
+      const double* Ab = A + (int64_t)p0 * lda;
+      const double* Bb = B + (int64_t)q0 * ldb;
+      const int same = (Ab == Bb && lda == ldb && pb == qb) ? 1 : 0;
+      const GramSched sched = make_sched(ntp, ntq, diag_blk);
+      const size_t smem = (size_t)GR_STAGES * (PB + (same ? 0 : QB)) * GR_S * sizeof(double);
+      if (al16)
+        gram_kernel<true><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, sched, partial, PB, QB);
+      else
+        gram_kernel<false><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, sched, partial, PB, QB);
+      ++g_launches;
+      const int tot = pb * qb;
+      double* Cblk = C + p0 + (size_t)q0 * ldc;
+      double* Cmir = (sym_lower && !diag_blk) ? C + q0 + (size_t)p0 * ldc : nullptr;
+      gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, grid, PB, QB, pb, qb, diag_blk ? 1 : 0, Cblk,
+                                                            ldc, Cmir);
+      ++g_launches;
+    }
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// block_mul
+// =====================================================================================
+namespace {
+
+constexpr int BM_THREADS = 256;
+constexpr int BM_RT = 128;            // rows per CTA tile (8 warps x 16 rows)
+constexpr int BM_SV = BM_RT + 4;      // padded stride of a V column in smem
+constexpr int BM_KC = 16;             // columns of V (rows of C) per stage
+constexpr int BM_SC = BM_KC + 4;      // padded stride of a C column chunk
+constexpr int BM_STAGES = 4;
+
+template <int NQT, bool ALIGN16>
+__global__ void __launch_bounds__(BM_THREADS)
+blockmul_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, const double* __restrict__ C, int ldc,
+                int q, double alpha, double beta, double* Y, int64_t ldy) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int QB = NQT * 8;
+  constexpr int STAGE = BM_KC * BM_SV + QB * BM_SC;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * BM_RT;
+  const int nk = (p + BM_KC - 1) / BM_KC;
+
+  double acc[2][NQT][2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < NQT; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+
+  auto issue = [&](int kc) {
+    if (kc < nk) {
+      double* sV = smem + (kc % BM_STAGES) * STAGE;
+      double* sC = sV + BM_KC * BM_SV;
+      const int k0 = kc * BM_KC;
+      if (ALIGN16) {
+        for (int id = tid; id < BM_KC * (BM_RT / 2); id += BM_THREADS) {
+          const int col = id / (BM_RT / 2), part = id % (BM_RT / 2);
+          const int64_t row = row0 + part * 2;
+          int64_t rem = (k0 + col < p) ? (n - row) * 8 : 0;
+          const int bytes = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+          const double* src = bytes > 0 ? V + (int64_t)(k0 + col) * ldv + row : V;
+          cp_async16(sV + col * BM_SV + part * 2, src, bytes);
+        }
+      } else {
+        for (int id = tid; id < BM_KC * BM_RT; id += BM_THREADS) {
+          const int col = id / BM_RT, part = id % BM_RT;
+          const int64_t row = row0 + part;
+          const int bytes = (k0 + col < p && row < n) ? 8 : 0;
+          const double* src = bytes > 0 ? V + (int64_t)(k0 + col) * ldv + row : V;
+          cp_async8(sV + col * BM_SV + part, src, bytes);
+        }
+      }
+      for (int id = tid; id < QB * BM_KC; id += BM_THREADS) {
+        const int j = id / BM_KC, kk = id % BM_KC;
+        const int bytes = (j < q && k0 + kk < p) ? 8 : 0;
+        const double* src = bytes > 0 ? C + (size_t)j * ldc + k0 + kk : C;
+        cp_async8(sC + j * BM_SC + kk, src, bytes);
+      }
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int s = 0; s < BM_STAGES - 1; ++s) issue(s);
+
+  const int a_off = (lane & 3) * BM_SV + warp * 16 + (lane >> 2);
+  const int b_off = (lane >> 2) * BM_SC + (lane & 3);
+  for (int kc = 0; kc < nk; ++kc) {
+    cp_async_wait<BM_STAGES - 2>();
+    __syncthreads();
+    issue(kc + BM_STAGES - 1);
+    const double* sV = smem + (kc % BM_STAGES) * STAGE;
+    const double* sC = sV + BM_KC * BM_SV;
+#pragma unroll
+    for (int k4 = 0; k4 < BM_KC / 4; ++k4) {
+      double a[2], b[NQT];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * BM_SV + a_off + r * 8];
+#pragma unroll
+      for (int c = 0; c < NQT; ++c) b[c] = sC[c * 8 * BM_SC + k4 * 4 + b_off];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < NQT; ++c) dmma884(acc[r][c][0], acc[r][c][1], a[r], b[c]);
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int64_t row = row0 + warp * 16 + r * 8 + (lane >> 2);
+    if (row >= n) continue;
+#pragma unroll
+    for (int c = 0; c < NQT; ++c) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = c * 8 + (lane & 3) * 2 + e;
+        if (col < q) {
+          double* dst = Y + row + (int64_t)col * ldy;
+          double v = alpha * acc[r][c][e];
+          if (beta != 0.0) v += beta * (*dst);
+          *dst = v;
+        }
+      }
+    }
+  }
+}
+
+template <int NQT>
+void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc,
+                     int q, double alpha, double beta, double* Y, int64_t ldy) {
+  constexpr int QB = NQT * 8;
+  constexpr size_t smem = (size_t)BM_STAGES * (BM_KC * BM_SV + QB * BM_SC) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_kernel<NQT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_kernel<NQT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const bool al16 = aligned16(V) && (ldv % 2 == 0);
+  const unsigned grid = (unsigned)((n + BM_RT - 1) / BM_RT);
+  if (al16)
+    blockmul_kernel<NQT, true><<<grid, BM_THREADS, smem, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy);
+  else
+    blockmul_kernel<NQT, false><<<grid, BM_THREADS, smem, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy);
+  ++g_launches;
+}
+
+}  // namespace
+
+void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc, int q,
+               double alpha, double beta, double* Y, int64_t ldy) {
+  if (n <= 0 || q <= 0) return;
+  for (int q0 = 0; q0 < q; q0 += 128) {
+    const int qb = std::min(128, q - q0);
+    const double* Cb = C + (size_t)q0 * ldc;
+    double* Yb = Y + (int64_t)q0 * ldy;
+    if (qb <= 40)
+      launch_blockmul<5>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy);
+    else if (qb <= 80)
+      launch_blockmul<10>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy);
+    else
+      launch_blockmul<16>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy);
+  }
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+
+// U(n x m) <- U * T with T (m x m, ld m) upper triangular with explicit zeros below the
+// diagonal (T = L^-T): the dtrmm('r','l','t','n') of ortho_cd (diaglib.f90:3327).  In place:
+// column blocks are processed last-to-first so that a block only reads columns that have
+// not been overwritten yet (U_new(:,j) depends on U(:,0..j) only).
+void block_trmm_inplace(cudaStream_t st, int64_t n, double* U, int64_t ldu, int m, const double* T) {
+  if (m <= 128) {
+    block_mul(st, n, U, ldu, m, T, m, m, 1.0, 0.0, U, ldu);
+    return;
+  }
+  const int nblk = (m + 127) / 128;
+  for (int b = nblk - 1; b >= 0; --b) {
+    const int q0 = b * 128, qb = std::min(128, m - q0);
+    block_mul(st, n, U, ldu, q0 + qb, T + (size_t)q0 * m, m, qb, 1.0, 0.0, U + (int64_t)q0 * ldu, ldu);
+  }
+}
+
+}  // namespace dlb

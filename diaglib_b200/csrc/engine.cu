@@ -1,0 +1,1227 @@
+// Host control plane of the B200 path: device-resident restatement of lobpcg_driver and
+// davidson_driver (diaglib.f90:171-556, 1483-1853) and of ortho_cd / ortho_vs_x / ortho /
+// check_guess (3185-3341, 3481-3574, 3052-3092, 3734-3786) on top of the sm_100a kernels in
+// dense.cu / sparse.cu / small.cu.  Control flow (iteration counters, done flags, n_act,
+// restart logic) stays on the host; every n-long block stays in HBM; only k x k matrices
+// and 2*n_max norms cross NVLink (NCCL all-reduce) or PCIe (status read-back).
+#include "common.cuh"
+#include "kernels.h"
+
+#include "../../include/diaglib_b200.h"
+#include "../../include/diaglib_b200_kernels.h"
+
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is resolved with dlopen at comm_init
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <list>
+#include <string>
+#include <vector>
+
+namespace dlb {
+
+int64_t g_launches = 0;
+
+namespace {
+
+constexpr double EPS = DBL_EPSILON;
+constexpr double TOL_ORTHO = 2.0 * EPS;  // diaglib.f90:151
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool ensure(size_t bytes) {
+    if (bytes <= cap) return true;
+    release();
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
+    cap = bytes;
+    return true;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct NcclApi {
+  void* handle = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool load() {
+    if (handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) return false;
+#define DLB_SYM(f)                                                      \
+  f = reinterpret_cast<decltype(f)>(dlsym(handle, "nccl" #f));          \
+  if (!f) return false;
+    DLB_SYM(GetUniqueId) DLB_SYM(CommInitRank) DLB_SYM(CommDestroy) DLB_SYM(AllReduce) DLB_SYM(AllGather)
+    DLB_SYM(Send) DLB_SYM(Recv) DLB_SYM(GroupStart) DLB_SYM(GroupEnd) DLB_SYM(GetErrorString)
+#undef DLB_SYM
+    return true;
+  }
+};
+
+enum Phase { PH_MV = 0, PH_DIAG, PH_ORTHO, PH_TOTAL, PH_GRAM, PH_RITZ, PH_RESID, PH_STAGE, PH_COUNT };
+
+struct Hist {
+  int n_max = 0;
+  std::vector<int> it, n_act, done;
+  std::vector<double> eig, rms, mx;
+  void clear(int nm) { n_max = nm; it.clear(); n_act.clear(); done.clear(); eig.clear(); rms.clear(); mx.clear(); }
+};
+
+struct Pending {
+  int ph;
+  cudaEvent_t a, b;
+  bool closed;
+};
+typedef std::list<Pending>::iterator PhaseHandle;
+
+struct Engine {
+  bool inited = false;
+  int device = -1;
+  cudaStream_t st = nullptr;
+  int num_sms = 148;
+  int status = 0;
+  std::string msg;
+
+  NcclApi nccl;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+
+  DevBuf partial, smallws, resid_scratch, scal;
+  void* h_pin = nullptr;  // pinned staging for small read-backs
+  size_t h_pin_bytes = 0;
+
+  // installed matrix + halo plan (built-in callbacks)
+  CsrDevice A;
+  DevBuf b_rowptr, b_col, b_val, b_diag, b_send, b_recv, b_halo;
+  std::vector<int> peer;
+  std::vector<int64_t> send_row0, send_cnt, recv_off, recv_cnt;
+
+  // small-matrix workspace (device)
+  double *d_metric = nullptr, *d_T = nullptr, *d_cholwork = nullptr, *d_xu = nullptr;
+  CholStatus* d_cholst = nullptr;
+
+  // statistics / history / timers of the last driver call
+  Hist hist;
+  int64_t st_cd_passes = 0, st_sweeps = 0, st_qr = 0, st_shifts = 0, st_launch0 = 0, st_launches = 0;
+  double t_acc[PH_COUNT] = {0};
+  std::list<Pending> pending;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t sw0 = nullptr, sw1 = nullptr;
+
+  void fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (status == 0) { status = code; msg = buf; }
+    std::fprintf(stderr, "diaglib_b200: %s\n", buf);
+  }
+
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    DLB_CUDA_CHECK(cudaEventCreate(&e));
+    return e;
+  }
+  PhaseHandle ph_open(int ph) {
+    Pending p{ph, get_event(), get_event(), false};
+    DLB_CUDA_CHECK(cudaEventRecord(p.a, st));
+    pending.push_back(p);
+    return std::prev(pending.end());
+  }
+  void ph_close(PhaseHandle h) {
+    DLB_CUDA_CHECK(cudaEventRecord(h->b, st));
+    h->closed = true;
+  }
+  void ph_resolve() {  // only valid right after a stream synchronize
+    for (auto it = pending.begin(); it != pending.end();) {
+      if (!it->closed) { ++it; continue; }
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, it->a, it->b) == cudaSuccess) t_acc[it->ph] += ms * 1e-3;
+      else cudaGetLastError();
+      ev_pool.push_back(it->a);
+      ev_pool.push_back(it->b);
+      it = pending.erase(it);
+    }
+  }
+  void sync() {
+    DLB_CUDA_CHECK(cudaStreamSynchronize(st));
+    ph_resolve();
+  }
+
+  bool nccl_ok(ncclResult_t r, const char* what) {
+    if (r == ncclSuccess) return true;
+    fail(DIAGLIB_B200_ECOMM, "NCCL %s failed: %s", what, nccl.GetErrorString ? nccl.GetErrorString(r) : "?");
+    return false;
+  }
+  void allreduce(double* d, size_t count, ncclRedOp_t op = ncclSum) {
+    if (nranks == 1 || count == 0) return;
+    nccl_ok(nccl.AllReduce(d, d, count, ncclDouble, op, comm, st), "AllReduce");
+  }
+
+  void ensure_small(int m, int xrows) {
+    const size_t mm = (size_t)m * m;
+    const size_t need = (4 * mm + (size_t)xrows * m + 64) * sizeof(double) + sizeof(CholStatus);
+    if (!smallws.ensure(need)) { fail(DIAGLIB_B200_EALLOC, "memory allocation failed. (small workspace)"); return; }
+    double* b = smallws.as<double>();
+    d_metric = b;
+    d_T = b + mm;
+    d_cholwork = b + 2 * mm;
+    d_xu = b + 4 * mm;
+    d_cholst = reinterpret_cast<CholStatus*>(b + 4 * mm + (size_t)xrows * m + 8);
+  }
+
+  void read_back(void* host_dst, const void* dev_src, size_t bytes) {
+    if (bytes <= h_pin_bytes) {
+      DLB_CUDA_CHECK(cudaMemcpyAsync(h_pin, dev_src, bytes, cudaMemcpyDeviceToHost, st));
+      sync();
+      std::memcpy(host_dst, h_pin, bytes);
+    } else {
+      DLB_CUDA_CHECK(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, st));
+      sync();
+    }
+  }
+
+  // ---- ortho_cd, diaglib.f90:3185-3341 ------------------------------------------------
+  // one host synchronisation per pass (the CholStatus read-back decides macro_done).
+  bool ortho_cd(int64_t n, int m, double* u, int64_t ldu, double& growth) {
+    const int maxit = 10;
+    growth = 1.0;
+    for (int it = 1;; ++it) {
+      if (it > maxit) {  // 3248-3254
+        std::printf("  ortho_cd failed with the following error: maximum number of iterations reached.\n");
+        return false;
+      }
+      ++st_cd_passes;
+      gram_tn(st, num_sms, n, u, ldu, m, u, ldu, m, d_metric, m, true, partial.as<double>());  // 3256
+      allreduce(d_metric, (size_t)m * m);
+      chol_inv(st, m, d_metric, m, d_T, d_cholwork, d_cholst);                                  // 3261-3316
+      CholStatus cs;
+      read_back(&cs, d_cholst, sizeof cs);
+      st_shifts += cs.n_shifts;
+      if (cs.hard_fail) {  // 3276-3284
+        fail(DIAGLIB_B200_ECHOL,
+             "ortho_cd failed with the following error: maximum number of iterations for factorization reached.");
+        return false;
+      }
+      const double rcond = cs.l_norm * cs.linv_norm;
+      growth *= cs.linv_norm;                                    // 3323
+      block_trmm_inplace(st, n, u, ldu, m, d_T);                 // 3327
+      if (EPS * rcond * rcond < TOL_ORTHO) return true;          // 3331-3332
+    }
+  }
+
+  // ---- ortho (QR fallback), diaglib.f90:3052-3092 --------------------------------------
+  // Cold failure path.  The reference orthonormalises with Householder QR (U R^-1 = Q); on
+  // the device the same Q (up to column signs) is produced by classical Gram-Schmidt with
+  // re-orthogonalisation, column by column, built from the gram / block_mul kernels.
+  void ortho_qr(int64_t n, int m, double* u, int64_t ldu) {
+    ++st_qr;
+    if (!scal.ensure(((size_t)m + 8) * sizeof(double))) { fail(DIAGLIB_B200_EALLOC, "memory allocation failed."); return; }
+    double* c = scal.as<double>();
+    for (int j = 0; j < m; ++j) {
+      double* uj = u + (int64_t)j * ldu;
+      for (int pass = 0; pass < 2 && j > 0; ++pass) {
+        gram_tn(st, num_sms, n, u, ldu, j, uj, ldu, 1, c, j, false, partial.as<double>());
+        allreduce(c, j);
+        block_mul(st, n, u, ldu, j, c, j, 1, -1.0, 1.0, uj, ldu);
+      }
+      gram_tn(st, num_sms, n, uj, ldu, 1, uj, ldu, 1, c, 1, false, partial.as<double>());
+      allreduce(c, 1);
+      double nrm2;
+      read_back(&nrm2, c, sizeof(double));
+      const double inv = 1.0 / std::sqrt(nrm2);
+      DLB_CUDA_CHECK(cudaMemcpyAsync(c, &inv, sizeof(double), cudaMemcpyHostToDevice, st));
+      sync();
+      block_mul(st, n, uj, ldu, 1, c, 1, 1, 1.0, 0.0, uj, ldu);
+    }
+  }
+
+  // ---- ortho_vs_x, diaglib.f90:3481-3574 -----------------------------------------------
+  void ortho_vs_x(int64_t n, int m, int k, const double* x, int64_t ldx, double* u, int64_t ldu) {
+    const int maxit = 10;
+    bool done = false;
+    int it = 0;
+    double growth = 1.0;
+    bool ok = ortho_cd(n, k, u, ldu, growth);       // 3533
+    if (status) return;
+    if (!ok) ortho_qr(n, k, u, ldu);                // 3534
+    while (!done) {
+      ++it;
+      ++st_sweeps;
+      gram_tn(st, num_sms, n, x, ldx, m, u, ldu, k, d_xu, m, false, partial.as<double>());  // 3543
+      allreduce(d_xu, (size_t)m * k);
+      block_mul(st, n, x, ldx, m, d_xu, m, k, -1.0, 1.0, u, ldu);                            // 3544
+      ok = ortho_cd(n, k, u, ldu, growth);                                                   // 3548
+      if (status) return;
+      double xu_norm;
+      if (!ok) {                                                                             // 3549,3558-3560
+        ortho_qr(n, k, u, ldu);
+        gram_tn(st, num_sms, n, x, ldx, m, u, ldu, k, d_xu, m, false, partial.as<double>());
+        allreduce(d_xu, (size_t)m * k);
+        std::vector<double> h((size_t)m * k);
+        read_back(h.data(), d_xu, h.size() * sizeof(double));
+        double s = 0.0;
+        for (double v : h) s += v * v;
+        xu_norm = std::sqrt(s);
+      } else {
+        xu_norm = growth * EPS;                                                              // 3562
+      }
+      done = xu_norm < TOL_ORTHO;
+      if (it > maxit && !done) {                                                             // 3568
+        fail(DIAGLIB_B200_EORTHO, " catastrophic failure of ortho_vs_x");
+        return;
+      }
+    }
+  }
+
+  // global row count / offset of this rank's row block
+  void global_rows(int64_t n_loc, int64_t& n_glob, int64_t& row0) {
+    n_glob = n_loc;
+    row0 = 0;
+    if (nranks == 1) return;
+    if (!scal.ensure((size_t)(nranks + 8) * sizeof(double))) return;
+    double* d = scal.as<double>();
+    const double mine = (double)n_loc;
+    DLB_CUDA_CHECK(cudaMemcpyAsync(d + nranks, &mine, sizeof(double), cudaMemcpyHostToDevice, st));
+    nccl_ok(nccl.AllGather(d + nranks, d, 1, ncclDouble, comm, st), "AllGather");
+    std::vector<double> all(nranks);
+    read_back(all.data(), d, nranks * sizeof(double));
+    n_glob = 0;
+    for (int r = 0; r < nranks; ++r) {
+      if (r < rank) row0 += (int64_t)all[r];
+      n_glob += (int64_t)all[r];
+    }
+  }
+
+  void halo_exchange(int m, const double* x, int64_t ldx);
+  void check_guess(int64_t n, int m, double* evec, int64_t ld);
+  void lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, double tol, double shift,
+              diaglib_matvec_t matvec, diaglib_precnd_t precnd, double* eig, double* evec, int32_t* ok);
+  void davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, double tol, int max_dav, double shift,
+                diaglib_matvec_t matvec, diaglib_precnd_t precnd, double* eig, double* evec, int32_t* ok);
+  void begin_call(int n_max) {
+    status = 0;
+    msg.clear();
+    hist.clear(n_max);
+    st_cd_passes = st_sweeps = st_qr = st_shifts = 0;
+    st_launch0 = g_launches;
+    for (double& t : t_acc) t = 0;
+  }
+  void end_call() { st_launches = g_launches - st_launch0; }
+  void record(int it, int n_act, int n_max, const double* eig, const double* r_norm, const int* done) {
+    hist.it.push_back(it);
+    hist.n_act.push_back(n_act);
+    for (int i = 0; i < n_max; ++i) {
+      hist.eig.push_back(eig[i]);
+      hist.rms.push_back(r_norm[2 * i]);
+      hist.mx.push_back(r_norm[2 * i + 1]);
+      hist.done.push_back(done[i]);
+    }
+  }
+};
+
+Engine g;
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// stateless splitmix64 fill, U[0,1): stand-in for random_number (check_guess, 3754)
+__global__ void random_fill_kernel(int64_t n, int m, int64_t ld, int64_t row0, int64_t n_glob, double* out) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  for (int j = 0; j < m; ++j) {
+    uint64_t z = (uint64_t)(row0 + row) + (uint64_t)n_glob * (uint64_t)j + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    out[row + (int64_t)j * ld] = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+  }
+}
+
+// a(i,i) = d(i), i < cnt  (Davidson restart, 1696-1699)
+__global__ void set_diag_kernel(int cnt, double* a, int lda, const double* d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) a[i + (size_t)i * lda] = d[i];
+}
+
+// ---- check_guess, diaglib.f90:3734-3786 ------------------------------------------------
+void Engine::check_guess(int64_t n, int m, double* evec, int64_t ld) {
+  double growth;
+  gram_tn(st, num_sms, n, evec, ld, m, evec, ld, m, d_metric, m, true, partial.as<double>());  // 3762 (and 3749)
+  allreduce(d_metric, (size_t)m * m);
+  std::vector<double> ov((size_t)m * m);
+  read_back(ov.data(), d_metric, ov.size() * sizeof(double));
+  double tr = 0.0;
+  for (int i = 0; i < m; ++i) tr += ov[i + (size_t)i * m];
+  if (tr == 0.0) {  // fac == zero (3750): no guess was provided
+    int64_t n_glob, row0;
+    global_rows(n, n_glob, row0);
+    random_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, m, ld, row0, n_glob, evec);
+    ++g_launches;
+    ortho_cd(n, m, evec, ld, growth);
+    return;
+  }
+  double diag_norm = 0.0, out_norm = 0.0;
+  for (int i = 0; i < m; ++i) {
+    diag_norm += ov[i + (size_t)i * m] * ov[i + (size_t)i * m];
+    for (int j = 0; j < i; ++j) out_norm += ov[j + (size_t)i * m] * ov[j + (size_t)i * m];
+  }
+  diag_norm = diag_norm / (double)m;
+  if (diag_norm != 1.0 || out_norm != 0.0) ortho_cd(n, m, evec, ld, growth);  // 3774-3779
+}
+
+void print_header(const char* name, double tol) {
+  std::printf("    %s iterations (tol=%10.2E):\n", name, tol);
+  std::printf("    ------------------------------------------------------------------\n");
+  std::printf("        iter  root              eigenvalue         rms         max ok\n");
+  std::printf("    ------------------------------------------------------------------\n");
+}
+void print_timings(const char* name, const double* t) {
+  std::printf("  timings for %s (device seconds):\n", name);
+  std::printf("    matrix-vector multiplications: %12.4f\n", t[PH_MV]);
+  std::printf("    diagonalization:               %12.4f\n", t[PH_DIAG]);
+  std::printf("    orthogonalization:             %12.4f\n", t[PH_ORTHO]);
+  std::printf("                                   ========================\n");
+  std::printf("    total:                         %12.4f\n", t[PH_TOTAL]);
+}
+
+// =======================================================================================
+// lobpcg_driver, standard branch — diaglib.f90:171-556
+// =======================================================================================
+void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, double tol, double shift,
+                    diaglib_matvec_t matvec, diaglib_precnd_t precnd, double* eig, double* evec, int32_t* ok_out) {
+  begin_call(n_max);
+  *ok_out = 0;
+  const int64_t nn = n;
+  const int len_a = 3 * n_max;
+  int64_t n_glob, row0;
+  global_rows(nn, n_glob, row0);
+
+  PhaseHandle ph_tot = ph_open(PH_TOTAL);
+  // workspaces (251-276).  bspace / bx_new of the reference are only used by the gen_eig
+  // branch and are not allocated; space/aspace are not zero-filled (284-286) because every
+  // column is written before it is read in the standard branch.
+  const size_t blk = (size_t)nn * n_max * sizeof(double);
+  DevBuf b_space, b_aspace, b_r, b_xnew, b_axnew, b_evec, b_red;
+  const bool evec_on_dev = is_device_ptr(evec);
+  const bool eig_on_dev = is_device_ptr(eig);
+  bool okm = b_space.ensure(3 * blk) && b_aspace.ensure(3 * blk) && b_r.ensure(blk) && b_xnew.ensure(blk) &&
+             b_axnew.ensure(blk);
+  if (!evec_on_dev) okm = okm && b_evec.ensure(blk);
+  const size_t eigw = eig_work_doubles(len_a);
+  const size_t cfw = coeffs_work_doubles(len_a, n_max, n_max);
+  const size_t red_doubles = (size_t)len_a * len_a + len_a + (size_t)len_a * n_max + eigw + cfw + 4 * n_max + 64;
+  okm = okm && b_red.ensure(red_doubles * sizeof(double));
+  if (okm) ensure_small(n_max, 2 * n_max);
+  okm = okm && resid_scratch.ensure(residual_scratch_bytes(n_max, num_sms));
+  auto cleanup = [&]() {
+    b_space.release(); b_aspace.release(); b_r.release(); b_xnew.release(); b_axnew.release(); b_evec.release();
+    b_red.release();
+  };
+  if (!okm || status) {
+    fail(DIAGLIB_B200_EALLOC, "memory allocation failed. (lobpcg workspaces)");
+    cleanup();
+    ph_close(ph_tot);
+    sync();
+    end_call();
+    return;
+  }
+  double* space = b_space.as<double>();
+  double* aspace = b_aspace.as<double>();
+  double* r = b_r.as<double>();
+  double* x_new = b_xnew.as<double>();
+  double* ax_new = b_axnew.as<double>();
+  double* d_evec = evec_on_dev ? evec : b_evec.as<double>();
+  double* a_red = b_red.as<double>();  // kept compact: leading dimension = current len_u
+  double* e_red = a_red + (size_t)len_a * len_a;
+  double* u_p = e_red + len_a;
+  double* eig_work = u_p + (size_t)len_a * n_max;
+  double* cf_work = eig_work + eigw;
+  double* d_norms = cf_work + cfw;                               // 2*n_max
+  int* d_active = reinterpret_cast<int*>(d_norms + 2 * n_max);   // n_max ints
+  EigStatus* d_eigst = reinterpret_cast<EigStatus*>(d_norms + 3 * n_max + 8);
+  CoeffStatus* d_cfst = reinterpret_cast<CoeffStatus*>(d_norms + 3 * n_max + 16);
+
+  if (!evec_on_dev) {
+    PhaseHandle h = ph_open(PH_STAGE);
+    DLB_CUDA_CHECK(cudaMemcpyAsync(d_evec, evec, blk, cudaMemcpyHostToDevice, st));
+    ph_close(h);
+  }
+
+  std::vector<double> h_eig(n_max), h_norms(2 * n_max), r_norm(2 * n_max, 0.0);
+  std::vector<int> done(n_max, 0), h_active(n_max, 1);
+  const int32_t n32 = n;
+  PhaseHandle h;
+
+  auto COL = [&](double* base, int col1) { return base + (size_t)nn * (col1 - 1); };  // 1-based column
+
+  check_guess(nn, n_max, d_evec, nn);                                                  // 295
+  block_copy(st, nn, n_max, d_evec, nn, space, nn);                                    // 306
+  h = ph_open(PH_MV);
+  { int32_t m32 = n_max; matvec(&n32, &m32, space, aspace); }                          // 309
+  ph_close(h);
+  if (shift != 0.0) block_axpy(st, nn, n_max, shift, space, nn, aspace, nn);           // 312
+  h = ph_open(PH_GRAM);
+  gram_tn(st, num_sms, nn, space, nn, n_max, aspace, nn, n_max, a_red, n_max, true, partial.as<double>());  // 313
+  allreduce(a_red, (size_t)n_max * n_max);
+  ph_close(h);
+  h = ph_open(PH_DIAG);
+  sym_eig(st, n_max, a_red, n_max, false, e_red, eig_work, d_eigst);                   // 315
+  ph_close(h);
+  h = ph_open(PH_RITZ);
+  block_mul(st, nn, space, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, space, nn);       // 322-323 (row-local, in place)
+  block_mul(st, nn, aspace, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, aspace, nn);     // 324-325
+  ph_close(h);
+  h = ph_open(PH_RESID);
+  DLB_CUDA_CHECK(cudaMemcpyAsync(d_active, h_active.data(), n_max * sizeof(int), cudaMemcpyHostToDevice, st));
+  residual_norms(st, num_sms, nn, n_max, aspace, nn, space, nn, e_red, d_active, r, nn, d_norms,
+                 resid_scratch.as<double>());                                          // 337-346
+  read_back(h_eig.data(), e_red, n_max * sizeof(double));                              // eig = e_red(1:n_max) (318)
+  int ind_x = 1, ind_w = ind_x + n_max, ind_p = 0;
+  {
+    int32_t m32 = n_max;
+    double fac = shift - h_eig[ind_x - 1];
+    precnd(&n32, &m32, &fac, COL(r, ind_x), COL(space, ind_w));                        // 352
+  }
+  ph_close(h);
+  h = ph_open(PH_ORTHO);
+  ortho_vs_x(nn, n_max, n_max, space, nn, COL(space, ind_w), nn);                      // 366
+  ph_close(h);
+
+  const double tol_rms = tol, tol_max = 10.0 * tol;
+  const double sqrtn = std::sqrt((double)n_glob);
+  bool ok = false;
+  int n_act = n_max;
+  if (verbose && rank == 0) print_header("LOBPCG", tol);
+
+  for (int it = 1; it <= max_iter && status == 0; ++it) {
+    h = ph_open(PH_MV);
+    { int32_t m32 = n_act; matvec(&n32, &m32, COL(space, ind_w), COL(aspace, ind_w)); }  // 394
+    ph_close(h);
+    if (shift != 0.0) block_axpy(st, nn, n_act, shift, COL(space, ind_w), nn, COL(aspace, ind_w), nn);  // 397
+    int len_u = n_max + 2 * n_act;
+    if (it == 1) len_u = 2 * n_max;
+    h = ph_open(PH_GRAM);
+    gram_tn(st, num_sms, nn, space, nn, len_u, aspace, nn, len_u, a_red, len_u, true, partial.as<double>());  // 403
+    allreduce(a_red, (size_t)len_u * len_u);
+    ph_close(h);
+    h = ph_open(PH_DIAG);
+    sym_eig(st, len_u, a_red, len_u, false, e_red, eig_work, d_eigst);                 // 406
+    ph_close(h);
+    h = ph_open(PH_RITZ);
+    block_mul(st, nn, space, nn, len_u, a_red, len_u, n_max, 1.0, 0.0, x_new, nn);     // 420
+    block_mul(st, nn, aspace, nn, len_u, a_red, len_u, n_max, 1.0, 0.0, ax_new, nn);   // 421
+    ph_close(h);
+    h = ph_open(PH_RESID);
+    for (int i = 0; i < n_max; ++i) h_active[i] = done[i] ? 0 : 1;
+    DLB_CUDA_CHECK(cudaMemcpyAsync(d_active, h_active.data(), n_max * sizeof(int), cudaMemcpyHostToDevice, st));
+    residual_norms(st, num_sms, nn, n_max, ax_new, nn, x_new, nn, e_red, d_active, r, nn, d_norms,
+                   resid_scratch.as<double>());                                        // 428-442
+    ph_close(h);
+    allreduce(d_norms, n_max, ncclSum);
+    allreduce(d_norms + n_max, n_max, ncclMax);
+    {
+      // one read-back for eigenvalues, norms and the eigensolver status
+      DLB_CUDA_CHECK(cudaMemcpyAsync(h_norms.data(), d_norms, 2 * n_max * sizeof(double), cudaMemcpyDeviceToHost, st));
+      EigStatus es;
+      DLB_CUDA_CHECK(cudaMemcpyAsync(&es, d_eigst, sizeof es, cudaMemcpyDeviceToHost, st));
+      read_back(h_eig.data(), e_red, n_max * sizeof(double));                          // 416
+      if (!es.converged) {                                                             // 412-415
+        fail(DIAGLIB_B200_EDSYEV, "dsyev failed. info = %6d", es.sweeps);
+        break;
+      }
+    }
+    for (int i = 0; i < n_max; ++i) {
+      if (done[i]) continue;
+      r_norm[2 * i] = std::sqrt(h_norms[i]) / sqrtn;                                    // 440
+      r_norm[2 * i + 1] = h_norms[n_max + i];                                           // 441
+    }
+    for (int i = 0; i < n_max; ++i) {                                                   // 446-455
+      if (done[i]) continue;
+      done[i] = (r_norm[2 * i] < tol_rms && r_norm[2 * i + 1] < tol_max && it > 1) ? 1 : 0;
+      if (!done[i]) {
+        for (int j = i + 1; j < n_max; ++j) done[j] = 0;
+        break;
+      }
+    }
+    record(it, n_act, n_max, h_eig.data(), r_norm.data(), done.data());
+    if (verbose && rank == 0) {                                                         // 459-464
+      for (int i = 0; i < n_targ; ++i)
+        std::printf("        %4d  %4d%24.12f%12.4E%12.4E%3s\n", it, i + 1, h_eig[i] - shift, r_norm[2 * i],
+                    r_norm[2 * i + 1], done[i] ? "T" : "F");
+      std::printf("\n");
+    }
+    bool all_done = true;
+    for (int i = 0; i < n_targ; ++i) all_done = all_done && done[i];
+    if (all_done) {                                                                     // 465-469
+      block_copy(st, nn, n_max, x_new, nn, d_evec, nn);
+      ok = true;
+      break;
+    }
+    int cnt = 0;
+    for (int i = 0; i < n_max; ++i) cnt += done[i];
+    n_act = n_max - cnt;                                                                // 475-478
+    ind_x = n_max - n_act + 1;
+    ind_p = ind_x + n_act;
+    ind_w = ind_p + n_act;
+    h = ph_open(PH_DIAG);
+    get_coeffs(st, len_u, len_u, n_max, n_act, a_red, u_p, cf_work, d_cfst);            // 488
+    ph_close(h);
+    // p = space u_p, ap = aspace u_p (495-498).  The products are row-local, so they are
+    // written straight into the p columns of space/aspace instead of going through evec.
+    h = ph_open(PH_RITZ);
+    block_mul(st, nn, space, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(space, ind_p), nn);
+    block_mul(st, nn, aspace, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(aspace, ind_p), nn);
+    block_copy(st, nn, n_max, x_new, nn, space, nn);                                    // 510
+    block_copy(st, nn, n_max, ax_new, nn, aspace, nn);                                  // 511
+    ph_close(h);
+    h = ph_open(PH_RESID);
+    {
+      int32_t m32 = n_act;
+      double fac = shift - h_eig[0];
+      precnd(&n32, &m32, &fac, COL(r, ind_x), COL(space, ind_w));                       // 518
+    }
+    ph_close(h);
+    h = ph_open(PH_ORTHO);
+    ortho_vs_x(nn, n_max + n_act, n_act, space, nn, COL(space, ind_w), nn);             // 528
+    ph_close(h);
+    {
+      CoeffStatus cs;  // checked lazily: the ortho_vs_x above has synchronised the stream
+      DLB_CUDA_CHECK(cudaMemcpy(&cs, d_cfst, sizeof cs, cudaMemcpyDeviceToHost));
+      st_sweeps += cs.sweeps;
+      st_cd_passes += cs.cd_passes;
+      st_qr += cs.qr;
+      if (cs.fail) fail(DIAGLIB_B200_EORTHO, " catastrophic failure of ortho_vs_x (get_coeffs)");
+    }
+  }
+  (void)ind_p;
+  if (eig_on_dev) DLB_CUDA_CHECK(cudaMemcpyAsync(eig, h_eig.data(), n_max * sizeof(double), cudaMemcpyHostToDevice, st));
+  else std::memcpy(eig, h_eig.data(), n_max * sizeof(double));
+  if (!evec_on_dev) {
+    h = ph_open(PH_STAGE);
+    DLB_CUDA_CHECK(cudaMemcpyAsync(evec, d_evec, blk, cudaMemcpyDeviceToHost, st));
+    ph_close(h);
+  }
+  ph_close(ph_tot);
+  sync();
+  if (verbose && rank == 0) print_timings("lobpcg", t_acc);
+  cleanup();
+  end_call();
+  *ok_out = (ok && status == 0) ? 1 : 0;
+}
+
+// =======================================================================================
+// davidson_driver — diaglib.f90:1483-1853
+// =======================================================================================
+void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, double tol, int max_dav,
+                      double shift, diaglib_matvec_t matvec, diaglib_precnd_t precnd, double* eig, double* evec,
+                      int32_t* ok_out) {
+  begin_call(n_max);
+  *ok_out = 0;
+  const int64_t nn = n;
+  const int min_dav = 10;
+  const int dim_dav = std::max(min_dav, max_dav);  // 1595
+  const int lda = dim_dav * n_max;                 // 1596
+  int64_t n_glob, row0;
+  global_rows(nn, n_glob, row0);
+
+  PhaseHandle ph_tot = ph_open(PH_TOTAL);
+  const size_t blk = (size_t)nn * n_max * sizeof(double);
+  const size_t big = (size_t)nn * lda * sizeof(double);
+  DevBuf b_space, b_aspace, b_r, b_evec, b_red;
+  const bool evec_on_dev = is_device_ptr(evec);
+  const bool eig_on_dev = is_device_ptr(eig);
+  bool okm = b_space.ensure(big) && b_aspace.ensure(big) && b_r.ensure(blk);
+  if (!evec_on_dev) okm = okm && b_evec.ensure(blk);
+  const size_t eigw = eig_work_doubles(lda);
+  const size_t red_doubles = 2 * (size_t)lda * lda + lda + eigw + 4 * n_max + 64;
+  okm = okm && b_red.ensure(red_doubles * sizeof(double));
+  if (okm) ensure_small(n_max, lda);
+  okm = okm && resid_scratch.ensure(residual_scratch_bytes(n_max, num_sms));
+  auto cleanup = [&]() { b_space.release(); b_aspace.release(); b_r.release(); b_evec.release(); b_red.release(); };
+  if (!okm || status) {
+    fail(DIAGLIB_B200_EALLOC, "memory allocation failed. (davidson workspaces)");
+    cleanup();
+    ph_close(ph_tot);
+    sync();
+    end_call();
+    return;
+  }
+  double* space = b_space.as<double>();
+  double* aspace = b_aspace.as<double>();
+  double* r = b_r.as<double>();
+  double* d_evec = evec_on_dev ? evec : b_evec.as<double>();
+  double* a_red = b_red.as<double>();
+  double* a_copy = a_red + (size_t)lda * lda;
+  double* e_red = a_copy + (size_t)lda * lda;
+  double* eig_work = e_red + lda;
+  double* d_norms = eig_work + eigw;
+  int* d_active = reinterpret_cast<int*>(d_norms + 2 * n_max);
+  EigStatus* d_eigst = reinterpret_cast<EigStatus*>(d_norms + 3 * n_max + 8);
+
+  DLB_CUDA_CHECK(cudaMemsetAsync(space, 0, big, st));                                   // 1632-1634
+  DLB_CUDA_CHECK(cudaMemsetAsync(aspace, 0, big, st));
+  DLB_CUDA_CHECK(cudaMemsetAsync(a_red, 0, (size_t)lda * lda * sizeof(double), st));
+  if (!evec_on_dev) {
+    PhaseHandle h = ph_open(PH_STAGE);
+    DLB_CUDA_CHECK(cudaMemcpyAsync(d_evec, evec, blk, cudaMemcpyHostToDevice, st));
+    ph_close(h);
+  }
+  std::vector<double> h_eig(n_max), h_norms(2 * n_max), r_norm(2 * n_max, 0.0);
+  std::vector<int> done(n_max, 0), h_active(n_max, 0);
+  const int32_t n32 = n;
+  const double sqrtn = std::sqrt((double)n_glob);
+  const double tol_rms = tol, tol_max = 10.0 * tol;
+  bool ok = false;
+  PhaseHandle h;
+  auto COL = [&](double* base, int col1) { return base + (size_t)nn * (col1 - 1); };
+
+  check_guess(nn, n_max, d_evec, nn);                                                   // 1644
+  block_copy(st, nn, n_max, d_evec, nn, space, nn);                                     // 1648
+  int n_act = n_max, ind = 1, i_beg = 1, m_dim = 1, ldu = 0, n_rst = 0, n_frozen = 0;
+  bool restart = false;
+  if (verbose && rank == 0) print_header("Davidson-Liu", tol);
+
+  for (int it = 1; it <= max_iter && status == 0; ++it) {
+    ldu = ldu + n_act;                                                                  // 1680
+    const int c1 = i_beg + n_rst;  // first column of the new block (1-based)
+    h = ph_open(PH_MV);
+    { int32_t m32 = n_act; matvec(&n32, &m32, COL(space, c1), COL(aspace, c1)); }       // 1685
+    ph_close(h);
+    h = ph_open(PH_GRAM);
+    double* a_blk = a_red + (size_t)lda * (c1 - 1);
+    gram_tn(st, num_sms, nn, space, nn, ldu, COL(aspace, c1), nn, n_act, a_blk, lda, false, partial.as<double>());  // 1691
+    // rows > ldu of these columns are zero on every rank, so the block can be reduced as one range
+    allreduce(a_blk, (size_t)(n_act - 1) * lda + ldu);
+    ph_close(h);
+    if (restart) {                                                                      // 1696-1702
+      if (n_rst > 0) { set_diag_kernel<<<(n_rst + 127) / 128, 128, 0, st>>>(n_rst, a_red, lda, e_red); ++g_launches; }
+      restart = false;
+      n_rst = 0;
+    }
+    h = ph_open(PH_DIAG);
+    DLB_CUDA_CHECK(cudaMemcpy2DAsync(a_copy, sizeof(double) * lda, a_red, sizeof(double) * lda, sizeof(double) * ldu,
+                                     ldu, cudaMemcpyDeviceToDevice, st));               // 1703 (the ldu x ldu part)
+    sym_eig(st, ldu, a_copy, lda, true, e_red, eig_work, d_eigst);                      // 1708
+    ph_close(h);
+    h = ph_open(PH_RITZ);
+    block_mul(st, nn, space, nn, ldu, a_copy, lda, n_max, 1.0, 0.0, d_evec, nn);        // 1717
+    block_mul(st, nn, aspace, nn, ldu, a_copy, lda, n_max, 1.0, 0.0, r, nn);            // 1721
+    ph_close(h);
+    h = ph_open(PH_RESID);
+    for (int i = 0; i < n_max; ++i) h_active[i] = (i < n_targ && !done[i]) ? 1 : 0;     // 1723-1727
+    DLB_CUDA_CHECK(cudaMemcpyAsync(d_active, h_active.data(), n_max * sizeof(int), cudaMemcpyHostToDevice, st));
+    residual_norms(st, num_sms, nn, n_max, r, nn, d_evec, nn, e_red, d_active, r, nn, d_norms,
+                   resid_scratch.as<double>());                                         // 1729-1731
+    ph_close(h);
+    allreduce(d_norms, n_max, ncclSum);
+    allreduce(d_norms + n_max, n_max, ncclMax);
+    {
+      DLB_CUDA_CHECK(cudaMemcpyAsync(h_norms.data(), d_norms, 2 * n_max * sizeof(double), cudaMemcpyDeviceToHost, st));
+      EigStatus es;
+      DLB_CUDA_CHECK(cudaMemcpyAsync(&es, d_eigst, sizeof es, cudaMemcpyDeviceToHost, st));
+      read_back(h_eig.data(), e_red, n_max * sizeof(double));                           // 1715
+      if (!es.converged) {
+        fail(DIAGLIB_B200_EDSYEV, "dsyev failed. info = %6d", es.sweeps);
+        break;
+      }
+    }
+    for (int i = 0; i < n_targ; ++i) {
+      if (done[i]) continue;
+      r_norm[2 * i] = std::sqrt(h_norms[i]) / sqrtn;                                     // 1730
+      r_norm[2 * i + 1] = h_norms[n_max + i];                                            // 1731
+    }
+    for (int i = 0; i < n_targ; ++i) {                                                   // 1737-1746
+      if (done[i]) continue;
+      done[i] = (r_norm[2 * i] < tol_rms && r_norm[2 * i + 1] < tol_max && it > 1) ? 1 : 0;
+      if (!done[i]) {
+        for (int j = i + 1; j < n_max; ++j) done[j] = 0;
+        break;
+      }
+    }
+    record(it, n_act, n_max, h_eig.data(), r_norm.data(), done.data());
+    if (verbose && rank == 0) {
+      for (int i = 0; i < n_targ; ++i)
+        std::printf("        %4d  %4d%24.12f%12.4E%12.4E%3s\n", it, i + 1, h_eig[i] - shift, r_norm[2 * i],
+                    r_norm[2 * i + 1], done[i] ? "T" : "F");
+      std::printf("\n");
+    }
+    bool all_done = true;
+    for (int i = 0; i < n_targ; ++i) all_done = all_done && done[i];
+    if (all_done) { ok = true; break; }                                                  // 1757-1760
+    if (m_dim < dim_dav) {                                                               // 1765
+      m_dim = m_dim + 1;
+      i_beg = i_beg + n_act;
+      n_act = n_max;
+      n_frozen = 0;
+      for (int i = 0; i < n_targ; ++i) {
+        if (done[i]) { n_act--; n_frozen++; } else break;
+      }
+      ind = n_max - n_act + 1;
+      h = ph_open(PH_RESID);
+      {
+        int32_t m32 = n_act;
+        double fac = -h_eig[ind - 1];
+        precnd(&n32, &m32, &fac, COL(r, ind), COL(space, i_beg));                        // 1786
+      }
+      ph_close(h);
+      h = ph_open(PH_ORTHO);
+      ortho_vs_x(nn, ldu, n_act, space, nn, COL(space, i_beg), nn);                      // 1792
+      ph_close(h);
+    } else {                                                                             // 1795-1825
+      if (verbose && rank == 0) std::printf("      Restarting davidson.\n");
+      n_act = n_max;
+      DLB_CUDA_CHECK(cudaMemsetAsync(space, 0, big, st));
+      block_copy(st, nn, n_max, d_evec, nn, space, nn);
+      DLB_CUDA_CHECK(cudaMemsetAsync(aspace, 0, big, st));
+      DLB_CUDA_CHECK(cudaMemsetAsync(a_red, 0, (size_t)lda * lda * sizeof(double), st));
+      ldu = 0; i_beg = 1; m_dim = 1; n_rst = 0;
+      for (int i = 0; i < n_targ; ++i) { if (done[i]) n_rst++; else break; }
+      restart = true;
+    }
+    if (verbose && rank == 0) {
+      std::printf("    ----------------------------------------\n");
+      std::printf("      # target vectors:    %4d\n      # new vectors added: %4d\n      # converged vectors: %4d\n",
+                  n_targ, n_act, n_frozen);
+      std::printf("    ----------------------------------------\n");
+    }
+  }
+  if (eig_on_dev) DLB_CUDA_CHECK(cudaMemcpyAsync(eig, h_eig.data(), n_max * sizeof(double), cudaMemcpyHostToDevice, st));
+  else std::memcpy(eig, h_eig.data(), n_max * sizeof(double));
+  if (!evec_on_dev) {
+    h = ph_open(PH_STAGE);
+    DLB_CUDA_CHECK(cudaMemcpyAsync(evec, d_evec, blk, cudaMemcpyDeviceToHost, st));
+    ph_close(h);
+  }
+  ph_close(ph_tot);
+  sync();
+  if (verbose && rank == 0) print_timings("davidson", t_acc);
+  cleanup();
+  end_call();
+  *ok_out = (ok && status == 0) ? 1 : 0;
+}
+
+// ---- halo exchange for the built-in CSR matvec ------------------------------------------
+void Engine::halo_exchange(int m, const double* x, int64_t ldx) {
+  if (nranks == 1 || A.n_halo == 0 || peer.empty()) return;
+  int64_t tot_send = 0, tot_recv = 0;
+  for (size_t i = 0; i < peer.size(); ++i) { tot_send += send_cnt[i]; tot_recv += recv_cnt[i]; }
+  if (!b_send.ensure((size_t)tot_send * m * sizeof(double)) || !b_recv.ensure((size_t)tot_recv * m * sizeof(double)) ||
+      !b_halo.ensure((size_t)A.n_halo * m * sizeof(double))) {
+    fail(DIAGLIB_B200_EALLOC, "memory allocation failed. (halo buffers)");
+    return;
+  }
+  double* sb = b_send.as<double>();
+  double* rb = b_recv.as<double>();
+  int64_t so = 0;
+  for (size_t i = 0; i < peer.size(); ++i) {
+    pack_rows(st, send_row0[i], send_cnt[i], m, x, ldx, sb + so * m);
+    so += send_cnt[i];
+  }
+  nccl_ok(nccl.GroupStart(), "GroupStart");
+  so = 0;
+  int64_t ro = 0;
+  for (size_t i = 0; i < peer.size(); ++i) {
+    if (send_cnt[i] > 0) nccl_ok(nccl.Send(sb + so * m, (size_t)send_cnt[i] * m, ncclDouble, peer[i], comm, st), "Send");
+    if (recv_cnt[i] > 0) nccl_ok(nccl.Recv(rb + ro * m, (size_t)recv_cnt[i] * m, ncclDouble, peer[i], comm, st), "Recv");
+    so += send_cnt[i];
+    ro += recv_cnt[i];
+  }
+  nccl_ok(nccl.GroupEnd(), "GroupEnd");
+  ro = 0;
+  double* hb = b_halo.as<double>();
+  for (size_t i = 0; i < peer.size(); ++i) {
+    if (recv_cnt[i] > 0)
+      DLB_CUDA_CHECK(cudaMemcpy2DAsync(hb + recv_off[i], sizeof(double) * A.n_halo, rb + ro * m,
+                                       sizeof(double) * recv_cnt[i], sizeof(double) * recv_cnt[i], m,
+                                       cudaMemcpyDeviceToDevice, st));
+    ro += recv_cnt[i];
+  }
+}
+
+// stages a host block through HBM for the standalone ortho entry points
+struct Staged {
+  double* dev = nullptr;
+  double* host = nullptr;
+  size_t bytes = 0;
+  bool owned = false;
+  Staged(const double* p, size_t b) : host(const_cast<double*>(p)), bytes(b) {
+    if (is_device_ptr(p)) { dev = host; return; }
+    owned = true;
+    DLB_CUDA_CHECK(cudaMalloc(&dev, std::max<size_t>(bytes, 8)));
+    DLB_CUDA_CHECK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, g.st));
+  }
+  void back() { if (owned) DLB_CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, g.st)); }
+  ~Staged() { if (owned) { cudaStreamSynchronize(g.st); cudaFree(dev); } }
+};
+
+bool require_init() {
+  if (g.inited) return true;
+  if (diaglib_b200_init(-1) == DIAGLIB_B200_OK) return true;
+  return false;
+}
+
+}  // namespace
+}  // namespace dlb
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+using namespace dlb;
+
+extern "C" {
+
+int32_t diaglib_b200_init(int32_t device) {
+  if (g.inited && (device < 0 || device == g.device)) return DIAGLIB_B200_OK;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    g.status = DIAGLIB_B200_ENODEVICE;
+    g.msg = "no CUDA device available: diaglib_b200 has no CPU fallback";
+    return DIAGLIB_B200_ENODEVICE;
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); g.status = DIAGLIB_B200_ENODEVICE; return g.status; }
+  g.device = device;
+  cudaDeviceProp prop;
+  DLB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  g.num_sms = prop.multiProcessorCount;
+  if (!g.st) DLB_CUDA_CHECK(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
+  if (!g.h_pin) {
+    g.h_pin_bytes = 1 << 20;
+    DLB_CUDA_CHECK(cudaMallocHost(&g.h_pin, g.h_pin_bytes));
+  }
+  if (!g.sw0) { DLB_CUDA_CHECK(cudaEventCreate(&g.sw0)); DLB_CUDA_CHECK(cudaEventCreate(&g.sw1)); }
+  if (!g.partial.ensure(gram_scratch_bytes(128, 128, g.num_sms))) return DIAGLIB_B200_EALLOC;
+  g.inited = true;
+  g.status = 0;
+  return DIAGLIB_B200_OK;
+}
+
+void diaglib_b200_finalize(void) {
+  if (!g.inited) return;
+  cudaStreamSynchronize(g.st);
+  if (g.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(g.comm);
+  g.comm = nullptr;
+  g.nranks = 1;
+  g.rank = 0;
+  for (DevBuf* b : {&g.partial, &g.smallws, &g.resid_scratch, &g.scal, &g.b_rowptr, &g.b_col, &g.b_val, &g.b_diag,
+                    &g.b_send, &g.b_recv, &g.b_halo})
+    b->release();
+  g.A = CsrDevice();
+  g.inited = false;
+}
+
+void* diaglib_b200_stream(void) { return g.st; }
+int32_t diaglib_b200_last_status(void) { return g.status; }
+const char* diaglib_b200_last_message(void) { return g.msg.c_str(); }
+
+void diaglib_b200_lobpcg_driver(const int32_t* verbose, const int32_t* gen_eig, const int32_t* n,
+                                const int32_t* n_targ, const int32_t* n_max, const int32_t* max_iter,
+                                const double* tol, const double* shift, diaglib_matvec_t matvec,
+                                diaglib_precnd_t precnd, diaglib_matvec_t /*bvec*/, double* eig, double* evec,
+                                int32_t* ok) {
+  *ok = 0;
+  if (!require_init()) return;
+  if (*gen_eig) {
+    g.status = 0;
+    g.fail(DIAGLIB_B200_EARG, "lobpcg_driver: gen_eig=.true. (generalized problem) is out of scope of this library");
+    return;
+  }
+  if (*n_targ > *n_max || *n_max < 1 || *n < 0) {
+    g.status = 0;
+    g.fail(DIAGLIB_B200_EARG, "lobpcg_driver: need 1 <= n_targ <= n_max");
+    return;
+  }
+  g.lobpcg(*verbose != 0, *n, *n_targ, *n_max, *max_iter, *tol, *shift, matvec, precnd, eig, evec, ok);
+}
+
+void diaglib_b200_davidson_driver(const int32_t* verbose, const int32_t* n, const int32_t* n_targ,
+                                  const int32_t* n_max, const int32_t* max_iter, const double* tol,
+                                  const int32_t* max_dav, const double* shift, diaglib_matvec_t matvec,
+                                  diaglib_precnd_t precnd, double* eig, double* evec, int32_t* ok) {
+  *ok = 0;
+  if (!require_init()) return;
+  if (*n_targ > *n_max || *n_max < 1 || *n < 0) {
+    g.status = 0;
+    g.fail(DIAGLIB_B200_EARG, "davidson_driver: need 1 <= n_targ <= n_max");
+    return;
+  }
+  g.davidson(*verbose != 0, *n, *n_targ, *n_max, *max_iter, *tol, *max_dav, *shift, matvec, precnd, eig, evec, ok);
+}
+
+void diaglib_b200_ortho_cd(const int32_t* n, const int32_t* m, double* u, double* growth, int32_t* ok) {
+  *ok = 0;
+  if (!require_init()) return;
+  g.begin_call(*m);
+  g.ensure_small(*m, *m);
+  Staged su(u, sizeof(double) * (size_t)*n * *m);
+  double gr = 1.0;
+  const bool okb = g.ortho_cd(*n, *m, su.dev, *n, gr);
+  su.back();
+  g.sync();
+  g.end_call();
+  *growth = gr;
+  *ok = okb ? 1 : 0;
+}
+
+void diaglib_b200_ortho_vs_x(const int32_t* n, const int32_t* m, const int32_t* k, const double* x, double* u,
+                             const double* /*ax*/, double* /*au*/) {
+  if (!require_init()) return;
+  g.begin_call(*k);
+  g.ensure_small(*k, *m);
+  Staged sx(x, sizeof(double) * (size_t)*n * *m);
+  Staged su(u, sizeof(double) * (size_t)*n * *k);
+  g.ortho_vs_x(*n, *m, *k, sx.dev, *n, su.dev, *n);
+  su.back();
+  g.sync();
+  g.end_call();
+}
+
+void diaglib_b200_ortho(const int32_t* n, const int32_t* m, double* u, double* /*w*/) {
+  if (!require_init()) return;
+  g.begin_call(*m);
+  Staged su(u, sizeof(double) * (size_t)*n * *m);
+  g.ortho_qr(*n, *m, su.dev, *n);
+  su.back();
+  g.sync();
+  g.end_call();
+}
+
+void diaglib_b200_csr_matvec(const int32_t* n, const int32_t* m, const double* x, double* ax) {
+  if (!g.inited || g.A.n != *n) {
+    g.fail(DIAGLIB_B200_EARG, "csr_matvec: no matrix installed for n = %d (diaglib_b200_set_csr)", *n);
+    return;
+  }
+  g.halo_exchange(*m, x, *n);
+  spmm_csr(g.st, g.A, *m, x, *n, g.b_halo.as<double>(), ax, *n, 0.0);
+}
+
+void diaglib_b200_diag_precnd(const int32_t* n, const int32_t* m, const double* shift, const double* x, double* px) {
+  if (!g.inited || g.A.n != *n || !g.A.diag) {
+    g.fail(DIAGLIB_B200_EARG, "diag_precnd: no matrix installed for n = %d (diaglib_b200_set_csr)", *n);
+    return;
+  }
+  diag_precnd(g.st, *n, *m, *shift, g.A.diag, x, *n, px, *n);
+}
+
+int32_t diaglib_b200_set_csr(int64_t n_loc, int64_t n_halo, const int64_t* rowptr, const int32_t* col,
+                             const double* val, const double* diag) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  const int64_t nnz = rowptr[n_loc];
+  if (!g.b_rowptr.ensure((n_loc + 1) * sizeof(int64_t)) || !g.b_col.ensure(std::max<int64_t>(nnz, 1) * sizeof(int32_t)) ||
+      !g.b_val.ensure(std::max<int64_t>(nnz, 1) * sizeof(double)) || !g.b_diag.ensure(std::max<int64_t>(n_loc, 1) * sizeof(double)))
+    return DIAGLIB_B200_EALLOC;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.b_rowptr.p, rowptr, (n_loc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.b_col.p, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.b_val.p, val, nnz * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.b_diag.p, diag, n_loc * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
+  g.A.n = n_loc;
+  g.A.nnz = nnz;
+  g.A.n_halo = n_halo;
+  g.A.rowptr = g.b_rowptr.as<int64_t>();
+  g.A.col = g.b_col.as<int32_t>();
+  g.A.val = g.b_val.as<double>();
+  g.A.diag = g.b_diag.as<double>();
+  g.peer.clear(); g.send_row0.clear(); g.send_cnt.clear(); g.recv_off.clear(); g.recv_cnt.clear();
+  return DIAGLIB_B200_OK;
+}
+
+int32_t diaglib_b200_set_halo(int32_t n_nbr, const int32_t* peer, const int64_t* send_row0, const int64_t* send_cnt,
+                              const int64_t* recv_off, const int64_t* recv_cnt) {
+  g.peer.assign(peer, peer + n_nbr);
+  g.send_row0.assign(send_row0, send_row0 + n_nbr);
+  g.send_cnt.assign(send_cnt, send_cnt + n_nbr);
+  g.recv_off.assign(recv_off, recv_off + n_nbr);
+  g.recv_cnt.assign(recv_cnt, recv_cnt + n_nbr);
+  return DIAGLIB_B200_OK;
+}
+
+int32_t diaglib_b200_comm_unique_id(void* out) {
+  if (!g.nccl.load()) return DIAGLIB_B200_ECOMM;
+  ncclUniqueId id;
+  if (g.nccl.GetUniqueId(&id) != ncclSuccess) return DIAGLIB_B200_ECOMM;
+  std::memcpy(out, &id, sizeof id);
+  return DIAGLIB_B200_OK;
+}
+
+int32_t diaglib_b200_comm_init(int32_t rank, int32_t nranks, const void* uid) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  if (nranks <= 1) { g.rank = 0; g.nranks = 1; return DIAGLIB_B200_OK; }
+  if (!g.nccl.load()) { g.fail(DIAGLIB_B200_ECOMM, "cannot load libnccl.so.2"); return DIAGLIB_B200_ECOMM; }
+  ncclUniqueId id;
+  std::memcpy(&id, uid, sizeof id);
+  if (g.nccl.CommInitRank(&g.comm, nranks, id, rank) != ncclSuccess) {
+    g.fail(DIAGLIB_B200_ECOMM, "ncclCommInitRank failed");
+    return DIAGLIB_B200_ECOMM;
+  }
+  g.rank = rank;
+  g.nranks = nranks;
+  return DIAGLIB_B200_OK;
+}
+int32_t diaglib_b200_comm_rank(void) { return g.rank; }
+int32_t diaglib_b200_comm_size(void) { return g.nranks; }
+
+int32_t diaglib_b200_history_len(void) { return (int32_t)g.hist.it.size(); }
+void diaglib_b200_history_get(int32_t* it, int32_t* n_act, double* eig, double* rms, double* mx, int32_t* done) {
+  const size_t L = g.hist.it.size();
+  for (size_t i = 0; i < L; ++i) { it[i] = g.hist.it[i]; n_act[i] = g.hist.n_act[i]; }
+  for (size_t i = 0; i < L * g.hist.n_max; ++i) {
+    eig[i] = g.hist.eig[i]; rms[i] = g.hist.rms[i]; mx[i] = g.hist.mx[i]; done[i] = g.hist.done[i];
+  }
+}
+void diaglib_b200_timers(double* out8) { for (int i = 0; i < 8; ++i) out8[i] = g.t_acc[i]; }
+void diaglib_b200_stats(int64_t* out8) {
+  out8[0] = g.st_cd_passes; out8[1] = g.st_sweeps; out8[2] = g.st_qr; out8[3] = g.st_shifts; out8[4] = g.st_launches;
+  out8[5] = g_launches; out8[6] = 0; out8[7] = 0;
+}
+
+// ---- kernel-level entry points (include/diaglib_b200_kernels.h) ---------------------------
+void* diaglib_b200_malloc(int64_t bytes) {
+  if (!require_init()) return nullptr;
+  void* p = nullptr;
+  if (cudaMalloc(&p, (size_t)std::max<int64_t>(bytes, 8)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void diaglib_b200_free(void* p) { if (p) cudaFree(p); }
+int32_t diaglib_b200_h2d(void* dev, const void* host, int64_t bytes) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
+  return 0;
+}
+int32_t diaglib_b200_d2h(void* host, const void* dev, int64_t bytes) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, g.st));
+  DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
+  return 0;
+}
+int32_t diaglib_b200_sync(void) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  g.sync();
+  return 0;
+}
+void diaglib_b200_timer_start(void) { if (require_init()) DLB_CUDA_CHECK(cudaEventRecord(g.sw0, g.st)); }
+double diaglib_b200_timer_stop_ms(void) {
+  if (!require_init()) return -1.0;
+  DLB_CUDA_CHECK(cudaEventRecord(g.sw1, g.st));
+  DLB_CUDA_CHECK(cudaEventSynchronize(g.sw1));
+  float ms = 0.f;
+  DLB_CUDA_CHECK(cudaEventElapsedTime(&ms, g.sw0, g.sw1));
+  return ms;
+}
+int32_t diaglib_b200_num_sms(void) { return require_init() ? g.num_sms : 0; }
+
+int32_t diaglib_b200_k_gram(int64_t n, const double* a, int64_t lda, int32_t p, const double* b, int64_t ldb,
+                            int32_t q, double* c, int32_t ldc, int32_t sym_lower) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  gram_tn(g.st, g.num_sms, n, a, lda, p, b, ldb, q, c, ldc, sym_lower != 0, g.partial.as<double>());
+  if (g.nranks > 1) {
+    if (ldc == p) g.allreduce(c, (size_t)p * q);
+    else for (int j = 0; j < q; ++j) g.allreduce(c + (size_t)j * ldc, p);
+  }
+  return 0;
+}
+int32_t diaglib_b200_k_block_mul(int64_t n, const double* v, int64_t ldv, int32_t p, const double* c, int32_t ldc,
+                                 int32_t q, double alpha, double beta, double* y, int64_t ldy) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  block_mul(g.st, n, v, ldv, p, c, ldc, q, alpha, beta, y, ldy);
+  return 0;
+}
+int32_t diaglib_b200_k_residual(int64_t n, int32_t m, const double* ax, int64_t ldax, const double* x, int64_t ldx,
+                                const double* theta_host, const int32_t* active_host, double* r, int64_t ldr,
+                                double* norms_host) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  DevBuf tmp;
+  if (!tmp.ensure((4 * (size_t)m + 16) * sizeof(double)) || !g.resid_scratch.ensure(residual_scratch_bytes(m, g.num_sms)))
+    return DIAGLIB_B200_EALLOC;
+  double* d_theta = tmp.as<double>();
+  double* d_norms = d_theta + m;
+  int* d_act = reinterpret_cast<int*>(d_norms + 2 * m);
+  DLB_CUDA_CHECK(cudaMemcpyAsync(d_theta, theta_host, m * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(d_act, active_host, m * sizeof(int), cudaMemcpyHostToDevice, g.st));
+  residual_norms(g.st, g.num_sms, n, m, ax, ldax, x, ldx, d_theta, d_act, r, ldr, d_norms, g.resid_scratch.as<double>());
+  g.allreduce(d_norms, m, ncclSum);
+  g.allreduce(d_norms + m, m, ncclMax);
+  DLB_CUDA_CHECK(cudaMemcpyAsync(norms_host, d_norms, 2 * m * sizeof(double), cudaMemcpyDeviceToHost, g.st));
+  g.sync();
+  tmp.release();
+  return 0;
+}
+int32_t diaglib_b200_k_sym_eig(int32_t k, double* a_host, int32_t lda, int32_t upper, double* w_host) {
+  if (!require_init()) return -1000;
+  DevBuf buf;
+  const size_t ew = eig_work_doubles(k);
+  if (!buf.ensure(((size_t)lda * k + k + ew + 8) * sizeof(double))) return -1001;
+  double* a = buf.as<double>();
+  double* w = a + (size_t)lda * k;
+  double* work = w + k;
+  EigStatus* es = reinterpret_cast<EigStatus*>(work + ew);
+  DLB_CUDA_CHECK(cudaMemcpyAsync(a, a_host, (size_t)lda * k * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  sym_eig(g.st, k, a, lda, upper != 0, w, work, es);
+  EigStatus h;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(a_host, a, (size_t)lda * k * sizeof(double), cudaMemcpyDeviceToHost, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(w_host, w, k * sizeof(double), cudaMemcpyDeviceToHost, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(&h, es, sizeof h, cudaMemcpyDeviceToHost, g.st));
+  g.sync();
+  buf.release();
+  return h.converged ? h.sweeps : -h.sweeps;
+}
+int32_t diaglib_b200_k_chol_inv(int32_t m, const double* metric_host, double* t_host, double* out5) {
+  if (!require_init()) return -1000;
+  g.ensure_small(m, m);
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.d_metric, metric_host, (size_t)m * m * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  chol_inv(g.st, m, g.d_metric, m, g.d_T, g.d_cholwork, g.d_cholst);
+  CholStatus cs;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(t_host, g.d_T, (size_t)m * m * sizeof(double), cudaMemcpyDeviceToHost, g.st));
+  g.read_back(&cs, g.d_cholst, sizeof cs);
+  out5[0] = cs.l_norm; out5[1] = cs.linv_norm; out5[2] = cs.shift_used; out5[3] = cs.info_first; out5[4] = cs.n_shifts;
+  return cs.hard_fail;
+}
+int32_t diaglib_b200_k_get_coeffs(int32_t len_a, int32_t len_u, int32_t n_max, int32_t n_act, const double* a_red_host,
+                                  double* u_p_host, int32_t* out4) {
+  if (!require_init()) return -1000;
+  DevBuf buf;
+  const size_t cw = coeffs_work_doubles(len_u, n_max, n_act);
+  if (!buf.ensure(((size_t)len_a * len_a + (size_t)len_u * n_act + cw + 8) * sizeof(double))) return -1001;
+  double* a = buf.as<double>();
+  double* up = a + (size_t)len_a * len_a;
+  double* work = up + (size_t)len_u * n_act;
+  CoeffStatus* cs = reinterpret_cast<CoeffStatus*>(work + cw);
+  DLB_CUDA_CHECK(cudaMemcpyAsync(a, a_red_host, (size_t)len_a * len_a * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  get_coeffs(g.st, len_a, len_u, n_max, n_act, a, up, work, cs);
+  CoeffStatus h;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(u_p_host, up, (size_t)len_u * n_act * sizeof(double), cudaMemcpyDeviceToHost, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(&h, cs, sizeof h, cudaMemcpyDeviceToHost, g.st));
+  g.sync();
+  buf.release();
+  out4[0] = h.sweeps; out4[1] = h.cd_passes; out4[2] = h.fail; out4[3] = h.qr;
+  return h.fail;
+}
+
+}  // extern "C"

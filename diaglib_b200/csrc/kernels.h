@@ -1,0 +1,93 @@
+// Internal C++ interface of the sm_100a kernels (device pointers, explicit stream).
+// Column-major everywhere, leading dimension in elements (Fortran convention of the
+// reference: explicit-shape x(n,*) blocks, diaglib.f90:221-228).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace dlb {
+
+// number of kernels launched by this library since load (bench.py reports it as gpu_launches)
+extern int64_t g_launches;
+
+// ---- dense.cu -------------------------------------------------------------------------
+// C(p x q, ldc) = A(n x p, lda)^T * B(n x q, ldb).  Replaces dgemm('t','n',p,q,n,...) at
+// diaglib.f90:313,403,1691,3256,3543,3762.  If sym_lower only tiles on/below the diagonal
+// are computed and the result is mirrored (callers consume one triangle: dsyev 'l' 406,
+// dpotrf 'l' 3261).  `partial` is scratch of at least gram_scratch_bytes(p,q,num_sms).
+size_t gram_scratch_bytes(int p, int q, int num_sms);
+void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t lda, int p, const double* B,
+             int64_t ldb, int q, double* C, int ldc, bool sym_lower, double* partial);
+
+// Y(n x q, ldy) = alpha * V(n x p, ldv) * C(p x q, ldc) + beta * Y.  Y may alias V when the
+// product is row-local (q <= 128).  Replaces dgemm('n','n',n,q,p,...) at
+// diaglib.f90:322,324,420,421,495,497,1717,1721,3544 and dtrmm('r','l','t','n') at 3327
+// (with C = L^-T stored as a full matrix with an explicit zero triangle).
+void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc, int q,
+               double alpha, double beta, double* Y, int64_t ldy);
+
+// U <- U * T, T upper triangular m x m (ld m), in place (dtrmm at diaglib.f90:3327).
+void block_trmm_inplace(cudaStream_t st, int64_t n, double* U, int64_t ldu, int m, const double* T);
+
+// ---- sparse.cu ------------------------------------------------------------------------
+struct CsrDevice {
+  int64_t n = 0;        // local rows
+  int64_t nnz = 0;
+  int64_t n_halo = 0;   // columns >= n index the halo block
+  int64_t* rowptr = nullptr;
+  int32_t* col = nullptr;
+  double* val = nullptr;
+  double* diag = nullptr;
+};
+// AX(n x m) = A * X (+ shift * X).  x_halo holds the remote rows (n_halo x m, ld n_halo).
+// Built-in conforming matvec(n,m,x,ax) (contract diaglib.f90:66; toy impl main.f90:72-90).
+void spmm_csr(cudaStream_t st, const CsrDevice& A, int m, const double* x, int64_t ldx, const double* x_halo,
+              double* ax, int64_t ldax, double shift);
+// px = x / (d + fac) where |d + fac| > 1e-5, else x  (main.f90:146-171).
+void diag_precnd(cudaStream_t st, int64_t n, int m, double fac, const double* diag, const double* x, int64_t ldx,
+                 double* px, int64_t ldpx);
+// r(:,j) = ax(:,j) - theta[j] * x(:,j) for the columns with active[j] != 0 (others: r = ax),
+// plus per-column sum of squares and max |r| of the active columns
+// (dcopy 428 + daxpy 438 + dnrm2 440 + maxval 441; Davidson 1729-1731).
+// norms_out[2*j] = sum r^2 (local rows), norms_out[2*j+1] = max |r|.  theta/active are device arrays.
+void residual_norms(cudaStream_t st, int num_sms, int64_t n, int m, const double* ax, int64_t ldax, const double* x,
+                    int64_t ldx, const double* theta, const int* active, double* r, int64_t ldr,
+                    double* norms_out, double* scratch);
+size_t residual_scratch_bytes(int m, int num_sms);
+// y += a * x on an n x m block (daxpy 312,397)
+void block_axpy(cudaStream_t st, int64_t n, int m, double a, const double* x, int64_t ldx, double* y, int64_t ldy);
+// y = x on an n x m block (dcopy)
+void block_copy(cudaStream_t st, int64_t n, int m, const double* x, int64_t ldx, double* y, int64_t ldy);
+// gathers rows [row0,row0+cnt) of an n x m block into a dense cnt x m buffer (halo packing)
+void pack_rows(cudaStream_t st, int64_t row0, int64_t cnt, int m, const double* x, int64_t ldx, double* out);
+
+// ---- small.cu (single-CTA dense kernels, replicated per rank) --------------------------
+struct CholStatus {      // written by chol_inv, read back by the host control loop
+  double l_norm, linv_norm, shift_used, unorm;
+  int info_first;        // dpotrf info of the un-shifted attempt (0 = fine)
+  int n_shifts;          // level-shift retries used (3265-3295)
+  int hard_fail;         // shift loop exhausted (3276-3284)
+  int pad;
+};
+// metric (m x m, ldm) -> Linv_t_full (m x m, ld m): the matrix T = L^-T (upper triangular,
+// explicit zeros below) such that U_ortho = U * T.  Follows dpotrf('l') 3261, the shift loop
+// 3265-3295, dtrtri('l','n') 3310 and norm_est 3314-3315.
+// `work` must hold 2*m*m doubles.
+void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, double* work, CholStatus* status_dev);
+
+struct EigStatus { int sweeps; int converged; };
+// Symmetric eigensolver replacing dsyev('v',uplo) (315,406,1708): a (k x k, lda) is
+// overwritten by the eigenvectors (ascending eigenvalues in w).  Parallel cyclic Jacobi.
+// `work` must hold 2*kp*kp + 4*kp doubles with kp = k rounded up to even.
+size_t eig_work_doubles(int k);
+void sym_eig(cudaStream_t st, int k, double* a, int lda, bool upper, double* w, double* work, EigStatus* status_dev);
+
+// get_coeffs (3686-3732) entirely on device: a_red (len_a x len_a, eigenvectors in the
+// first len_u rows/cols) -> u_p (len_u x n_act, ld len_u).  u_x is read in place from a_red.
+struct CoeffStatus { int sweeps; int cd_passes; int fail; int qr; };
+size_t coeffs_work_doubles(int len_u, int n_max, int n_act);
+void get_coeffs(cudaStream_t st, int len_a, int len_u, int n_max, int n_act, const double* a_red, double* u_p,
+                double* work, CoeffStatus* status_dev);
+
+}  // namespace dlb

@@ -1,0 +1,467 @@
+// Single-CTA dense kernels for the k x k reduced problems of the diaglib hot path.  They are
+// launched with one CTA and replicated on every rank: identical (all-reduced) input and
+// deterministic code give bit-identical results everywhere, so no broadcast is needed.
+//
+//   chol_inv   : dpotrf('l') + level-shift retries + dtrtri('l','n') + norm_est  (ortho_cd,
+//                diaglib.f90:3261-3316)
+//   sym_eig    : dsyev('v',uplo) replacement (diaglib.f90:315,406,1708), parallel cyclic Jacobi
+//   get_coeffs : diaglib.f90:3686-3732 including its ortho_vs_x / ortho_cd on the small
+//                coefficient blocks, all inside one kernel
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cfloat>
+
+namespace dlb {
+namespace {
+
+constexpr int SM_THREADS = 1024;
+constexpr double EPS = DBL_EPSILON;       // epsilon(one)
+constexpr double TOL_ORTHO = 2.0 * EPS;   // diaglib.f90:151
+
+__device__ double cta_sum(double v, double* s_red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  const int nw = (blockDim.x + 31) >> 5;
+  for (int w = 0; w < nw; ++w) t += s_red[w];
+  return t;
+}
+__device__ double cta_max(double v, double* s_red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  const int nw = (blockDim.x + 31) >> 5;
+  for (int w = 0; w < nw; ++w) t = fmax(t, s_red[w]);
+  return t;
+}
+
+// norm_est, diaglib.f90:3447-3479 : max |diag| + Frobenius norm of the strict lower part
+__device__ double cta_norm_est(int m, const double* a, int ld, double* s_red) {
+  double dmax = 0.0, od = 0.0;
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e % m, j = e / m;
+    const double v = a[i + (size_t)j * ld];
+    if (i == j) dmax = fmax(dmax, fabs(v));
+    else if (i > j) od = fma(v, v, od);
+  }
+  const double d = cta_max(dmax, s_red);
+  const double o = cta_sum(od, s_red);
+  return d + sqrt(o);
+}
+
+// In-place lower Cholesky of the lower triangle of L (m x m, ld).  Returns LAPACK-style info
+// (0 ok, j+1 = first non-positive pivot).  Uniform across the CTA.
+__device__ int cta_potrf_lower(int m, double* L, int ld) {
+  for (int j = 0; j < m; ++j) {
+    __syncthreads();
+    const double ajj = L[j + (size_t)j * ld];
+    if (!(ajj > 0.0)) return j + 1;  // also catches NaN, like dpotrf's disnan test
+    const double s = sqrt(ajj);
+    __syncthreads();
+    for (int i = j + threadIdx.x; i < m; i += blockDim.x)
+      L[i + (size_t)j * ld] = (i == j) ? s : L[i + (size_t)j * ld] / s;
+    __syncthreads();
+    const int rem = m - j - 1;
+    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
+      const int k = j + 1 + e / rem, i = j + 1 + e % rem;
+      if (i >= k) L[i + (size_t)k * ld] = fma(-L[i + (size_t)j * ld], L[k + (size_t)j * ld], L[i + (size_t)k * ld]);
+    }
+  }
+  __syncthreads();
+  return 0;
+}
+
+// Li = inverse of the lower triangular L (one thread per column, forward substitution).
+// Li is written in full (zeros above the diagonal).
+__device__ void cta_trtri_lower(int m, const double* L, int ldl, double* Li, int ldi) {
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    for (int i = 0; i < j; ++i) Li[i + (size_t)j * ldi] = 0.0;
+    Li[j + (size_t)j * ldi] = 1.0 / L[j + (size_t)j * ldl];
+    for (int i = j + 1; i < m; ++i) {
+      double s = 0.0;
+      for (int k = j; k < i; ++k) s = fma(L[i + (size_t)k * ldl], Li[k + (size_t)j * ldi], s);
+      Li[i + (size_t)j * ldi] = -s / L[i + (size_t)i * ldl];
+    }
+  }
+  __syncthreads();
+}
+
+// The factor-and-invert step of one ortho_cd pass (diaglib.f90:3257-3316).
+//   G (m x m, ldg) : metric, lower triangle used
+//   L, Li          : m x m scratch (ld m)
+//   T (m x m, ld m): output L^-T, upper triangular with explicit zeros
+// unorm_sq = ||U||_F^2; the reference calls dnrm2(n*m,u,1) (3268), which equals
+// sqrt(trace(G)) up to rounding, and the trace is already here.
+__device__ void cta_chol_inv(int m, const double* G, int ldg, double* L, double* Li, double* T, CholStatus* st,
+                             double* s_red) {
+  double tr = 0.0;
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e % m, j = e / m;
+    const double v = G[i + (size_t)j * ldg];
+    L[i + (size_t)j * m] = v;
+    if (i == j) tr += v;
+  }
+  const double unorm = sqrt(fmax(cta_sum(tr, s_red), 0.0));
+  int info = cta_potrf_lower(m, L, m);
+  const int info_first = info;
+  int n_shifts = 0, hard_fail = 0;
+  double shift = 0.0;
+  if (info != 0) {
+    double alpha = 100.0;
+    while (info != 0) {
+      if (n_shifts >= 10) { hard_fail = 1; break; }  // 3276-3284
+      ++n_shifts;
+      shift = fmax(EPS * alpha * unorm, TOL_ORTHO);   // 3287
+      __syncthreads();
+      for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+        const int i = e % m, j = e / m;
+        L[i + (size_t)j * m] = G[i + (size_t)j * ldg] + (i == j ? shift : 0.0);
+      }
+      info = cta_potrf_lower(m, L, m);
+      alpha *= 10.0;
+    }
+  }
+  double l_norm = 0.0, linv_norm = 0.0;
+  if (!hard_fail) {
+    cta_trtri_lower(m, L, m, Li, m);
+    l_norm = cta_norm_est(m, L, m, s_red);
+    linv_norm = cta_norm_est(m, Li, m, s_red);
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+      const int i = e % m, j = e / m;
+      T[i + (size_t)j * m] = (i <= j) ? Li[j + (size_t)i * m] : 0.0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->l_norm = l_norm;
+    st->linv_norm = linv_norm;
+    st->shift_used = shift;
+    st->unorm = unorm;
+    st->info_first = info_first;
+    st->n_shifts = n_shifts;
+    st->hard_fail = hard_fail;
+    st->pad = 0;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SM_THREADS)
+chol_inv_kernel(int m, const double* G, int ldg, double* T, double* work, CholStatus* st) {
+  __shared__ double s_red[32];
+  extern __shared__ __align__(16) double dyn[];
+  double* L = work;
+  double* Li = work + (size_t)m * m;
+  if (2 * m * m * (int)sizeof(double) <= 96 * 1024) {  // keep the factors on chip when small
+    L = dyn;
+    Li = dyn + (size_t)m * m;
+  }
+  cta_chol_inv(m, G, ldg, L, Li, T, st, s_red);
+}
+
+// ---------------------------------------------------------------------------------------
+// Symmetric eigensolver: parallel-order cyclic Jacobi (two-sided), all in one CTA.
+// A and Z live in shared memory when 2*kp*lds doubles fit, else in `work` (L2 resident).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SM_THREADS)
+sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, int use_smem, EigStatus* st) {
+  extern __shared__ __align__(16) double dyn[];
+  __shared__ int s_flag;
+  const int kp = (k + 1) & ~1;
+  const int lds = kp | 1;  // odd stride: row accesses are bank-conflict free
+  const int half = kp / 2;
+  double* A = use_smem ? dyn : work;
+  double* Z = A + (size_t)kp * lds;
+  double* rc = Z + (size_t)kp * lds;   // half cosines
+  double* rs = rc + half;              // half sines
+  int* rp = reinterpret_cast<int*>(rs + half);  // 2*half ints (p, q)
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (int e = tid; e < kp * kp; e += nt) {
+    const int i = e % kp, j = e / kp;
+    double v = 0.0;
+    if (i < k && j < k) {
+      const int lo = i < j ? i : j, hi = i < j ? j : i;
+      v = upper ? a[lo + (size_t)hi * lda] : a[hi + (size_t)lo * lda];
+    }
+    A[i + (size_t)j * lds] = v;
+    Z[i + (size_t)j * lds] = (i == j) ? 1.0 : 0.0;
+  }
+  if (tid == 0) s_flag = 0;
+  __syncthreads();
+
+  int sweeps = 0, converged = 0;
+  const int max_sweeps = 40;
+  while (sweeps < max_sweeps) {
+    for (int r = 0; r < kp - 1; ++r) {
+      // phase 1: rotation angles for the kp/2 disjoint pairs of this round
+      if (tid < half) {
+        int p, q;
+        if (tid == 0) { p = kp - 1; q = r; }
+        else { p = (r + tid) % (kp - 1); q = (r - tid + (kp - 1)) % (kp - 1); }
+        if (p > q) { const int t = p; p = q; q = t; }
+        const double app = A[p + (size_t)p * lds], aqq = A[q + (size_t)q * lds], apq = A[p + (size_t)q * lds];
+        double c = 1.0, s = 0.0;
+        if (fabs(apq) > EPS * sqrt(fabs(app) * fabs(aqq)) && fabs(apq) > 1e-300) {
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
+          s = t * c;
+          s_flag = 1;
+        }
+        rc[tid] = c; rs[tid] = s; rp[2 * tid] = p; rp[2 * tid + 1] = q;
+      }
+      __syncthreads();
+      // phase 2: column rotations  A <- A J,  Z <- Z J
+      for (int e = tid; e < half * kp; e += nt) {
+        const int pr = e / kp, i = e % kp;
+        const double s = rs[pr];
+        if (s != 0.0) {
+          const double c = rc[pr];
+          const int p = rp[2 * pr], q = rp[2 * pr + 1];
+          const double ap = A[i + (size_t)p * lds], aq = A[i + (size_t)q * lds];
+          A[i + (size_t)p * lds] = c * ap - s * aq;
+          A[i + (size_t)q * lds] = s * ap + c * aq;
+          const double zp = Z[i + (size_t)p * lds], zq = Z[i + (size_t)q * lds];
+          Z[i + (size_t)p * lds] = c * zp - s * zq;
+          Z[i + (size_t)q * lds] = s * zp + c * zq;
+        }
+      }
+      __syncthreads();
+      // phase 3: row rotations  A <- J^T A ; the rotated pivot is set to exactly zero
+      for (int e = tid; e < half * kp; e += nt) {
+        const int pr = e / kp, j = e % kp;
+        const double s = rs[pr];
+        if (s != 0.0) {
+          const double c = rc[pr];
+          const int p = rp[2 * pr], q = rp[2 * pr + 1];
+          const double ap = A[p + (size_t)j * lds], aq = A[q + (size_t)j * lds];
+          double np_ = c * ap - s * aq, nq_ = s * ap + c * aq;
+          if (j == q) np_ = 0.0;
+          if (j == p) nq_ = 0.0;
+          A[p + (size_t)j * lds] = np_;
+          A[q + (size_t)j * lds] = nq_;
+        }
+      }
+      __syncthreads();
+    }
+    ++sweeps;
+    const int any = s_flag;
+    __syncthreads();
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    if (!any) { converged = 1; break; }
+  }
+
+  // ascending sort by rank, largest-magnitude component made positive, write back into a
+  for (int i = tid; i < k; i += nt) {
+    const double di = A[i + (size_t)i * lds];
+    int rank = 0;
+    for (int j = 0; j < k; ++j) {
+      const double dj = A[j + (size_t)j * lds];
+      rank += (dj < di || (dj == di && j < i)) ? 1 : 0;
+    }
+    double best = 0.0, sign = 1.0;
+    for (int rr = 0; rr < k; ++rr) {
+      const double v = Z[rr + (size_t)i * lds];
+      if (fabs(v) > best) { best = fabs(v); sign = v < 0.0 ? -1.0 : 1.0; }
+    }
+    w[rank] = di;
+    for (int rr = 0; rr < k; ++rr) a[rr + (size_t)rank * lda] = sign * Z[rr + (size_t)i * lds];
+  }
+  if (tid == 0) { st->sweeps = sweeps; st->converged = converged; }
+}
+
+// ---------------------------------------------------------------------------------------
+// get_coeffs (diaglib.f90:3686-3732) in one CTA: u_p = u_x(:,active) - e_i, then
+// ortho_vs_x(len_u, n_max, n_act, u_x, u_p) (3481-3574) with ortho_cd (3185-3341) inside.
+// ---------------------------------------------------------------------------------------
+// G(m x m) = U^T U for a small n x m block
+__device__ void cta_gram(int n, int m, const double* U, int ldu, double* G) {
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e % m, j = e / m;
+    if (i < j) continue;  // lower triangle + mirror
+    double s = 0.0;
+    const double* ui = U + (size_t)i * ldu;
+    const double* uj = U + (size_t)j * ldu;
+    for (int r = 0; r < n; ++r) s = fma(ui[r], uj[r], s);
+    G[i + (size_t)j * m] = s;
+    G[j + (size_t)i * m] = s;
+  }
+  __syncthreads();
+}
+
+// returns ok (uniform); growth accumulated as in 3323
+__device__ bool cta_ortho_cd(int n, int m, double* U, int ldu, double* G, double* L, double* Li, double* T,
+                             double* tmp, CholStatus* st, double* s_red, double& growth, int* passes) {
+  growth = 1.0;
+  for (int it = 1;; ++it) {
+    if (it > 10) return false;  // 3248-3254
+    if (threadIdx.x == 0) ++(*passes);
+    cta_gram(n, m, U, ldu, G);
+    cta_chol_inv(m, G, m, L, Li, T, st, s_red);
+    if (st->hard_fail) return false;
+    const double l_norm = st->l_norm, linv_norm = st->linv_norm;
+    const double rcond = l_norm * linv_norm;
+    growth *= linv_norm;
+    // U <- U T  (T upper triangular): out of place into tmp, then copy back
+    for (int e = threadIdx.x; e < n * m; e += blockDim.x) {
+      const int r = e % n, j = e / n;
+      double s = 0.0;
+      for (int k = 0; k <= j; ++k) s = fma(U[r + (size_t)k * ldu], T[k + (size_t)j * m], s);
+      tmp[e] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * m; e += blockDim.x) U[(e % n) + (size_t)(e / n) * ldu] = tmp[e];
+    __syncthreads();
+    if (EPS * rcond * rcond < TOL_ORTHO) return true;  // 3331-3332
+  }
+}
+
+// modified Gram-Schmidt with one re-orthogonalisation: device stand-in for the Householder
+// fallback `ortho` (3052-3092) on the small coefficient blocks.  Cold path.
+__device__ void cta_mgs2(int n, int m, double* U, int ldu, double* s_red) {
+  for (int j = 0; j < m; ++j) {
+    double* uj = U + (size_t)j * ldu;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int i = 0; i < j; ++i) {
+        const double* ui = U + (size_t)i * ldu;
+        double s = 0.0;
+        for (int r = threadIdx.x; r < n; r += blockDim.x) s = fma(ui[r], uj[r], s);
+        const double d = cta_sum(s, s_red);
+        for (int r = threadIdx.x; r < n; r += blockDim.x) uj[r] = fma(-d, ui[r], uj[r]);
+        __syncthreads();
+      }
+    double s = 0.0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) s = fma(uj[r], uj[r], s);
+    const double nrm = sqrt(cta_sum(s, s_red));
+    for (int r = threadIdx.x; r < n; r += blockDim.x) uj[r] = uj[r] / nrm;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SM_THREADS)
+get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_red, double* u_p, double* work,
+                  CoeffStatus* cst) {
+  __shared__ double s_red[32];
+  __shared__ CholStatus s_chol;
+  __shared__ int s_passes;
+  const int off_x = n_max - n_act;
+  const double* u_x = a_red;  // len_u x n_max, ld len_a (eigenvectors left there by sym_eig)
+  double* G = work;                                 // n_act^2
+  double* L = G + (size_t)n_act * n_act;            // n_act^2
+  double* Li = L + (size_t)n_act * n_act;           // n_act^2
+  double* T = Li + (size_t)n_act * n_act;           // n_act^2
+  double* xu = T + (size_t)n_act * n_act;           // n_max x n_act
+  double* tmp = xu + (size_t)n_max * n_act;         // len_u x n_act
+  if (threadIdx.x == 0) s_passes = 0;
+  // u_p = u_x(:,ind_x:n_max) with 1 removed from the x coefficient (3716-3722)
+  for (int e = threadIdx.x; e < len_u * n_act; e += blockDim.x) {
+    const int r = e % len_u, j = e / len_u;
+    double v = u_x[r + (size_t)(off_x + j) * len_a];
+    if (r == off_x + j) v -= 1.0;
+    u_p[r + (size_t)j * len_u] = v;
+  }
+  __syncthreads();
+  // ortho_vs_x(len_u, n_max, n_act, u_x, u_p)
+  double growth = 1.0;
+  int sweeps = 0, fail = 0, qr = 0;
+  bool ok = cta_ortho_cd(len_u, n_act, u_p, len_u, G, L, Li, T, tmp, &s_chol, s_red, growth, &s_passes);
+  if (!ok) { cta_mgs2(len_u, n_act, u_p, len_u, s_red); ++qr; }
+  bool done = false;
+  while (!done) {
+    ++sweeps;
+    // xu = u_x^T u_p ; u_p -= u_x xu   (3543-3544)
+    for (int e = threadIdx.x; e < n_max * n_act; e += blockDim.x) {
+      const int i = e % n_max, j = e / n_max;
+      const double* xi = u_x + (size_t)i * len_a;
+      const double* uj = u_p + (size_t)j * len_u;
+      double s = 0.0;
+      for (int r = 0; r < len_u; ++r) s = fma(xi[r], uj[r], s);
+      xu[e] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < len_u * n_act; e += blockDim.x) {
+      const int r = e % len_u, j = e / len_u;
+      double s = u_p[r + (size_t)j * len_u];
+      for (int i = 0; i < n_max; ++i) s = fma(-u_x[r + (size_t)i * len_a], xu[i + (size_t)j * n_max], s);
+      tmp[e] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < len_u * n_act; e += blockDim.x) u_p[e] = tmp[e];
+    __syncthreads();
+    ok = cta_ortho_cd(len_u, n_act, u_p, len_u, G, L, Li, T, tmp, &s_chol, s_red, growth, &s_passes);
+    double xu_norm;
+    if (!ok) {
+      cta_mgs2(len_u, n_act, u_p, len_u, s_red);
+      ++qr;
+      double s = 0.0;
+      for (int e = threadIdx.x; e < n_max * n_act; e += blockDim.x) {
+        const int i = e % n_max, j = e / n_max;
+        const double* xi = u_x + (size_t)i * len_a;
+        const double* uj = u_p + (size_t)j * len_u;
+        double d = 0.0;
+        for (int r = 0; r < len_u; ++r) d = fma(xi[r], uj[r], d);
+        s = fma(d, d, s);
+      }
+      xu_norm = sqrt(cta_sum(s, s_red));
+    } else {
+      xu_norm = growth * EPS;  // 3562
+    }
+    done = xu_norm < TOL_ORTHO;
+    if (sweeps > 10 && !done) { fail = 1; break; }  // 3568
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { cst->sweeps = sweeps; cst->cd_passes = s_passes; cst->fail = fail; cst->qr = qr; }
+}
+
+}  // namespace
+
+void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, double* work, CholStatus* status_dev) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  const size_t need = 2 * (size_t)m * m * sizeof(double);
+  const size_t smem = need <= 96 * 1024 ? need : 0;
+  const int threads = m <= 48 ? 256 : SM_THREADS;
+  chol_inv_kernel<<<1, threads, smem, st>>>(m, metric, ldm, T, work, status_dev);
+  ++g_launches;
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+
+size_t eig_work_doubles(int k) {
+  const int kp = (k + 1) & ~1, lds = kp | 1;
+  return 2 * (size_t)kp * lds + 2 * (size_t)kp + 8;
+}
+
+void sym_eig(cudaStream_t st, int k, double* a, int lda, bool upper, double* w, double* work, EigStatus* status_dev) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    attr_set = true;
+  }
+  const size_t need = eig_work_doubles(k) * sizeof(double);
+  const int use_smem = need <= 224 * 1024 ? 1 : 0;
+  sym_eig_kernel<<<1, SM_THREADS, use_smem ? need : 0, st>>>(k, a, lda, upper ? 1 : 0, w, work, use_smem, status_dev);
+  ++g_launches;
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+
+size_t coeffs_work_doubles(int len_u, int n_max, int n_act) {
+  return 4 * (size_t)n_act * n_act + (size_t)n_max * n_act + (size_t)len_u * n_act + 8;
+}
+
+void get_coeffs(cudaStream_t st, int len_a, int len_u, int n_max, int n_act, const double* a_red, double* u_p,
+                double* work, CoeffStatus* status_dev) {
+  get_coeffs_kernel<<<1, SM_THREADS, 0, st>>>(len_a, len_u, n_max, n_act, a_red, u_p, work, status_dev);
+  ++g_launches;
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace dlb

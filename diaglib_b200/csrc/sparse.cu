@@ -1,0 +1,200 @@
+// HBM-bound streaming kernels of the diaglib hot path: CSR block matvec (SpMM), diagonal
+// shift-and-invert preconditioner, fused residual + norms, block axpy/copy, halo packing.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+
+namespace dlb {
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// SpMM, one thread per row, JB columns of the block accumulated in registers per sweep over
+// the row.  Consecutive threads own consecutive rows, so for banded/stencil matrices every
+// gather x[col + j*ld] is a shifted coalesced access and each row sum is formed in CSR
+// order with FMAs (the same order as the CPU oracle: results are bit-identical).
+// Columns >= n address the halo block (rows owned by neighbouring ranks).
+// ---------------------------------------------------------------------------------------
+template <int JB>
+__global__ void __launch_bounds__(256)
+spmm_csr_kernel(int64_t n, int64_t n_halo, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                const double* __restrict__ val, int m, const double* __restrict__ x, int64_t ldx,
+                const double* __restrict__ xh, double* __restrict__ ax, int64_t ldax, double shift) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const int64_t b = rowptr[row], e = rowptr[row + 1];
+  for (int j0 = 0; j0 < m; j0 += JB) {
+    double acc[JB];
+#pragma unroll
+    for (int jj = 0; jj < JB; ++jj) acc[jj] = 0.0;
+    if (j0 + JB <= m) {
+      for (int64_t k = b; k < e; ++k) {
+        const int64_t c = col[k];
+        const double v = val[k];
+        const double* xp;
+        int64_t ld;
+        if (c < n) { xp = x + c + (int64_t)j0 * ldx; ld = ldx; }
+        else { xp = xh + (c - n) + (int64_t)j0 * n_halo; ld = n_halo; }
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) acc[jj] = fma(v, xp[(int64_t)jj * ld], acc[jj]);
+      }
+#pragma unroll
+      for (int jj = 0; jj < JB; ++jj) {
+        double s = acc[jj];
+        if (shift != 0.0) s = fma(shift, x[row + (int64_t)(j0 + jj) * ldx], s);
+        ax[row + (int64_t)(j0 + jj) * ldax] = s;
+      }
+    } else {
+      const int jn = m - j0;
+      for (int64_t k = b; k < e; ++k) {
+        const int64_t c = col[k];
+        const double v = val[k];
+        const double* xp;
+        int64_t ld;
+        if (c < n) { xp = x + c + (int64_t)j0 * ldx; ld = ldx; }
+        else { xp = xh + (c - n) + (int64_t)j0 * n_halo; ld = n_halo; }
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj)
+          if (jj < jn) acc[jj] = fma(v, xp[(int64_t)jj * ld], acc[jj]);
+      }
+#pragma unroll
+      for (int jj = 0; jj < JB; ++jj)
+        if (jj < jn) {
+          double s = acc[jj];
+          if (shift != 0.0) s = fma(shift, x[row + (int64_t)(j0 + jj) * ldx], s);
+          ax[row + (int64_t)(j0 + jj) * ldax] = s;
+        }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+diag_precnd_kernel(int64_t n, int m, double fac, const double* __restrict__ diag, const double* __restrict__ x,
+                   int64_t ldx, double* __restrict__ px, int64_t ldpx) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const double d = diag[row] + fac;
+  const bool use = fabs(d) > 1.0e-5;
+  for (int j = 0; j < m; ++j) {
+    const double v = x[row + (int64_t)j * ldx];
+    px[row + (int64_t)j * ldpx] = use ? v / d : v;
+  }
+}
+
+// one CTA per (row slice, column): grid = (slices, m)
+constexpr int RN_THREADS = 256;
+__global__ void __launch_bounds__(RN_THREADS)
+residual_kernel(int64_t n, int m, const double* ax, int64_t ldax, const double* __restrict__ x, int64_t ldx,
+                const double* __restrict__ theta, const int* __restrict__ active, double* r, int64_t ldr,
+                double* __restrict__ scratch) {
+  const int j = blockIdx.y;
+  const int nsl = gridDim.x;
+  const int64_t per = (n + nsl - 1) / nsl;
+  const int64_t r0 = (int64_t)blockIdx.x * per, r1 = r0 + per < n ? r0 + per : n;
+  const bool act = active[j] != 0;
+  const double th = theta[j];
+  const double* axj = ax + (int64_t)j * ldax;
+  const double* xj = x + (int64_t)j * ldx;
+  double* rj = r + (int64_t)j * ldr;
+  double ss = 0.0, mx = 0.0;
+  if (act) {
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += RN_THREADS) {
+      const double v = fma(-th, xj[i], axj[i]);
+      rj[i] = v;
+      ss = fma(v, v, ss);
+      mx = fmax(mx, fabs(v));
+    }
+  } else if (axj != rj) {
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += RN_THREADS) rj[i] = axj[i];
+  }
+  __shared__ double s_ss[RN_THREADS / 32], s_mx[RN_THREADS / 32];
+  ss = warp_sum(ss);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) { s_ss[threadIdx.x >> 5] = ss; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < RN_THREADS / 32; ++w) { a += s_ss[w]; b = fmax(b, s_mx[w]); }
+    scratch[(size_t)blockIdx.x * 2 * m + j] = a;
+    scratch[(size_t)blockIdx.x * 2 * m + m + j] = b;
+  }
+}
+__global__ void residual_final_kernel(int nsl, int m, const double* __restrict__ scratch, double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  double a = 0.0, b = 0.0;
+  for (int s = 0; s < nsl; ++s) {
+    a += scratch[(size_t)s * 2 * m + j];
+    b = fmax(b, scratch[(size_t)s * 2 * m + m + j]);
+  }
+  out[j] = a;
+  out[m + j] = b;
+}
+
+__global__ void __launch_bounds__(256)
+axpy_kernel(int64_t n, int m, double a, const double* __restrict__ x, int64_t ldx, double* __restrict__ y,
+            int64_t ldy) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  for (int j = 0; j < m; ++j) y[row + (int64_t)j * ldy] = fma(a, x[row + (int64_t)j * ldx], y[row + (int64_t)j * ldy]);
+}
+
+}  // namespace
+
+void spmm_csr(cudaStream_t st, const CsrDevice& A, int m, const double* x, int64_t ldx, const double* x_halo,
+              double* ax, int64_t ldax, double shift) {
+  if (A.n <= 0 || m <= 0) return;
+  const unsigned grid = (unsigned)((A.n + 255) / 256);
+  spmm_csr_kernel<8><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, m, x, ldx, x_halo, ax, ldax, shift);
+  ++g_launches;
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+
+void diag_precnd(cudaStream_t st, int64_t n, int m, double fac, const double* diag, const double* x, int64_t ldx,
+                 double* px, int64_t ldpx) {
+  if (n <= 0 || m <= 0) return;
+  diag_precnd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, m, fac, diag, x, ldx, px, ldpx);
+  ++g_launches;
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+
+static int residual_slices(int m, int num_sms) { return std::max(1, (num_sms * 8 + m - 1) / m); }
+size_t residual_scratch_bytes(int m, int num_sms) {
+  return (size_t)residual_slices(std::max(1, m), num_sms) * 2 * std::max(1, m) * sizeof(double);
+}
+void residual_norms(cudaStream_t st, int num_sms, int64_t n, int m, const double* ax, int64_t ldax, const double* x,
+                    int64_t ldx, const double* theta, const int* active, double* r, int64_t ldr,
+                    double* norms_out, double* scratch) {
+  if (m <= 0) return;
+  int nsl = residual_slices(m, num_sms);
+  nsl = (int)std::max<int64_t>(1, std::min<int64_t>(nsl, (n + RN_THREADS - 1) / RN_THREADS));
+  residual_kernel<<<dim3(nsl, m), RN_THREADS, 0, st>>>(n, m, ax, ldax, x, ldx, theta, active, r, ldr, scratch);
+  ++g_launches;
+  residual_final_kernel<<<(m + 63) / 64, 64, 0, st>>>(nsl, m, scratch, norms_out);
+  ++g_launches;
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+
+void block_axpy(cudaStream_t st, int64_t n, int m, double a, const double* x, int64_t ldx, double* y, int64_t ldy) {
+  if (n <= 0 || m <= 0) return;
+  axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, m, a, x, ldx, y, ldy);
+  ++g_launches;
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+
+void block_copy(cudaStream_t st, int64_t n, int m, const double* x, int64_t ldx, double* y, int64_t ldy) {
+  if (n <= 0 || m <= 0 || x == y) return;
+  if (ldx == n && ldy == n)
+    DLB_CUDA_CHECK(cudaMemcpyAsync(y, x, sizeof(double) * (size_t)n * m, cudaMemcpyDeviceToDevice, st));
+  else
+    DLB_CUDA_CHECK(cudaMemcpy2DAsync(y, sizeof(double) * ldy, x, sizeof(double) * ldx, sizeof(double) * n, m,
+                                     cudaMemcpyDeviceToDevice, st));
+}
+
+void pack_rows(cudaStream_t st, int64_t row0, int64_t cnt, int m, const double* x, int64_t ldx, double* out) {
+  if (cnt <= 0 || m <= 0) return;
+  DLB_CUDA_CHECK(cudaMemcpy2DAsync(out, sizeof(double) * cnt, x + row0, sizeof(double) * ldx, sizeof(double) * cnt, m,
+                                   cudaMemcpyDeviceToDevice, st));
+}
+
+}  // namespace dlb

@@ -1,0 +1,49 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed for the bootstrap only.
+The data path (k x k all-reduces, SpMM halo exchange) runs on the library's own NCCL
+communicator created from a unique id that rank 0 broadcasts here."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import partition
+from .api import _check, lib, set_csr
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_comm(dist=None):
+    """Create the library's NCCL communicator over the ranks of torch.distributed's default
+    group (already initialised by the caller).  No-op for a single process."""
+    rank, world, _ = env_rank()
+    if world <= 1 or dist is None:
+        return rank, world
+    uid = np.zeros(128, dtype=np.uint8)
+    if rank == 0:
+        _check(lib().diaglib_b200_comm_unique_id(C.c_void_p(uid.ctypes.data)), "comm_unique_id")
+    box = [uid.tobytes()]
+    dist.broadcast_object_list(box, src=0)
+    uid = np.frombuffer(box[0], dtype=np.uint8).copy()
+    _check(lib().diaglib_b200_comm_init(rank, world, C.c_void_p(uid.ctypes.data)), "comm_init")
+    return rank, world
+
+
+def install_partitioned(gen_rows, n: int, rank: int, world: int, dist=None):
+    """gen_rows(r0, r1) -> (rowptr, col_global, val, diag) for the owned rows.  Localises the
+    columns, exchanges the needed ranges and installs matrix + halo plan.  Returns (r0, r1)."""
+    r0, r1 = partition.row_range(n, rank, world)
+    rowptr, col, val, diag = gen_rows(r0, r1)
+    if world == 1:
+        set_csr(rowptr, col, val, diag)
+        return r0, r1
+    needed = partition.needed_ranges(col, n, rank, world)
+    all_needed = [None] * world
+    dist.all_gather_object(all_needed, needed)
+    col_loc, n_halo, recv = partition.localize(col, n, rank, world, needed)
+    plan = partition.halo_plan(recv, all_needed, n, rank, world)
+    set_csr(rowptr, col_loc, val, diag, n_halo=n_halo, halo_plan=plan)
+    return r0, r1

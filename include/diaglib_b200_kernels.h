@@ -1,0 +1,56 @@
+/*
+ * diaglib_b200_kernels.h — kernel-level C-ABI entry points.  These are NOT part of the
+ * reference's interface; they expose the individual sm_100a kernels behind the drivers so
+ * that tests/ can check each one against the CPU oracle and bench.py can time the dominant
+ * kernel for its roofline leg.  All matrix arguments are column-major.  "dev" = device
+ * pointer, "host" = host pointer.
+ */
+#ifndef DIAGLIB_B200_KERNELS_H
+#define DIAGLIB_B200_KERNELS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* device memory helpers (so that harnesses need nothing but this library) */
+void* diaglib_b200_malloc(int64_t bytes);
+void diaglib_b200_free(void* dev);
+int32_t diaglib_b200_h2d(void* dev, const void* host, int64_t bytes);
+int32_t diaglib_b200_d2h(void* host, const void* dev, int64_t bytes);
+int32_t diaglib_b200_sync(void);
+/* CUDA-event stopwatch on the library stream */
+void diaglib_b200_timer_start(void);
+double diaglib_b200_timer_stop_ms(void);
+int32_t diaglib_b200_num_sms(void);
+
+/* C(p x q, dev, ldc) = A(n x p, dev)^T B(n x q, dev), all-reduced over the communicator.
+ * replaces dgemm('t','n') at diaglib.f90:313,403,1691,3256,3543 */
+int32_t diaglib_b200_k_gram(int64_t n, const double* a_dev, int64_t lda, int32_t p, const double* b_dev,
+                            int64_t ldb, int32_t q, double* c_dev, int32_t ldc, int32_t sym_lower);
+/* Y(n x q, dev) = alpha V(n x p, dev) C(p x q, dev) + beta Y.  replaces dgemm('n','n') at
+ * diaglib.f90:322,420,495,1717,3544 */
+int32_t diaglib_b200_k_block_mul(int64_t n, const double* v_dev, int64_t ldv, int32_t p, const double* c_dev,
+                                 int32_t ldc, int32_t q, double alpha, double beta, double* y_dev, int64_t ldy);
+/* r = ax - theta_j x, norms[0..m) = sum r^2 (all-reduced), norms[m..2m) = max|r| (all-reduced);
+ * theta (m, host), active (m, host), norms (2m, host).  diaglib.f90:428-442 */
+int32_t diaglib_b200_k_residual(int64_t n, int32_t m, const double* ax_dev, int64_t ldax, const double* x_dev,
+                                int64_t ldx, const double* theta_host, const int32_t* active_host, double* r_dev,
+                                int64_t ldr, double* norms_host);
+/* dsyev('v',uplo) replacement on a host matrix (k x k, lda): a overwritten by eigenvectors,
+ * w ascending.  returns sweeps (<0 if not converged).  diaglib.f90:315,406,1708 */
+int32_t diaglib_b200_k_sym_eig(int32_t k, double* a_host, int32_t lda, int32_t upper, double* w_host);
+/* one factor+invert step of ortho_cd on a host metric (m x m): T = L^-T (m x m).
+ * out5 = {l_norm, linv_norm, shift_used, info_first, n_shifts}; returns hard_fail.
+ * diaglib.f90:3261-3316 */
+int32_t diaglib_b200_k_chol_inv(int32_t m, const double* metric_host, double* t_host, double* out5);
+/* get_coeffs on host matrices: a_red (len_a x len_a, eigenvectors in place) -> u_p (len_u x n_act).
+ * out4 = {sweeps, cd_passes, fail, qr}.  diaglib.f90:3686-3732 */
+int32_t diaglib_b200_k_get_coeffs(int32_t len_a, int32_t len_u, int32_t n_max, int32_t n_act,
+                                  const double* a_red_host, double* u_p_host, int32_t* out4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,218 @@
+"""GPU parity tests of the drivers and the public block routines against the CPU oracle on
+identical inputs, through the reference-shaped interface (diaglib_b200.lobpcg_driver etc.).
+
+Bar (BASELINE.json north_star): eigenvalues to 1e-10 relative, residual norms below the
+requested tolerance, iteration count within +-1 of the reference algorithm."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from diaglib_b200 import problems as P
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL = 1e-10
+
+
+def dense_as_csr(a):
+    n = a.shape[0]
+    rowptr = np.arange(0, n * n + 1, n, dtype=np.int64)
+    col = np.tile(np.arange(n, dtype=np.int32), n)
+    return rowptr, col, np.ascontiguousarray(a).reshape(-1), np.diag(a).copy()
+
+
+def install(D, oracle, csr):
+    rp, c, v, d = csr
+    oracle.set_csr(rp, c, v, d)
+    D.set_csr(rp, c, v, d)
+
+
+def check_solution(csr, eig, evec, n_targ, tol):
+    rp, c, v, d = csr
+    import scipy.sparse as sp
+    n = len(rp) - 1
+    a = sp.csr_matrix((v, c, rp), shape=(n, n))
+    x = evec[:, :n_targ]
+    res = a @ x - x * eig[:n_targ]
+    assert (np.linalg.norm(res, axis=0) / np.sqrt(n)).max() < tol
+    assert np.abs(res).max() < 10 * tol
+    assert np.abs(x.T @ x - np.eye(n_targ)).max() < 1e-11
+
+
+def run_both(D, oracle, driver, csr, n_targ, n_max, tol=1e-8, max_iter=200, max_dav=20, shift=0.0, seed=1):
+    n = len(csr[0]) - 1
+    install(D, oracle, csr)
+    ev_o = P.guess(n, n_max, seed=seed)
+    ev_g = ev_o.copy(order="F")
+    eig_g = np.zeros(n_max)
+    if driver == "lobpcg":
+        ro = oracle.lobpcg(ev_o, n_targ, max_iter, tol, shift=shift)
+        ok = D.lobpcg_driver(False, False, n, n_targ, n_max, max_iter, tol, shift, None, None, None, eig_g, ev_g)
+    else:
+        ro = oracle.davidson(ev_o, n_targ, max_iter, tol, max_dav, shift=shift)
+        ok = D.davidson_driver(False, n, n_targ, n_max, max_iter, tol, max_dav, shift, None, None, eig_g, ev_g)
+    hg = D.last_history(n_max)
+    return ro, ok, eig_g, ev_g, hg, ev_o
+
+
+def assert_parity(ro, ok, eig_g, hg, n_targ):
+    assert ok == ro["ok"]
+    scale = np.abs(ro["eig"][:n_targ]).max()
+    assert np.abs(eig_g[:n_targ] - ro["eig"][:n_targ]).max() / scale < REL
+    assert abs(len(hg["it"]) - len(ro["it"])) <= 1
+
+
+@pytest.mark.parametrize("driver", ["lobpcg", "davidson"])
+def test_c1_toy_matrix(gpu_lib, oracle, driver):
+    """config C1 = the reference's own test (main.f90:14-18, 283-401)"""
+    n, n_want, tol = 1000, 10, 1e-8
+    n_eig = P.n_eig_rule(n_want)
+    csr = dense_as_csr(P.toy_dense(n))
+    ro, ok, eig_g, ev_g, hg, _ = run_both(gpu_lib, oracle, driver, csr, n_want, n_eig, tol=tol, max_iter=100, max_dav=20)
+    assert ok
+    assert_parity(ro, ok, eig_g, hg, n_want)
+    gold = np.array(json.load(open(os.path.join(GOLD, "toy_dense_eigs.json")))["eig"])[:n_want]
+    assert np.abs(eig_g[:n_want] - gold).max() / gold.max() < REL
+    check_solution(csr, eig_g, ev_g, n_want, tol)
+    hist = json.load(open(os.path.join(GOLD, "c1_oracle_history.json")))[driver]
+    assert abs(len(hg["it"]) - hist["iterations"]) <= 1
+    st = gpu_lib.last_stats()
+    assert st["qr_fallbacks"] == 0 and st["launches"] > 0
+
+
+@pytest.mark.parametrize("driver,gen,n_targ", [("lobpcg", "toy_sparse", 8), ("lobpcg", "lap3d", 6), ("davidson", "toy_sparse", 5),
+                                               ("davidson", "lap3d", 4), ("lobpcg", "fci_like", 4)])
+def test_sparse_configs_small(gpu_lib, oracle, driver, gen, n_targ):
+    """scaled-down C2 / C3 / C4 generators"""
+    if gen == "toy_sparse":
+        csr = P.toy_sparse(1 << 14)
+    elif gen == "lap3d":
+        csr = P.lap3d(32, 32, 16, delta=256.0 / (1 << 14))
+    else:
+        csr = P.fci_like(1 << 14, n_strides=12, bandwidth=1 << 10, big_delta=0.01)
+    n_max = P.n_eig_rule(n_targ)
+    ro, ok, eig_g, ev_g, hg, _ = run_both(gpu_lib, oracle, driver, csr, n_targ, n_max, max_iter=400, max_dav=12)
+    assert ok and ro["ok"]
+    assert_parity(ro, ok, eig_g, hg, n_targ)
+    check_solution(csr, eig_g, ev_g, n_targ, 1e-8)
+    # per-iteration eigenvalue histories agree while both run
+    L = min(len(hg["it"]), len(ro["it"]))
+    assert np.abs(hg["eig"][:L, :n_targ] - ro["hist_eig"][:L, :n_targ]).max() < 1e-6 * np.abs(ro["eig"][:n_targ]).max()
+
+
+def test_lobpcg_shift_returned_in_eig(gpu_lib, oracle):
+    """quirk: LOBPCG returns eig INCLUDING the shift (diaglib.f90:416 vs 461)"""
+    csr = P.toy_sparse(3000)
+    ro, ok, eig_g, ev_g, hg, _ = run_both(gpu_lib, oracle, "lobpcg", csr, 4, 8, shift=2.5)
+    assert ok
+    assert_parity(ro, ok, eig_g, hg, 4)
+    check_solution(csr, eig_g - 2.5, ev_g, 4, 1e-8)
+
+
+def test_lobpcg_ntarg_equals_nmax_and_odd_n(gpu_lib, oracle):
+    csr = P.toy_sparse(2501)  # odd n: exercises the 8-byte loaders
+    ro, ok, eig_g, ev_g, hg, _ = run_both(gpu_lib, oracle, "lobpcg", csr, 5, 5, max_iter=300)
+    assert_parity(ro, ok, eig_g, hg, 5)
+    if ok:
+        check_solution(csr, eig_g, ev_g, 5, 1e-8)
+
+
+def test_not_converged_returns_ok_false(gpu_lib, oracle):
+    csr = P.toy_sparse(4000)
+    ro, ok, eig_g, ev_g, hg, _ = run_both(gpu_lib, oracle, "lobpcg", csr, 6, 11, max_iter=3)
+    assert not ok and not ro["ok"] and len(hg["it"]) == 3
+    assert np.abs(eig_g[:6] - ro["eig"][:6]).max() < 1e-8 * np.abs(ro["eig"][:6]).max()
+
+
+def test_davidson_restart_path(gpu_lib, oracle):
+    """max_dav below min_dav=10 is raised to 10 (1595): a slow problem forces a restart (1795-1825)"""
+    csr = P.lap3d(16, 16, 16, delta=16.0 / 4096)
+    ro, ok, eig_g, ev_g, hg, _ = run_both(gpu_lib, oracle, "davidson", csr, 3, 6, max_iter=300, max_dav=5)
+    assert len(ro["it"]) > 10, "problem too easy to exercise the restart"
+    assert ok and ro["ok"]
+    assert_parity(ro, ok, eig_g, hg, 3)
+    check_solution(csr, eig_g, ev_g, 3, 1e-8)
+
+
+def test_zero_guess_makes_random_start(gpu_lib):
+    """check_guess: all-zero evec -> library-generated start vectors (diaglib.f90:3750-3755)"""
+    csr = P.toy_sparse(2000)
+    gpu_lib.set_csr(*csr)
+    n, n_max = 2000, 9
+    ev = np.zeros((n, n_max), order="F")
+    eig = np.zeros(n_max)
+    ok = gpu_lib.lobpcg_driver(False, False, n, 4, n_max, 300, 1e-8, 0.0, None, None, None, eig, ev)
+    assert ok
+    check_solution(csr, eig, ev, 4, 1e-8)
+
+
+def test_device_resident_evec(gpu_lib, oracle):
+    """evec/eig may live in HBM (detected): same result as with host buffers"""
+    from diaglib_b200 import kernels as K
+    csr = P.toy_sparse(3000)
+    ro, ok, eig_h, ev_h, hg, _ = run_both(gpu_lib, oracle, "lobpcg", csr, 4, 9)
+    dev = K.DeviceArray.from_numpy(P.guess(3000, 9))
+    eig = np.zeros(9)
+    ok2 = gpu_lib.lobpcg_driver(False, False, 3000, 4, 9, 200, 1e-8, 0.0, None, None, None, eig, dev)
+    assert ok and ok2
+    assert np.array_equal(eig, eig_h)
+    assert np.array_equal(dev.numpy(), ev_h)
+
+
+def test_gen_eig_is_rejected(gpu_lib):
+    ev = P.guess(100, 4)
+    with pytest.raises(gpu_lib.DiaglibError):
+        gpu_lib.lobpcg_driver(False, True, 100, 2, 4, 10, 1e-8, 0.0, None, None, None, np.zeros(4), ev)
+
+
+# ---- public block routines -------------------------------------------------------------------
+@pytest.mark.parametrize("n,m", [(1000, 15), (20000, 37), (5001, 8), (3000, 133)])
+def test_ortho_cd_vs_oracle(gpu_lib, oracle, n, m):
+    rng = np.random.default_rng(m)
+    u = np.asfortranarray(rng.standard_normal((n, m)))
+    u[:, m // 2] = u[:, 0] + 1e-6 * rng.standard_normal(n)
+    uo = u.copy(order="F")
+    go, oko = oracle.ortho_cd(uo)
+    g, ok = gpu_lib.ortho_cd(n, m, u)
+    assert ok and oko
+    assert np.linalg.norm(u.T @ u - np.eye(m)) < 1e-13 * m
+    assert abs(g - go) < 1e-6 * go
+    assert np.abs(u - uo).max() < 1e-7
+    assert gpu_lib.last_stats()["ortho_cd_passes"] >= 2
+
+
+def test_ortho_cd_rank_deficient_uses_level_shift(gpu_lib, oracle):
+    rng = np.random.default_rng(0)
+    u = np.asfortranarray(rng.standard_normal((4000, 10)))
+    u[:, 6] = u[:, 1]
+    g, ok = gpu_lib.ortho_cd(4000, 10, u)
+    assert gpu_lib.last_stats()["chol_shifts"] >= 1
+    assert np.all(np.isfinite(u))
+
+
+@pytest.mark.parametrize("n,m,k", [(1000, 15, 15), (20000, 74, 37), (5001, 30, 8), (4000, 300, 15)])
+def test_ortho_vs_x_vs_oracle(gpu_lib, oracle, n, m, k):
+    rng = np.random.default_rng(k)
+    x, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    x = np.asfortranarray(x)
+    u = np.asfortranarray(rng.standard_normal((n, k)) + 30.0 * x[:, :k])
+    uo = u.copy(order="F")
+    oracle.ortho_vs_x(x, uo)
+    gpu_lib.ortho_vs_x(n, m, k, x, u)
+    assert np.linalg.norm(x.T @ u) < 1e-13 * np.sqrt(m * k)
+    assert np.linalg.norm(u.T @ u - np.eye(k)) < 1e-13 * k
+    assert np.abs(u - uo).max() < 1e-9
+
+
+def test_ortho_qr_fallback(gpu_lib, oracle):
+    rng = np.random.default_rng(7)
+    u = np.asfortranarray(rng.standard_normal((3000, 11)))
+    uo = u.copy(order="F")
+    oracle.ortho(uo)
+    gpu_lib.ortho(3000, 11, u)
+    assert np.linalg.norm(u.T @ u - np.eye(11)) < 1e-13
+    # same Q up to column signs (Householder R may have negative diagonal entries)
+    s = np.sign(np.sum(u * uo, axis=0))
+    assert np.abs(u * s - uo).max() < 1e-10

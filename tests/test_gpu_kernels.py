@@ -1,0 +1,232 @@
+"""GPU parity tests of the individual sm_100a kernels against numpy / the CPU oracle, all
+through the C-ABI (include/diaglib_b200_kernels.h)."""
+import numpy as np
+import pytest
+
+from diaglib_b200 import problems as P
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+@pytest.fixture(scope="module")
+def K(gpu_lib):
+    from diaglib_b200 import kernels
+    return kernels
+
+
+def rnd(n, m, seed):
+    return np.asfortranarray(np.random.default_rng(seed).standard_normal((n, m)))
+
+
+# ---- gram: dgemm('t','n') replacement -------------------------------------------------------
+@pytest.mark.parametrize("n,p,q", [(1000, 15, 15), (4096, 37, 37), (4099, 74, 37), (10000, 111, 111), (33, 5, 3),
+                                   (7, 3, 2), (20000, 128, 128), (3001, 1, 1), (5000, 133, 133), (2048, 300, 15)])
+def test_gram_full(K, n, p, q):
+    a, b = rnd(n, p, 1), rnd(n, q, 2)
+    da, db = K.DeviceArray.from_numpy(a), K.DeviceArray.from_numpy(b)
+    c = K.gram(da, p, db, q)
+    ref = a.T @ b
+    assert np.abs(c - ref).max() <= 1e-12 * np.sqrt(n) * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n,p", [(1000, 15), (4097, 37), (10000, 111), (9000, 74), (6000, 133), (3000, 8), (2500, 260)])
+def test_gram_symmetric_lower(K, n, p):
+    """V^T (A V) with symmetric A: only the lower triangle is computed, then mirrored"""
+    v = rnd(n, p, 3)
+    d = np.linspace(1.0, 2.0, n)
+    av = np.asfortranarray(v * d[:, None])
+    dv, dav = K.DeviceArray.from_numpy(v), K.DeviceArray.from_numpy(av)
+    c = K.gram(dv, p, dav, p, sym_lower=True)
+    ref = v.T @ av
+    assert np.abs(c - ref).max() <= 1e-12 * np.sqrt(n) * np.abs(ref).max()
+    assert np.array_equal(c, c.T)
+    c2 = K.gram(dv, p, dv, p, sym_lower=True)  # same operand (ortho_cd metric)
+    assert np.abs(c2 - v.T @ v).max() <= 1e-12 * np.sqrt(n) * np.abs(ref).max()
+
+
+def test_gram_column_offsets_and_odd_ld(K):
+    """sub-blocks of a wider block with an odd leading dimension exercise the 8-byte loader"""
+    n, w = 3001, 40
+    a = rnd(n, w, 4)
+    da = K.DeviceArray.from_numpy(a)
+    c = K.gram(da, 7, da, 11, a_off=3, b_off=20)
+    assert np.abs(c - a[:, 3:10].T @ a[:, 20:31]).max() < 1e-10
+
+
+def test_gram_is_deterministic(K):
+    a = rnd(50000, 37, 5)
+    da = K.DeviceArray.from_numpy(a)
+    c1 = K.gram(da, 37, da, 37, sym_lower=True)
+    c2 = K.gram(da, 37, da, 37, sym_lower=True)
+    assert np.array_equal(c1, c2)
+
+
+# ---- block_mul: dgemm('n','n') / dtrmm replacement -------------------------------------------
+@pytest.mark.parametrize("n,p,q", [(1000, 15, 15), (4096, 111, 37), (4099, 74, 37), (130, 30, 5), (7, 3, 2),
+                                   (5000, 111, 74), (5001, 128, 128), (3000, 300, 15), (2000, 40, 133), (999, 1, 1)])
+def test_block_mul(K, n, p, q):
+    v, c, y0 = rnd(n, p, 6), rnd(p, q, 7), rnd(n, q, 8)
+    dv, dy = K.DeviceArray.from_numpy(v), K.DeviceArray.from_numpy(y0)
+    K.block_mul(dv, p, c, dy, alpha=1.0, beta=0.0)
+    ref = v @ c
+    assert np.abs(dy.numpy() - ref).max() <= 1e-13 * p * max(1.0, np.abs(ref).max())
+    dy2 = K.DeviceArray.from_numpy(y0)
+    K.block_mul(dv, p, c, dy2, alpha=-1.0, beta=1.0)  # U -= X (X^T U), diaglib.f90:3544
+    ref2 = y0 - v @ c
+    assert np.abs(dy2.numpy() - ref2).max() <= 1e-13 * p * max(1.0, np.abs(ref2).max())
+
+
+def test_block_mul_in_place_row_local(K):
+    n, m = 5003, 37
+    u = rnd(n, m, 9)
+    t = np.asfortranarray(np.triu(rnd(m, m, 10)))
+    du = K.DeviceArray.from_numpy(u)
+    K.block_mul(du, m, t, du)
+    assert np.abs(du.numpy() - u @ t).max() < 1e-11
+
+
+def test_block_mul_writes_into_own_columns(K):
+    """P = space * u_p written into columns of space itself (diaglib.f90:495-496)"""
+    n, w, p, q = 3000, 30, 20, 6
+    s = rnd(n, w, 11)
+    c = rnd(p, q, 12)
+    ds = K.DeviceArray.from_numpy(s)
+    K.block_mul(ds, p, c, ds, y_off=22)
+    out = ds.numpy()
+    assert np.array_equal(out[:, :22], s[:, :22])
+    assert np.abs(out[:, 22:28] - s[:, :p] @ c).max() < 1e-11
+
+
+# ---- residual + norms (dcopy/daxpy/dnrm2/maxval fusion) --------------------------------------
+def test_residual_norms(K):
+    n, m = 10007, 9
+    ax, x = rnd(n, m, 13), rnd(n, m, 14)
+    theta = np.linspace(0.5, 3.0, m)
+    active = np.array([1, 1, 0, 1, 0, 1, 1, 1, 0], np.int32)
+    dax, dx, dr = K.DeviceArray.from_numpy(ax), K.DeviceArray.from_numpy(x), K.DeviceArray((n, m))
+    ss, mx = K.residual(dax, dx, theta, active, dr)
+    r = dr.numpy()
+    for j in range(m):
+        if active[j]:
+            ref = ax[:, j] - theta[j] * x[:, j]
+            assert np.abs(r[:, j] - ref).max() < 1e-14
+            assert abs(ss[j] - ref @ ref) < 1e-10 * (ref @ ref)
+            assert abs(mx[j] - np.abs(ref).max()) < 1e-14
+        else:
+            assert np.array_equal(r[:, j], ax[:, j])
+
+
+# ---- symmetric eigensolver (dsyev replacement) ------------------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 3, 15, 30, 45, 74, 111, 112, 150, 300])
+def test_sym_eig_vs_lapack(K, oracle, k):
+    rng = np.random.default_rng(k)
+    s = rng.standard_normal((k, k))
+    a = np.diag(np.arange(1.0, k + 1)) + 0.3 * (s + s.T)
+    w_ref, _ = oracle.dsyev(a)
+    for upper in (False, True):
+        tri = np.triu(a) if upper else np.tril(a)  # the other triangle must not be referenced
+        tri = tri + (np.tril(np.full((k, k), np.nan), -1) if upper else np.triu(np.full((k, k), np.nan), 1))
+        w, z, sweeps = K.sym_eig(tri, upper=upper)
+        scale = np.abs(w_ref).max()
+        assert np.abs(w - w_ref).max() <= 50 * EPS * scale * max(1, np.sqrt(k))
+        assert np.abs(a @ z - z * w).max() <= 200 * EPS * scale * np.sqrt(k)
+        assert np.abs(z.T @ z - np.eye(k)).max() <= 100 * EPS * np.sqrt(k)
+        assert np.all(np.diff(w) >= 0)
+
+
+def test_sym_eig_lobpcg_like_matrix(K, oracle):
+    """a_red of a converging LOBPCG: diag(eig) block plus small couplings; some exact zeros"""
+    rng = np.random.default_rng(5)
+    k = 45
+    a = np.diag(np.concatenate([np.arange(2.0, 17.0), 50 + 10 * rng.random(30)]))
+    c = 1e-6 * rng.standard_normal((k, k))
+    a += c + c.T
+    a[20, :5] = a[:5, 20] = 0.0
+    w_ref, _ = oracle.dsyev(a)
+    w, z, _ = K.sym_eig(a)
+    assert np.abs(w - w_ref).max() < 1e-13 * 60
+    # sign convention: largest component positive (deterministic across ranks)
+    assert np.all(z[np.abs(z).argmax(axis=0), np.arange(k)] > 0)
+
+
+# ---- Cholesky factor + inverse + norm estimates (one ortho_cd pass) ---------------------------
+@pytest.mark.parametrize("m", [1, 5, 15, 37, 64, 100, 133])
+def test_chol_inv(K, oracle, m):
+    import ctypes as C
+    u = rnd(4 * m + 10, m, m)
+    g = u.T @ u
+    t, st = K.chol_inv(g)
+    L = np.linalg.cholesky(g)
+    assert st["info_first"] == 0 and st["n_shifts"] == 0 and st["hard_fail"] == 0
+    assert np.abs(np.tril(t, -1)).max() == 0.0
+    assert np.abs(t - np.linalg.inv(L).T).max() <= 1e-10 * np.abs(t).max()
+    mi = C.byref(C.c_int32(m))
+    Lf = np.asfortranarray(L)
+    Li = np.asfortranarray(np.linalg.inv(L))
+    assert abs(st["l_norm"] - oracle.lib().oracle_norm_est(mi, Lf.ctypes.data_as(C.c_void_p))) < 1e-10 * st["l_norm"]
+    assert abs(st["linv_norm"] - oracle.lib().oracle_norm_est(mi, Li.ctypes.data_as(C.c_void_p))) < 1e-8 * st["linv_norm"]
+    q = u @ t
+    assert np.abs(q.T @ q - np.eye(m)).max() < 1e-10
+
+
+def test_chol_inv_level_shift(K):
+    """rank-deficient metric: dpotrf fails, the level-shift loop (diaglib.f90:3265-3295) rescues"""
+    u = rnd(200, 12, 21)
+    u[:, 7] = u[:, 2]
+    g = u.T @ u
+    t, st = K.chol_inv(g)
+    assert st["info_first"] != 0 and st["n_shifts"] >= 1 and st["hard_fail"] == 0
+    unorm = np.sqrt(np.trace(g))
+    assert st["shift"] >= EPS * 100 * unorm * 0.99
+    assert np.all(np.isfinite(t))
+
+
+# ---- get_coeffs (P coefficients) ----------------------------------------------------------------
+@pytest.mark.parametrize("n_max,n_act,first", [(15, 15, True), (15, 9, False), (37, 37, False), (37, 20, False), (6, 1, False)])
+def test_get_coeffs_vs_oracle(K, oracle, n_max, n_act, first):
+    rng = np.random.default_rng(n_max * 100 + n_act)
+    len_u = 2 * n_max if first else n_max + 2 * n_act
+    s = rng.standard_normal((len_u, len_u))
+    a = np.diag(np.arange(1.0, len_u + 1)) + 0.02 * (s + s.T)
+    _, z, _ = K.sym_eig(a)
+    z = np.asfortranarray(z)
+    u_p, st = K.get_coeffs(z, len_u, n_max, n_act)
+    u_x_ref, u_p_ref = oracle.get_coeffs(z, len_u, n_max, n_act)
+    assert st["fail"] == 0 and st["qr"] == 0
+    u_x = z[:, :n_max]
+    assert np.linalg.norm(u_x.T @ u_p) < 1e-14 * np.sqrt(len_u) * 10
+    assert np.linalg.norm(u_p.T @ u_p - np.eye(n_act)) < 1e-13
+    assert np.abs(u_p - u_p_ref).max() < 1e-9
+
+
+# ---- built-in callbacks -------------------------------------------------------------------------
+@pytest.mark.parametrize("gen,m", [("lap3d", 37), ("toy_sparse", 13), ("fci_like", 5), ("lap3d", 3)])
+def test_spmm_bit_exact_vs_oracle(K, gpu_lib, oracle, gen, m):
+    import ctypes as C
+    if gen == "lap3d":
+        n = 16 ** 3
+        rp, c, v, d = P.lap3d(16, 16, 16, delta=0.25)
+    elif gen == "toy_sparse":
+        n = 5000
+        rp, c, v, d = P.toy_sparse(n)
+    else:
+        n = 4096
+        rp, c, v, d = P.fci_like(n, n_strides=20, bandwidth=512)
+    oracle.set_csr(rp, c, v, d)
+    gpu_lib.set_csr(rp, c, v, d)
+    x = P.guess(n, m)
+    ref = oracle.csr_matvec(x)
+    dx, dax = K.DeviceArray.from_numpy(x), K.DeviceArray((n, m))
+    i32 = lambda v_: C.byref(C.c_int32(v_))  # noqa: E731
+    gpu_lib.lib().diaglib_b200_csr_matvec(i32(n), i32(m), C.c_void_p(dx.ptr), C.c_void_p(dax.ptr))
+    gpu_lib.lib().diaglib_b200_sync()
+    assert np.array_equal(dax.numpy(), ref)  # same summation order, FMA on both sides
+    # preconditioner incl. the |d+fac| <= 1e-5 guard (main.f90:161-166)
+    for fac in (-1.5, -float(d[7])):
+        refp = oracle.diag_precnd(x, fac)
+        dpx = K.DeviceArray((n, m))
+        gpu_lib.lib().diaglib_b200_diag_precnd(i32(n), i32(m), C.byref(C.c_double(fac)), C.c_void_p(dx.ptr),
+                                              C.c_void_p(dpx.ptr))
+        gpu_lib.lib().diaglib_b200_sync()
+        assert np.array_equal(dpx.numpy(), refp)

@@ -1,0 +1,151 @@
+"""CPU tests: the oracle against the known-answer data the reference's own test defines
+(dense LAPACK on the toy matrix, main.f90:311-342) and against structural invariants."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from diaglib_b200 import problems as P
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+EPS = np.finfo(float).eps
+
+# BASELINE.md section 2 (printed digits of the reference's lapack.txt check)
+BASELINE_EIGS = [1.869398101309, 3.000476106191, 4.017712612105, 5.016812067990, 6.013523333955,
+                 7.010610707515, 8.008385419234, 9.006729203366, 10.005490234949, 11.004549919231,
+                 12.003824214451, 13.003254791546, 14.002801027083, 15.002434279316, 16.002134042057]
+
+
+def gold_eigs():
+    return np.array(json.load(open(os.path.join(GOLD, "toy_dense_eigs.json")))["eig"])
+
+
+def test_golden_matches_baseline_md():
+    assert np.abs(gold_eigs()[:15] - np.array(BASELINE_EIGS)).max() < 5e-12
+
+
+def test_dense_lapack_crosscheck(oracle):
+    a = P.toy_dense(1000)
+    w, z = oracle.dsyev(a)
+    assert np.abs(w[:20] - gold_eigs()).max() < 1e-10
+    assert np.abs(a @ z[:, :5] - z[:, :5] * w[:5]).max() < 1e-9
+
+
+@pytest.mark.parametrize("driver", ["lobpcg", "davidson"])
+def test_c1_toy_driver(oracle, driver):
+    """config C1: n=1000, 10 roots of 15, tol 1e-8, itmax 100, m_max 20 (main.f90:14-18)"""
+    n, n_want, tol = 1000, 10, 1e-8
+    n_eig = P.n_eig_rule(n_want)
+    a = P.toy_dense(n)
+    oracle.set_dense(a)
+    ev = P.guess(n, n_eig)
+    if driver == "lobpcg":
+        r = oracle.lobpcg(ev, n_want, 100, tol, matvec="oracle_dense_matvec")
+    else:
+        r = oracle.davidson(ev, n_want, 100, tol, 20, matvec="oracle_dense_matvec")
+    assert r["ok"] and r["status"] == 0
+    g = gold_eigs()[:n_want]
+    assert np.abs(r["eig"][:n_want] - g).max() / np.abs(g).max() < 1e-10
+    # returned vectors: residuals below the requested tolerance, orthonormal
+    x = ev[:, :n_want]
+    res = a @ x - x * r["eig"][:n_want]
+    assert (np.linalg.norm(res, axis=0) / np.sqrt(n)).max() < tol
+    assert np.abs(res).max() < 10 * tol
+    assert np.abs(x.T @ x - np.eye(n_want)).max() < 1e-12
+    hist = json.load(open(os.path.join(GOLD, "c1_oracle_history.json")))[driver]
+    assert abs(len(r["it"]) - hist["iterations"]) <= 1
+    assert r["stats"]["qr_fallbacks"] == 0
+
+
+def test_lobpcg_shift_is_returned_in_eig(oracle):
+    """quirk: LOBPCG returns eig INCLUDING shift (diaglib.f90:416 vs 461)"""
+    n, n_want = 300, 4
+    a = P.toy_dense(n)
+    oracle.set_dense(a)
+    w = np.linalg.eigvalsh(a)
+    ev = P.guess(n, 8)
+    r = oracle.lobpcg(ev, n_want, 200, 1e-8, shift=2.5, matvec="oracle_dense_matvec")
+    assert r["ok"]
+    assert np.abs(r["eig"][:n_want] - (w[:n_want] + 2.5)).max() < 1e-8
+
+
+def test_ortho_cd_invariants(oracle):
+    rng = np.random.default_rng(0)
+    u = np.asfortranarray(rng.standard_normal((5000, 24)))
+    u[:, 3] = u[:, 2] + 1e-7 * rng.standard_normal(5000)  # nearly dependent columns: forces extra passes
+    span = u.copy()
+    growth, ok = oracle.ortho_cd(u)
+    assert ok and growth >= 1.0
+    assert np.linalg.norm(u.T @ u - np.eye(24)) < 1e-13
+    # same span
+    q, _ = np.linalg.qr(span)
+    assert np.linalg.norm(u - q @ (q.T @ u)) < 1e-6
+
+
+def test_ortho_vs_x_invariants(oracle):
+    rng = np.random.default_rng(1)
+    x, _ = np.linalg.qr(rng.standard_normal((4000, 30)))
+    x = np.asfortranarray(x)
+    u = np.asfortranarray(rng.standard_normal((4000, 12)) + x[:, :12] * 50.0)
+    oracle.ortho_vs_x(x, u)
+    assert np.linalg.norm(x.T @ u) < 1e-13
+    assert np.linalg.norm(u.T @ u - np.eye(12)) < 1e-13
+
+
+def test_ortho_qr(oracle):
+    rng = np.random.default_rng(2)
+    u = np.asfortranarray(rng.standard_normal((500, 9)))
+    oracle.ortho(u)
+    assert np.linalg.norm(u.T @ u - np.eye(9)) < 1e-13
+
+
+def test_norm_est_bound(oracle):
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    L = np.asfortranarray(np.tril(rng.standard_normal((17, 17))))
+    est = oracle.lib().oracle_norm_est(C.byref(C.c_int32(17)), L.ctypes.data_as(C.c_void_p))
+    assert est >= np.linalg.norm(L, 2) - 1e-12
+    assert abs(est - (np.abs(np.diag(L)).max() + np.linalg.norm(np.tril(L, -1)))) < 1e-12
+
+
+def test_get_coeffs_orthogonal(oracle):
+    rng = np.random.default_rng(4)
+    n_max, n_act = 7, 5
+    len_u = n_max + 2 * n_act
+    s = rng.standard_normal((len_u, len_u))
+    s = np.diag(np.arange(1, len_u + 1.0)) + 0.05 * (s + s.T)
+    _, z = np.linalg.eigh(s)
+    a_red = np.asfortranarray(z)
+    u_x, u_p = oracle.get_coeffs(a_red, len_u, n_max, n_act)
+    assert np.linalg.norm(u_x.T @ u_p) < 1e-14
+    assert np.linalg.norm(u_p.T @ u_p - np.eye(n_act)) < 1e-14
+
+
+def test_csr_callbacks_match_dense(oracle):
+    n = 257
+    rp, c, v, d = P.toy_sparse(n)
+    a = P.csr_to_dense(n, rp, c, v)
+    assert np.abs(a - a.T).max() == 0.0
+    oracle.set_csr(rp, c, v, d)
+    x = P.guess(n, 5)
+    ax = oracle.csr_matvec(x)
+    assert np.abs(ax - a @ x).max() < 1e-13
+    px = oracle.diag_precnd(x, -1.5)
+    assert np.abs(px - x / (d[:, None] - 1.5)).max() < 1e-15
+    # guard |d + fac| <= 1e-5 -> copy (main.f90:161-166)
+    px = oracle.diag_precnd(x, -d[3])
+    assert np.all(px[3] == x[3])
+
+
+def test_sparse_lobpcg_small(oracle):
+    nx = 16
+    n = nx ** 3
+    rp, c, v, d = P.lap3d(nx, nx, nx, delta=256.0 / n)
+    oracle.set_csr(rp, c, v, d)
+    a = P.csr_to_dense(n, rp, c, v)
+    w = np.linalg.eigvalsh(a)
+    ev = P.guess(n, 9)
+    r = oracle.lobpcg(ev, 4, 300, 1e-8)
+    assert r["ok"]
+    assert np.abs(r["eig"][:4] - w[:4]).max() / abs(w[3]) < 1e-10
