@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the diaglib hot path on B200 (contract in the task brief).
+
+Workload (BASELINE.json configs[2], "C3", the configuration the metric is quoted on; it fits
+one GPU): 3-D 7-point Laplacian on 256^3 (n = 2^24 = 16 777 216) with the permuted-progression
+diagonal d_i = 6 + delta (1 + pi(i)), delta = 1; 32 roots (n_max = 37), tol 1e-8, LOBPCG; start
+vectors = unit vectors on the 37 lowest diagonal entries + 10 % relative uniform noise
+("benchmark problem").  One STEP = one complete lobpcg_driver solve to convergence.
+
+  value      iterations/s with the start vectors already resident in HBM (device-pointer evec)
+  e2e        same metric through the reference-shaped call with HOST (pinned) evec/eig buffers:
+             the H2D copy of the guess and the D2H copy of the eigenvectors are inside the call
+  roofline   the dominant kernel family (block_mul) timed alone, live, at the workload's shape
+  cpu_baseline  the CPU oracle (C++ restatement of diaglib on OpenBLAS, NOT a gfortran build) on
+             a bounded sample of the same workload, extrapolated linearly in n
+
+python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nx 256]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from diaglib_b200 import problems as P  # noqa: E402
+
+N_TARG, TOL, DELTA, NOISE, MAX_ITER = 32, 1e-8, 1.0, 0.1, 200
+METRIC, UNIT = "lobpcg_iters_per_s", "iterations/s"
+
+
+def make_guess(diag_glob, n_glob, n_max, r0, r1):
+    g = P.guess_lowest_diag(diag_glob, n_max, r0, r1)
+    g += P.guess(n_glob, n_max, r0, r1) * (NOISE / np.sqrt(n_glob / 12.0))
+    return g
+
+
+def global_diag(nx, ny, nz):
+    n = nx * ny * nz
+    return P.lap3d_diag(np.arange(n, dtype=np.int64), n.bit_length() - 1, DELTA, 1)
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.p = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def oracle_sample(nx_s, iters, threads):
+    """CPU oracle on a bounded sample of the workload: lap3d nx_s^3, `iters` LOBPCG iterations."""
+    from oracle import oracle as O
+    O.set_threads(threads)
+    n_s = nx_s ** 3
+    n_max = P.n_eig_rule(N_TARG)
+    csr = P.lap3d(nx_s, nx_s, nx_s, delta=DELTA)
+    O.set_csr(*csr)
+    ev = make_guess(csr[3], n_s, n_max, 0, n_s)
+    t0 = time.time()
+    r = O.lobpcg(ev, N_TARG, iters, TOL)
+    wall = time.time() - t0
+    its = len(r["it"])
+    return n_s, its, wall, O.get_threads()
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference algorithm on the host cores (oracle port; the Fortran
+    reference cannot be built in this image)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_full = args.nx ** 3
+    nx_s = min(args.nx, 128)
+    it_s = 4
+    for _ in range(args.warmup):
+        oracle_sample(min(nx_s, 64), 2, threads)
+    t_tot, its_tot = 0.0, 0
+    for _ in range(args.steps):
+        n_s, its, wall, nthr = oracle_sample(nx_s, it_s, threads)
+        t_tot += wall
+        its_tot += its
+    ips_sample = its_tot / t_tot
+    value = ips_sample * (n_s / n_full)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C3 lap3d {args.nx}^3 n={n_full} n_targ={N_TARG} n_max={P.n_eig_rule(N_TARG)} LOBPCG tol={TOL}",
+                   "delta": DELTA, "guess": "lowest-diag unit + 10% noise"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthr, "kind": "port",
+                         "sample": f"{it_s} LOBPCG iterations (+ setup) of the same workload at n={n_s} ({nx_s}^3), "
+                                   f"iterations/s scaled by n_sample/n (all per-iteration work is O(n)); C++ restatement "
+                                   f"of diaglib on OpenBLAS 0.3.31 ({nthr} threads), not a gfortran build"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--nx", type=int, default=256, help="grid edge (n = nx^3); 256 is the headline workload")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import diaglib_b200 as D
+    from diaglib_b200 import dist as DD, kernels as K, partition
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D.init(local)
+    DD.init_comm(dist if world > 1 else None)
+
+    nx = args.nx
+    n = nx ** 3
+    n_max = P.n_eig_rule(N_TARG)
+    r0, r1 = DD.install_partitioned(lambda a, b: P.lap3d(nx, nx, nx, a, b, delta=DELTA), n, rank, world,
+                                    dist if world > 1 else None)
+    n_loc = r1 - r0
+    guess = make_guess(global_diag(nx, nx, nx), n, n_max, r0, r1)
+    blk_bytes = guess.nbytes
+
+    d_guess = K.DeviceArray.from_numpy(guess)
+    d_evec = K.DeviceArray((n_loc, n_max))
+    h_evec_t = torch.empty((n_max, n_loc), dtype=torch.float64, pin_memory=True)  # pinned, column-major n_loc x n_max
+    h_evec = h_evec_t.numpy().T
+    h_guess_t = torch.empty((n_max, n_loc), dtype=torch.float64, pin_memory=True)
+    h_guess_t.numpy().T[...] = guess
+    h_eig_t = torch.empty(n_max, dtype=torch.float64, pin_memory=True)
+    eig = np.zeros(n_max)
+    lib = D.lib()
+
+    def barrier():
+        lib.diaglib_b200_sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def solve_resident():
+        # refresh the working block from the resident guess (device-to-device, outside the timed region)
+        lib.diaglib_b200_d2d(d_evec.ptr, d_guess.ptr, blk_bytes)
+        barrier()
+        t0 = time.perf_counter()
+        K.timer_start()
+        ok = D.lobpcg_driver(False, False, n_loc, N_TARG, n_max, MAX_ITER, TOL, 0.0, None, None, None, eig, d_evec)
+        ms = K.timer_stop_ms()
+        wall = time.perf_counter() - t0
+        return ok, ms, wall
+
+    def solve_e2e():
+        h_evec_t.copy_(h_guess_t)  # host-side refresh of the caller's buffer, outside the timed region
+        barrier()
+        t0 = time.perf_counter()
+        ok = D.lobpcg_driver(False, False, n_loc, N_TARG, n_max, MAX_ITER, TOL, 0.0, None, None, None,
+                             h_eig_t.numpy(), h_evec)
+        lib.diaglib_b200_sync()
+        wall = time.perf_counter() - t0
+        return ok, wall
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up ------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        ok, ms, wall = solve_resident()
+        assert ok, "warm-up solve did not converge"
+    its = len(D.last_history(n_max)["it"])
+
+    # ---- timed: K solves, start vectors resident in HBM ------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    tot_ms, tot_its, launches = 0.0, 0, 0
+    for _ in range(args.steps):
+        ok, ms, wall = solve_resident()
+        assert ok
+        tot_ms += maxr(ms)
+        tot_its += len(D.last_history(n_max)["it"])
+        launches += D.last_stats()["launches"]
+    clocks = sampler.stop() if rank == 0 else None
+    hist = D.last_history(n_max)
+    timers = D.last_timers()
+    ms_per_step = tot_ms / args.steps
+    value = tot_its / (tot_ms * 1e-3)
+
+    # ---- e2e: host buffers, H2D + D2H inside the call ---------------------------------------
+    solve_e2e()
+    e2e_t, e2e_its = 0.0, 0
+    for _ in range(args.steps):
+        ok, wall = solve_e2e()
+        assert ok
+        e2e_t += maxr(wall)
+        e2e_its += len(D.last_history(n_max)["it"])
+    e2e_value = e2e_its / e2e_t
+    eig_e2e = h_eig_t.numpy().copy()
+
+    # ---- per-kernel-family shares (one extra, untimed, profiled solve) ------------------------
+    D.set_profile(True)
+    solve_resident()
+    prof = D.last_timers()
+    D.set_profile(False)
+
+    # ---- roofline of the dominant kernel family, timed alone at the workload's shape -----------
+    roof = None
+    if rank == 0 or world > 1:
+        p, q = 3 * n_max, n_max
+        v = K.DeviceArray((n_loc, p))
+        y = K.DeviceArray((n_loc, q))
+        cm = np.asfortranarray(np.random.default_rng(0).standard_normal((p, q)))
+        cd = K.DeviceArray.from_numpy(cm)
+        lib.diaglib_b200_k_fill_uniform(v.ptr, n_loc, p, n_loc, 1)
+        reps = 5
+        for _ in range(3):
+            lib.diaglib_b200_k_block_mul(n_loc, v.ptr, n_loc, p, cd.ptr, p, q, 1.0, 0.0, y.ptr, n_loc)
+        lib.diaglib_b200_sync()
+        K.timer_start()
+        for _ in range(reps):
+            lib.diaglib_b200_k_block_mul(n_loc, v.ptr, n_loc, p, cd.ptr, p, q, 1.0, 0.0, y.ptr, n_loc)
+        bm_ms = K.timer_stop_ms() / reps
+        flops = 2.0 * n_loc * p * q
+        bytes_alg = 8.0 * n_loc * (p + q)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        f64 = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")))
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        f64_peak = f64["dgemm_8192_tflops_burst"]
+        t_hbm = bytes_alg / (hbm_peak * 1e9)
+        t_f64 = flops / (f64_peak * 1e12)
+        bound = "tensor" if t_f64 >= t_hbm else "hbm"
+        ach_tf = flops / (bm_ms * 1e-3) / 1e12
+        ach_gb = bytes_alg / (bm_ms * 1e-3) / 1e9
+        roof = {"kernel": f"blockmul_kernel Y(n x {q}) = V(n x {p}) C, n={n_loc}", "bound": bound,
+                "achieved": ach_tf if bound == "tensor" else ach_gb, "peak": f64_peak if bound == "tensor" else hbm_peak,
+                "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                "frac": (ach_tf / f64_peak) if bound == "tensor" else (ach_gb / hbm_peak),
+                "peak_source": ("cuBLAS DGEMM 8192^3 measured on this pool (profiles/fp64_peaks_r01.json); "
+                                "MEASURED_PEAKS.json has no FP64 figure") if bound == "tensor" else
+                               ("MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"),
+                "traffic": None, "ms_per_launch": bm_ms, "achieved_gbs": ach_gb, "achieved_tflops": ach_tf,
+                "hbm_frac": ach_gb / hbm_peak, "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops}
+        # second family: symmetric Gram at len_u = 3 n_max
+        w = K.DeviceArray((n_loc, p))
+        lib.diaglib_b200_k_fill_uniform(w.ptr, n_loc, p, n_loc, 12345)
+        cg = K.DeviceArray((p, p))
+        for _ in range(2):
+            lib.diaglib_b200_k_gram(n_loc, v.ptr, n_loc, p, w.ptr, n_loc, p, cg.ptr, p, 1)
+        lib.diaglib_b200_sync()
+        K.timer_start()
+        for _ in range(reps):
+            lib.diaglib_b200_k_gram(n_loc, v.ptr, n_loc, p, w.ptr, n_loc, p, cg.ptr, p, 1)
+        gr_ms = K.timer_stop_ms() / reps
+        gflops = 1.0 * n_loc * p * (p + 1)  # lower triangle only
+        gbytes = 8.0 * n_loc * 2 * p
+        roof["gram"] = {"kernel": f"gram_kernel sym {p}x{p}, n={n_loc}", "ms_per_launch": gr_ms,
+                        "achieved_tflops": gflops / (gr_ms * 1e-3) / 1e12, "achieved_gbs": gbytes / (gr_ms * 1e-3) / 1e9,
+                        "frac_tensor": gflops / (gr_ms * 1e-3) / 1e12 / f64_peak, "frac_hbm": gbytes / (gr_ms * 1e-3) / 1e9 / hbm_peak}
+        for a in (v, y, cd, w, cg):
+            a.free()
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        nx_s = min(nx, 128)
+        n_s, its_s, wall_s, nthr = oracle_sample(nx_s, 4, threads)
+        cpu = {"value": (its_s / wall_s) * (n_s / n), "unit": UNIT, "cores": nthr, "kind": "port",
+               "sample": f"{its_s} LOBPCG iterations (+ setup) of the same workload at n={n_s} ({nx_s}^3) in {wall_s:.1f} s, "
+                         f"scaled by n_sample/n; C++ restatement of diaglib on OpenBLAS ({nthr} threads), not a gfortran build"}
+
+    if rank == 0:
+        res_max = float(hist["rms"][-1][:N_TARG].max()) if len(hist["it"]) else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3 lap3d {nx}^3 n={n} n_targ={N_TARG} n_max={n_max} LOBPCG tol={TOL} (BASELINE.json configs[2])",
+                       "delta": DELTA, "guess": "lowest-diag unit + 10% noise", "rows_per_gpu": n_loc,
+                       "l2": "inputs larger than L2 (every block >= 4.9 GB at N=1)", "parallelism": f"row-partition x{world}"},
+            "time_to_converge_s": ms_per_step * 1e-3, "iterations": tot_its / args.steps, "converged": True,
+            "final_rms_residual_max": res_max, "eig_lowest": [float(x) for x in eig[:4]],
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(blk_bytes), "d2h_bytes_per_step": int(blk_bytes + 8 * n_max),
+                    "time_to_converge_s": e2e_t / args.steps, "eig_matches_resident": bool(np.array_equal(eig_e2e, eig))},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "phases_s": {k: round(float(v), 5) for k, v in timers.items()},
+            "profiled_families_s": {k: round(float(prof[k]), 5) for k in ("k_gram", "k_block_mul", "k_copy", "mv", "diag", "total")},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

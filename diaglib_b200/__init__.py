@@ -21,4 +21,5 @@ from .api import (  # noqa: F401
     last_history,
     last_stats,
     last_timers,
+    set_profile,
 )

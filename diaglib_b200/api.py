@@ -53,6 +53,8 @@ def lib():
         L.diaglib_b200_free.argtypes = [C.c_void_p]
         L.diaglib_b200_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.diaglib_b200_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.diaglib_b200_d2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.diaglib_b200_k_fill_uniform.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64]
         L.diaglib_b200_timer_stop_ms.restype = C.c_double
         L.diaglib_b200_set_csr.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.diaglib_b200_set_halo.argtypes = [C.c_int32] + [C.c_void_p] * 5
@@ -194,9 +196,15 @@ def last_history(n_max: int):
 
 
 def last_timers():
-    t = np.zeros(8)
+    t = np.zeros(12)
     lib().diaglib_b200_timers(_ptr(t))
-    return dict(mv=t[0], diag=t[1], ortho=t[2], total=t[3], gram=t[4], ritz=t[5], resid=t[6], stage=t[7])
+    return dict(mv=t[0], diag=t[1], ortho=t[2], total=t[3], gram=t[4], ritz=t[5], resid=t[6], stage=t[7],
+                k_gram=t[8], k_block_mul=t[9], k_copy=t[11])
+
+
+def set_profile(on: bool) -> None:
+    """per-kernel-family device timing (two CUDA events per launch); off by default"""
+    lib().diaglib_b200_set_profile(C.c_int32(1 if on else 0))
 
 
 def last_stats():

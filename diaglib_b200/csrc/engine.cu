@@ -75,7 +75,8 @@ struct NcclApi {
   }
 };
 
-enum Phase { PH_MV = 0, PH_DIAG, PH_ORTHO, PH_TOTAL, PH_GRAM, PH_RITZ, PH_RESID, PH_STAGE, PH_COUNT };
+enum Phase { PH_MV = 0, PH_DIAG, PH_ORTHO, PH_TOTAL, PH_GRAM, PH_RITZ, PH_RESID, PH_STAGE,
+             PH_KGRAM, PH_KBMUL, PH_KSMALL, PH_KCOPY, PH_COUNT };
 
 struct Hist {
   int n_max = 0;
@@ -200,6 +201,35 @@ struct Engine {
     }
   }
 
+  // kernel-family wrappers: optional per-family device timing (diaglib_b200_set_profile)
+  bool profile = false;
+  void kgram(int64_t n, const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, double* C, int ldc,
+             bool sym) {
+    PhaseHandle h;
+    if (profile) h = ph_open(PH_KGRAM);
+    gram_tn(st, num_sms, n, A, lda, p, B, ldb, q, C, ldc, sym, partial.as<double>());
+    if (profile) ph_close(h);
+  }
+  void kbmul(int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc, int q, double alpha,
+             double beta, double* Y, int64_t ldy) {
+    PhaseHandle h;
+    if (profile) h = ph_open(PH_KBMUL);
+    block_mul(st, n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy);
+    if (profile) ph_close(h);
+  }
+  void ktrmm(int64_t n, double* U, int64_t ldu, int m, const double* T) {
+    PhaseHandle h;
+    if (profile) h = ph_open(PH_KBMUL);
+    block_trmm_inplace(st, n, U, ldu, m, T);
+    if (profile) ph_close(h);
+  }
+  void kcopy(int64_t n, int m, const double* x, int64_t ldx, double* y, int64_t ldy) {
+    PhaseHandle h;
+    if (profile) h = ph_open(PH_KCOPY);
+    block_copy(st, n, m, x, ldx, y, ldy);
+    if (profile) ph_close(h);
+  }
+
   // ---- ortho_cd, diaglib.f90:3185-3341 ------------------------------------------------
   // one host synchronisation per pass (the CholStatus read-back decides macro_done).
   bool ortho_cd(int64_t n, int m, double* u, int64_t ldu, double& growth) {
@@ -211,7 +241,7 @@ struct Engine {
         return false;
       }
       ++st_cd_passes;
-      gram_tn(st, num_sms, n, u, ldu, m, u, ldu, m, d_metric, m, true, partial.as<double>());  // 3256
+      kgram(n, u, ldu, m, u, ldu, m, d_metric, m, true);  // 3256
       allreduce(d_metric, (size_t)m * m);
       chol_inv(st, m, d_metric, m, d_T, d_cholwork, d_cholst);                                  // 3261-3316
       CholStatus cs;
@@ -224,7 +254,7 @@ struct Engine {
       }
       const double rcond = cs.l_norm * cs.linv_norm;
       growth *= cs.linv_norm;                                    // 3323
-      block_trmm_inplace(st, n, u, ldu, m, d_T);                 // 3327
+      ktrmm(n, u, ldu, m, d_T);                 // 3327
       if (EPS * rcond * rcond < TOL_ORTHO) return true;          // 3331-3332
     }
   }
@@ -240,18 +270,18 @@ struct Engine {
     for (int j = 0; j < m; ++j) {
       double* uj = u + (int64_t)j * ldu;
       for (int pass = 0; pass < 2 && j > 0; ++pass) {
-        gram_tn(st, num_sms, n, u, ldu, j, uj, ldu, 1, c, j, false, partial.as<double>());
+        kgram(n, u, ldu, j, uj, ldu, 1, c, j, false);
         allreduce(c, j);
-        block_mul(st, n, u, ldu, j, c, j, 1, -1.0, 1.0, uj, ldu);
+        kbmul(n, u, ldu, j, c, j, 1, -1.0, 1.0, uj, ldu);
       }
-      gram_tn(st, num_sms, n, uj, ldu, 1, uj, ldu, 1, c, 1, false, partial.as<double>());
+      kgram(n, uj, ldu, 1, uj, ldu, 1, c, 1, false);
       allreduce(c, 1);
       double nrm2;
       read_back(&nrm2, c, sizeof(double));
       const double inv = 1.0 / std::sqrt(nrm2);
       DLB_CUDA_CHECK(cudaMemcpyAsync(c, &inv, sizeof(double), cudaMemcpyHostToDevice, st));
       sync();
-      block_mul(st, n, uj, ldu, 1, c, 1, 1, 1.0, 0.0, uj, ldu);
+      kbmul(n, uj, ldu, 1, c, 1, 1, 1.0, 0.0, uj, ldu);
     }
   }
 
@@ -267,15 +297,15 @@ struct Engine {
     while (!done) {
       ++it;
       ++st_sweeps;
-      gram_tn(st, num_sms, n, x, ldx, m, u, ldu, k, d_xu, m, false, partial.as<double>());  // 3543
+      kgram(n, x, ldx, m, u, ldu, k, d_xu, m, false);  // 3543
       allreduce(d_xu, (size_t)m * k);
-      block_mul(st, n, x, ldx, m, d_xu, m, k, -1.0, 1.0, u, ldu);                            // 3544
+      kbmul(n, x, ldx, m, d_xu, m, k, -1.0, 1.0, u, ldu);                            // 3544
       ok = ortho_cd(n, k, u, ldu, growth);                                                   // 3548
       if (status) return;
       double xu_norm;
       if (!ok) {                                                                             // 3549,3558-3560
         ortho_qr(n, k, u, ldu);
-        gram_tn(st, num_sms, n, x, ldx, m, u, ldu, k, d_xu, m, false, partial.as<double>());
+        kgram(n, x, ldx, m, u, ldu, k, d_xu, m, false);
         allreduce(d_xu, (size_t)m * k);
         std::vector<double> h((size_t)m * k);
         read_back(h.data(), d_xu, h.size() * sizeof(double));
@@ -369,7 +399,7 @@ __global__ void set_diag_kernel(int cnt, double* a, int lda, const double* d) {
 // ---- check_guess, diaglib.f90:3734-3786 ------------------------------------------------
 void Engine::check_guess(int64_t n, int m, double* evec, int64_t ld) {
   double growth;
-  gram_tn(st, num_sms, n, evec, ld, m, evec, ld, m, d_metric, m, true, partial.as<double>());  // 3762 (and 3749)
+  kgram(n, evec, ld, m, evec, ld, m, d_metric, m, true);  // 3762 (and 3749)
   allreduce(d_metric, (size_t)m * m);
   std::vector<double> ov((size_t)m * m);
   read_back(ov.data(), d_metric, ov.size() * sizeof(double));
@@ -478,21 +508,21 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
   auto COL = [&](double* base, int col1) { return base + (size_t)nn * (col1 - 1); };  // 1-based column
 
   check_guess(nn, n_max, d_evec, nn);                                                  // 295
-  block_copy(st, nn, n_max, d_evec, nn, space, nn);                                    // 306
+  kcopy(nn, n_max, d_evec, nn, space, nn);                                    // 306
   h = ph_open(PH_MV);
   { int32_t m32 = n_max; matvec(&n32, &m32, space, aspace); }                          // 309
   ph_close(h);
   if (shift != 0.0) block_axpy(st, nn, n_max, shift, space, nn, aspace, nn);           // 312
   h = ph_open(PH_GRAM);
-  gram_tn(st, num_sms, nn, space, nn, n_max, aspace, nn, n_max, a_red, n_max, true, partial.as<double>());  // 313
+  kgram(nn, space, nn, n_max, aspace, nn, n_max, a_red, n_max, true);  // 313
   allreduce(a_red, (size_t)n_max * n_max);
   ph_close(h);
   h = ph_open(PH_DIAG);
   sym_eig(st, n_max, a_red, n_max, false, e_red, eig_work, d_eigst);                   // 315
   ph_close(h);
   h = ph_open(PH_RITZ);
-  block_mul(st, nn, space, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, space, nn);       // 322-323 (row-local, in place)
-  block_mul(st, nn, aspace, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, aspace, nn);     // 324-325
+  kbmul(nn, space, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, space, nn);       // 322-323 (row-local, in place)
+  kbmul(nn, aspace, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, aspace, nn);     // 324-325
   ph_close(h);
   h = ph_open(PH_RESID);
   DLB_CUDA_CHECK(cudaMemcpyAsync(d_active, h_active.data(), n_max * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -524,15 +554,15 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
     int len_u = n_max + 2 * n_act;
     if (it == 1) len_u = 2 * n_max;
     h = ph_open(PH_GRAM);
-    gram_tn(st, num_sms, nn, space, nn, len_u, aspace, nn, len_u, a_red, len_u, true, partial.as<double>());  // 403
+    kgram(nn, space, nn, len_u, aspace, nn, len_u, a_red, len_u, true);  // 403
     allreduce(a_red, (size_t)len_u * len_u);
     ph_close(h);
     h = ph_open(PH_DIAG);
     sym_eig(st, len_u, a_red, len_u, false, e_red, eig_work, d_eigst);                 // 406
     ph_close(h);
     h = ph_open(PH_RITZ);
-    block_mul(st, nn, space, nn, len_u, a_red, len_u, n_max, 1.0, 0.0, x_new, nn);     // 420
-    block_mul(st, nn, aspace, nn, len_u, a_red, len_u, n_max, 1.0, 0.0, ax_new, nn);   // 421
+    kbmul(nn, space, nn, len_u, a_red, len_u, n_max, 1.0, 0.0, x_new, nn);     // 420
+    kbmul(nn, aspace, nn, len_u, a_red, len_u, n_max, 1.0, 0.0, ax_new, nn);   // 421
     ph_close(h);
     h = ph_open(PH_RESID);
     for (int i = 0; i < n_max; ++i) h_active[i] = done[i] ? 0 : 1;
@@ -576,7 +606,7 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
     bool all_done = true;
     for (int i = 0; i < n_targ; ++i) all_done = all_done && done[i];
     if (all_done) {                                                                     // 465-469
-      block_copy(st, nn, n_max, x_new, nn, d_evec, nn);
+      kcopy(nn, n_max, x_new, nn, d_evec, nn);
       ok = true;
       break;
     }
@@ -592,10 +622,10 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
     // p = space u_p, ap = aspace u_p (495-498).  The products are row-local, so they are
     // written straight into the p columns of space/aspace instead of going through evec.
     h = ph_open(PH_RITZ);
-    block_mul(st, nn, space, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(space, ind_p), nn);
-    block_mul(st, nn, aspace, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(aspace, ind_p), nn);
-    block_copy(st, nn, n_max, x_new, nn, space, nn);                                    // 510
-    block_copy(st, nn, n_max, ax_new, nn, aspace, nn);                                  // 511
+    kbmul(nn, space, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(space, ind_p), nn);
+    kbmul(nn, aspace, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(aspace, ind_p), nn);
+    kcopy(nn, n_max, x_new, nn, space, nn);                                    // 510
+    kcopy(nn, n_max, ax_new, nn, aspace, nn);                                  // 511
     ph_close(h);
     h = ph_open(PH_RESID);
     {
@@ -699,7 +729,7 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
   auto COL = [&](double* base, int col1) { return base + (size_t)nn * (col1 - 1); };
 
   check_guess(nn, n_max, d_evec, nn);                                                   // 1644
-  block_copy(st, nn, n_max, d_evec, nn, space, nn);                                     // 1648
+  kcopy(nn, n_max, d_evec, nn, space, nn);                                     // 1648
   int n_act = n_max, ind = 1, i_beg = 1, m_dim = 1, ldu = 0, n_rst = 0, n_frozen = 0;
   bool restart = false;
   if (verbose && rank == 0) print_header("Davidson-Liu", tol);
@@ -712,7 +742,7 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
     ph_close(h);
     h = ph_open(PH_GRAM);
     double* a_blk = a_red + (size_t)lda * (c1 - 1);
-    gram_tn(st, num_sms, nn, space, nn, ldu, COL(aspace, c1), nn, n_act, a_blk, lda, false, partial.as<double>());  // 1691
+    kgram(nn, space, nn, ldu, COL(aspace, c1), nn, n_act, a_blk, lda, false);  // 1691
     // rows > ldu of these columns are zero on every rank, so the block can be reduced as one range
     allreduce(a_blk, (size_t)(n_act - 1) * lda + ldu);
     ph_close(h);
@@ -727,8 +757,8 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
     sym_eig(st, ldu, a_copy, lda, true, e_red, eig_work, d_eigst);                      // 1708
     ph_close(h);
     h = ph_open(PH_RITZ);
-    block_mul(st, nn, space, nn, ldu, a_copy, lda, n_max, 1.0, 0.0, d_evec, nn);        // 1717
-    block_mul(st, nn, aspace, nn, ldu, a_copy, lda, n_max, 1.0, 0.0, r, nn);            // 1721
+    kbmul(nn, space, nn, ldu, a_copy, lda, n_max, 1.0, 0.0, d_evec, nn);        // 1717
+    kbmul(nn, aspace, nn, ldu, a_copy, lda, n_max, 1.0, 0.0, r, nn);            // 1721
     ph_close(h);
     h = ph_open(PH_RESID);
     for (int i = 0; i < n_max; ++i) h_active[i] = (i < n_targ && !done[i]) ? 1 : 0;     // 1723-1727
@@ -794,7 +824,7 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
       if (verbose && rank == 0) std::printf("      Restarting davidson.\n");
       n_act = n_max;
       DLB_CUDA_CHECK(cudaMemsetAsync(space, 0, big, st));
-      block_copy(st, nn, n_max, d_evec, nn, space, nn);
+      kcopy(nn, n_max, d_evec, nn, space, nn);
       DLB_CUDA_CHECK(cudaMemsetAsync(aspace, 0, big, st));
       DLB_CUDA_CHECK(cudaMemsetAsync(a_red, 0, (size_t)lda * lda * sizeof(double), st));
       ldu = 0; i_beg = 1; m_dim = 1; n_rst = 0;
@@ -1095,7 +1125,8 @@ void diaglib_b200_history_get(int32_t* it, int32_t* n_act, double* eig, double* 
     eig[i] = g.hist.eig[i]; rms[i] = g.hist.rms[i]; mx[i] = g.hist.mx[i]; done[i] = g.hist.done[i];
   }
 }
-void diaglib_b200_timers(double* out8) { for (int i = 0; i < 8; ++i) out8[i] = g.t_acc[i]; }
+void diaglib_b200_timers(double* out12) { for (int i = 0; i < 12; ++i) out12[i] = g.t_acc[i]; }
+void diaglib_b200_set_profile(int32_t on) { g.profile = on != 0; }
 void diaglib_b200_stats(int64_t* out8) {
   out8[0] = g.st_cd_passes; out8[1] = g.st_sweeps; out8[2] = g.st_qr; out8[3] = g.st_shifts; out8[4] = g.st_launches;
   out8[5] = g_launches; out8[6] = 0; out8[7] = 0;
@@ -1118,6 +1149,19 @@ int32_t diaglib_b200_h2d(void* dev, const void* host, int64_t bytes) {
 int32_t diaglib_b200_d2h(void* host, const void* dev, int64_t bytes) {
   if (!require_init()) return DIAGLIB_B200_ENODEVICE;
   DLB_CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, g.st));
+  DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
+  return 0;
+}
+int32_t diaglib_b200_d2d(void* dst, const void* src, int64_t bytes) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g.st));
+  DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
+  return 0;
+}
+int32_t diaglib_b200_k_fill_uniform(double* dev, int64_t n, int32_t m, int64_t ld, int64_t seed_row0) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  random_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g.st>>>(n, m, ld, seed_row0, n, dev);
+  DLB_CUDA_CHECK(cudaGetLastError());
   DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
   return 0;
 }

@@ -173,3 +173,17 @@ def csr_to_dense(n_cols: int, rowptr, col, val):
 def n_eig_rule(n_want: int) -> int:
     """Search-space rule of the reference driver: n_eig = min(2*n_want, n_want+5) (main.f90:354)."""
     return min(2 * n_want, n_want + 5)
+
+
+def guess_lowest_diag(diag_glob, n_max: int, r0: int = 0, r1: int | None = None):
+    """Unit start vectors on the n_max smallest diagonal entries (ties: lowest index first),
+    mirrors guess_evec(1) (main.f90:1337-1347).  diag_glob is the GLOBAL diagonal."""
+    diag_glob = np.asarray(diag_glob)
+    n = diag_glob.shape[0]
+    r1 = n if r1 is None else r1
+    order = np.argsort(diag_glob, kind="stable")[:n_max]
+    out = np.zeros((r1 - r0, n_max), dtype=np.float64, order="F")
+    for j, ipos in enumerate(order):
+        if r0 <= ipos < r1:
+            out[ipos - r0, j] = 1.0
+    return out

@@ -119,8 +119,12 @@ int32_t diaglib_b200_comm_size(void);
 int32_t diaglib_b200_history_len(void);
 void diaglib_b200_history_get(int32_t* it, int32_t* n_act, double* eig, double* rms, double* max, int32_t* done);
 /* seconds: [0] matvec [1] reduced eigensolve [2] orthogonalisation [3] total
- *          [4] gram [5] ritz/projection [6] residual+precnd [7] h2d+d2h staging */
-void diaglib_b200_timers(double* out8);
+ *          [4] gram [5] ritz/projection [6] residual+precnd [7] h2d+d2h staging
+ * and, when profiling is on, per kernel family:
+ *          [8] gram kernels [9] block_mul/trmm kernels [10] unused [11] block copies */
+void diaglib_b200_timers(double* out12);
+/* per-kernel-family device timing (two events per launch); off by default */
+void diaglib_b200_set_profile(int32_t on);
 /* counters: [0] ortho_cd passes [1] ortho_vs_x sweeps [2] QR fallbacks [3] Cholesky shifts
  *           [4] kernel launches issued by the library during the last driver call */
 void diaglib_b200_stats(int64_t* out8);

@@ -19,7 +19,10 @@ void* diaglib_b200_malloc(int64_t bytes);
 void diaglib_b200_free(void* dev);
 int32_t diaglib_b200_h2d(void* dev, const void* host, int64_t bytes);
 int32_t diaglib_b200_d2h(void* host, const void* dev, int64_t bytes);
+int32_t diaglib_b200_d2d(void* dst_dev, const void* src_dev, int64_t bytes);
 int32_t diaglib_b200_sync(void);
+/* fills an n x m block (ld) with stateless-hash U[0,1) values (test / bench data) */
+int32_t diaglib_b200_k_fill_uniform(double* dev, int64_t n, int32_t m, int64_t ld, int64_t seed_row0);
 /* CUDA-event stopwatch on the library stream */
 void diaglib_b200_timer_start(void);
 double diaglib_b200_timer_stop_ms(void);

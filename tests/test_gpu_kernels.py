@@ -171,15 +171,28 @@ def test_chol_inv(K, oracle, m):
 
 
 def test_chol_inv_level_shift(K):
-    """rank-deficient metric: dpotrf fails, the level-shift loop (diaglib.f90:3265-3295) rescues"""
+    """indefinite metric: dpotrf fails, the level-shift loop (diaglib.f90:3265-3295) rescues"""
     u = rnd(200, 12, 21)
-    u[:, 7] = u[:, 2]
     g = u.T @ u
-    t, st = K.chol_inv(g)
-    assert st["info_first"] != 0 and st["n_shifts"] >= 1 and st["hard_fail"] == 0
+    w, z = np.linalg.eigh(g)
     unorm = np.sqrt(np.trace(g))
-    assert st["shift"] >= EPS * 100 * unorm * 0.99
-    assert np.all(np.isfinite(t))
+    w[0] = -50 * EPS * unorm  # slightly negative direction, as produced by a rank-deficient block
+    g2 = (z * w) @ z.T
+    g2 = 0.5 * (g2 + g2.T)
+    t, st = K.chol_inv(g2)
+    assert st["info_first"] != 0 and st["n_shifts"] >= 1 and st["hard_fail"] == 0
+    # shift = max(eps*alpha*unorm, tol_ortho), alpha = 100, 1000, ... (3267, 3287, 3291)
+    un2 = np.sqrt(np.trace(g2))
+    assert abs(st["shift"] - EPS * 100 * 10 ** (st["n_shifts"] - 1) * un2) <= 1e-3 * st["shift"]
+    L = np.linalg.cholesky(g2 + st["shift"] * np.eye(12))
+    assert np.abs(t - np.linalg.inv(L).T).max() <= 1e-6 * np.abs(t).max()
+
+
+def test_chol_inv_hard_fail(K):
+    """a strongly indefinite metric exhausts the 10 shifts (3276-3284)"""
+    g = -np.eye(6)
+    t, st = K.chol_inv(g)
+    assert st["hard_fail"] == 1 and st["n_shifts"] == 10
 
 
 # ---- get_coeffs (P coefficients) ----------------------------------------------------------------
