@@ -21,14 +21,16 @@ namespace {
 
 constexpr int GR_THREADS = 512;
 constexpr int GR_WARPS = GR_THREADS / 32;
-constexpr int GR_KT = 32;          // rows of n per pipeline stage
-constexpr int GR_S = GR_KT + 4;    // padded column stride in shared memory (doubles)
 constexpr int GR_STAGES = 3;
 constexpr int GR_MAXB = 128;       // max p / q handled by one launch
+// Rows of n per pipeline stage (KT) are chosen per launch: narrow blocks get long stages so
+// that enough bytes are in flight per SM; the shared-memory column stride is KT + 4 doubles
+// (== 4 mod 16), which makes every DMMA fragment load bank-conflict free.
 
-// A warp task is a 2 x 4 block of 8x8 output tiles (16 x 32 elements); bit r*4+c of tmask
-// says whether tile (ti0+r, tj0+c) is computed.  The host balances the tasks over the four
-// SM sub-partitions (warp id mod 4), which matters for the triangular (sym_lower) case.
+// A warp task is (part of) a 2 x 4 frame of 8x8 output tiles; bit r*4+c of tmask says whether
+// tile (ti0+r, tj0+c) is computed.  The host picks the task shape (2x4, 2x2, 1x2 or 1x1 tiles)
+// so that all 16 warps have work even for narrow blocks, and balances the tasks over the
+// four SM sub-partitions (warp id mod 4), which matters for the triangular (sym_lower) case.
 struct GramTask {
   uint8_t ti0, tj0, tmask, pad;
 };
@@ -38,25 +40,27 @@ struct GramSched {
 
 template <bool ALIGN16>
 __device__ __forceinline__ void gram_load_stage(double* s, const double* __restrict__ M, int64_t ld, int ncols,
-                                                int64_t k0, int64_t n, int tid) {
+                                                int64_t k0, int64_t n, int tid, int KT) {
+  const int S = KT + 4;
   if (ALIGN16) {
-    const int total = ncols * (GR_KT / 2);
+    const int half = KT >> 1;
+    const int total = ncols * half;
     for (int id = tid; id < total; id += GR_THREADS) {
-      const int col = id / (GR_KT / 2), part = id % (GR_KT / 2);
+      const int col = id / half, part = id - col * half;
       const int64_t row = k0 + part * 2;
       int64_t rem = (n - row) * 8;
       const int bytes = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
       const double* src = M + (int64_t)col * ld + (bytes > 0 ? row : 0);
-      cp_async16(s + col * GR_S + part * 2, src, bytes);
+      cp_async16(s + col * S + part * 2, src, bytes);
     }
   } else {
-    const int total = ncols * GR_KT;
+    const int total = ncols * KT;
     for (int id = tid; id < total; id += GR_THREADS) {
-      const int col = id / GR_KT, part = id % GR_KT;
+      const int col = id / KT, part = id - col * KT;
       const int64_t row = k0 + part;
       const int bytes = row < n ? 8 : 0;
       const double* src = M + (int64_t)col * ld + (bytes > 0 ? row : 0);
-      cp_async8(s + col * GR_S + part, src, bytes);
+      cp_async8(s + col * S + part, src, bytes);
     }
   }
 }
@@ -64,10 +68,12 @@ __device__ __forceinline__ void gram_load_stage(double* s, const double* __restr
 template <bool ALIGN16>
 __global__ void __launch_bounds__(GR_THREADS, 1)
 gram_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const double* __restrict__ B, int64_t ldb,
-            int q, int same, const __grid_constant__ GramSched sched, double* __restrict__ partial, int PB, int QB) {
+            int q, int same, int KT, const __grid_constant__ GramSched sched, double* __restrict__ partial, int PB,
+            int QB) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int stage_doubles = (PB + (same ? 0 : QB)) * GR_S;
+  const int S = KT + 4;
+  const int stage_doubles = (PB + (same ? 0 : QB)) * S;
 
   const GramTask t0 = sched.t[warp][0], t1 = sched.t[warp][1];
   double acc[2][2][4][2];
@@ -78,16 +84,16 @@ gram_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const d
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[s][r][c][0] = acc[s][r][c][1] = 0.0;
 
-  const int64_t nchunks = (n + GR_KT - 1) / GR_KT;
+  const int64_t nchunks = (n + KT - 1) / KT;
   const int64_t first = blockIdx.x, stride = gridDim.x;
   const int64_t my_chunks = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
 
   auto issue = [&](int64_t local_idx) {
     if (local_idx < my_chunks) {
       double* s = smem + (local_idx % GR_STAGES) * stage_doubles;
-      const int64_t k0 = (first + local_idx * stride) * GR_KT;
-      gram_load_stage<ALIGN16>(s, A, lda, p, k0, n, tid);
-      if (!same) gram_load_stage<ALIGN16>(s + PB * GR_S, B, ldb, q, k0, n, tid);
+      const int64_t k0 = (first + local_idx * stride) * KT;
+      gram_load_stage<ALIGN16>(s, A, lda, p, k0, n, tid, KT);
+      if (!same) gram_load_stage<ALIGN16>(s + PB * S, B, ldb, q, k0, n, tid, KT);
     }
     cp_async_commit();
   };
@@ -95,44 +101,51 @@ gram_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const d
 #pragma unroll
   for (int s = 0; s < GR_STAGES - 1; ++s) issue(s);
 
-  const int frag_off = (lane >> 2) * GR_S + (lane & 3);
+  const int frag_off = (lane >> 2) * S + (lane & 3);
   for (int64_t it = 0; it < my_chunks; ++it) {
     cp_async_wait<GR_STAGES - 2>();
     __syncthreads();
     issue(it + GR_STAGES - 1);
     const double* sA = smem + (it % GR_STAGES) * stage_doubles;
-    const double* sB = same ? sA : sA + PB * GR_S;
+    const double* sB = same ? sA : sA + PB * S;
 #pragma unroll
-    for (int ks = 0; ks < GR_KT / 4; ++ks) {
+    for (int s = 0; s < 2; ++s) {
+      const GramTask t = s == 0 ? t0 : t1;
+      if (t.tmask == 0) continue;
+      const double* pa = sA + (t.ti0 * 8) * S + frag_off;
+      const double* pb = sB + (t.tj0 * 8) * S + frag_off;
+      if (t.tmask == 0xFF) {
+        for (int k8 = 0; k8 < KT; k8 += 16) {
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const GramTask t = s == 0 ? t0 : t1;
-        if (t.tmask == 0) continue;
-        const double* pa = sA + (t.ti0 * 8) * GR_S + ks * 4 + frag_off;
-        const double* pb = sB + (t.tj0 * 8) * GR_S + ks * 4 + frag_off;
-        if (t.tmask == 0xFF) {
-          double a[2], b[4];
+          for (int ks = 0; ks < 4; ++ks) {
+            double a[2], b[4];
 #pragma unroll
-          for (int r = 0; r < 2; ++r) a[r] = pa[r * 8 * GR_S];
+            for (int r = 0; r < 2; ++r) a[r] = pa[r * 8 * S + k8 + ks * 4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) b[c] = pb[c * 8 * GR_S];
+            for (int c = 0; c < 4; ++c) b[c] = pb[c * 8 * S + k8 + ks * 4];
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
+            for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) dmma884(acc[s][r][c][0], acc[s][r][c][1], a[r], b[c]);
-        } else {
-          double a[2] = {0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+              for (int c = 0; c < 4; ++c) dmma884(acc[s][r][c][0], acc[s][r][c][1], a[r], b[c]);
+          }
+        }
+      } else {
+        const bool ra0 = (t.tmask & 0x0F) != 0, ra1 = (t.tmask & 0xF0) != 0;
+        for (int k8 = 0; k8 < KT; k8 += 16) {
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
-            if (t.tmask & (0xF << (4 * r))) a[r] = pa[r * 8 * GR_S];
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (t.tmask & (0x11 << c)) b[c] = pb[c * 8 * GR_S];
-#pragma unroll
-          for (int r = 0; r < 2; ++r)
+          for (int ks = 0; ks < 4; ++ks) {
+            double a[2] = {0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+            if (ra0) a[0] = pa[k8 + ks * 4];
+            if (ra1) a[1] = pa[8 * S + k8 + ks * 4];
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              if (t.tmask & (1 << (r * 4 + c))) dmma884(acc[s][r][c][0], acc[s][r][c][1], a[r], b[c]);
+              if (t.tmask & (0x11 << c)) b[c] = pb[c * 8 * S + k8 + ks * 4];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (t.tmask & (1 << (r * 4 + c))) dmma884(acc[s][r][c][0], acc[s][r][c][1], a[r], b[c]);
+          }
         }
       }
     }
@@ -184,17 +197,36 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, int ncta,
 // Build a balanced task schedule for a p x q block (tile counts ntp x ntq).
 GramSched make_sched(int ntp, int ntq, bool sym_lower) {
   struct T { int ti0, tj0, mask, cnt; };
+  const int shapes[4][2] = {{2, 4}, {2, 2}, {1, 2}, {1, 1}};
   std::vector<T> tasks;
-  for (int ti0 = 0; ti0 < ntp; ti0 += 2)
-    for (int tj0 = 0; tj0 < ntq; tj0 += 4) {
-      int mask = 0, cnt = 0;
-      for (int r = 0; r < 2; ++r)
-        for (int c = 0; c < 4; ++c) {
-          const int ti = ti0 + r, tj = tj0 + c;
-          if (ti < ntp && tj < ntq && (!sym_lower || tj <= ti)) { mask |= 1 << (r * 4 + c); ++cnt; }
-        }
-      if (cnt) tasks.push_back({ti0, tj0, mask, cnt});
-    }
+  for (int sh = 0; sh < 4; ++sh) {
+    const int tr = shapes[sh][0], tc = shapes[sh][1];
+    tasks.clear();
+    for (int ti0 = 0; ti0 < ntp; ti0 += tr)
+      for (int tj0 = 0; tj0 < ntq; tj0 += tc) {
+        int mask = 0, cnt = 0;
+        for (int r = 0; r < tr; ++r)
+          for (int c = 0; c < tc; ++c) {
+            const int ti = ti0 + r, tj = tj0 + c;
+            if (ti < ntp && tj < ntq && (!sym_lower || tj <= ti)) { mask |= 1 << (r * 4 + c); ++cnt; }
+          }
+        if (cnt) tasks.push_back({ti0, tj0, mask, cnt});
+      }
+    // the coarsest shape that keeps every warp busy; finer shapes only if they still fit 32 slots
+    if ((int)tasks.size() >= GR_WARPS || sh == 3) break;
+    // peek: would the next finer shape overflow the 2 slots per warp?
+    const int ntr = shapes[sh + 1][0], ntc = shapes[sh + 1][1];
+    int nxt = 0;
+    for (int ti0 = 0; ti0 < ntp; ti0 += ntr)
+      for (int tj0 = 0; tj0 < ntq; tj0 += ntc) {
+        bool any = false;
+        for (int r = 0; r < ntr && !any; ++r)
+          for (int c = 0; c < ntc && !any; ++c)
+            any = (ti0 + r < ntp && tj0 + c < ntq && (!sym_lower || tj0 + c <= ti0 + r));
+        nxt += any;
+      }
+    if (nxt > 2 * GR_WARPS) break;
+  }
   std::stable_sort(tasks.begin(), tasks.end(), [](const T& a, const T& b) { return a.cnt > b.cnt; });
   GramSched s{};
   int load_q[4] = {0, 0, 0, 0};
@@ -219,6 +251,14 @@ GramSched make_sched(int ntp, int ntq, bool sym_lower) {
   return s;
 }
 
+// stage length: as long as three stages fit in shared memory, capped at 128 rows
+int pick_kt(int cols) {
+  const int budget = 200 * 1024 / (GR_STAGES * 8);  // doubles per stage
+  int kt = 128;
+  while (kt > 16 && cols * (kt + 4) > budget) kt >>= 1;
+  return kt;
+}
+
 }  // namespace
 
 size_t gram_scratch_bytes(int p, int q, int num_sms) {
@@ -237,8 +277,6 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
     attr_set = true;
   }
   const bool al16 = aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0);
-  const int64_t nchunks = (n + GR_KT - 1) / GR_KT;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, nchunks));
   for (int p0 = 0; p0 < p; p0 += GR_MAXB)
     for (int q0 = 0; q0 < q; q0 += GR_MAXB) {
       const bool diag_blk = sym_lower && p0 == q0;
@@ -250,11 +288,15 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
       const double* Bb = B + (int64_t)q0 * ldb;
       const int same = (Ab == Bb && lda == ldb && pb == qb) ? 1 : 0;
       const GramSched sched = make_sched(ntp, ntq, diag_blk);
-      const size_t smem = (size_t)GR_STAGES * (PB + (same ? 0 : QB)) * GR_S * sizeof(double);
+      const int cols = PB + (same ? 0 : QB);
+      const int KT = pick_kt(cols);
+      const int64_t nchunks = (n + KT - 1) / KT;
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, nchunks));
+      const size_t smem = (size_t)GR_STAGES * cols * (KT + 4) * sizeof(double);
       if (al16)
-        gram_kernel<true><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, sched, partial, PB, QB);
+        gram_kernel<true><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
       else
-        gram_kernel<false><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, sched, partial, PB, QB);
+        gram_kernel<false><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
       ++g_launches;
       const int tot = pb * qb;
       double* Cblk = C + p0 + (size_t)q0 * ldc;
@@ -374,19 +416,166 @@ blockmul_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, con
   }
 }
 
+// Persistent variant: C (p x q) stays resident in shared memory for the CTA's lifetime, the
+// CTA walks over row tiles (stride gridDim.x) and the cp.async ring runs continuously across
+// (tile, k-chunk) pairs, so there is no pipeline fill/drain bubble per row tile.
+template <int NQT, bool ALIGN16>
+__global__ void __launch_bounds__(BM_THREADS)
+blockmul_persistent_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, const double* __restrict__ C,
+                           int ldc, int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int QB = NQT * 8;
+  constexpr int STAGE = BM_KC * BM_SV;
+  double* sC = smem;                       // [QB][PS], zero padded
+  double* ring = smem + (size_t)QB * PS;   // BM_STAGES x STAGE
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nk = (p + BM_KC - 1) / BM_KC;
+  const int64_t ntiles = (n + BM_RT - 1) / BM_RT;
+  const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_chunks = my_tiles * nk;
+
+  for (int id = tid; id < QB * PS; id += BM_THREADS) {
+    const int j = id / PS, k = id - j * PS;
+    sC[id] = (j < q && k < p) ? C[(size_t)j * ldc + k] : 0.0;
+  }
+
+  auto issue = [&](int64_t c) {
+    if (c < my_chunks) {
+      const int64_t ti = c / nk;
+      const int kc = (int)(c - ti * nk);
+      const int64_t row0 = (blockIdx.x + ti * gridDim.x) * BM_RT;
+      double* sV = ring + (c % BM_STAGES) * STAGE;
+      const int k0 = kc * BM_KC;
+      if (ALIGN16) {
+        for (int id = tid; id < BM_KC * (BM_RT / 2); id += BM_THREADS) {
+          const int col = id / (BM_RT / 2), part = id % (BM_RT / 2);
+          const int64_t row = row0 + part * 2;
+          int64_t rem = (k0 + col < p) ? (n - row) * 8 : 0;
+          const int bytes = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+          const double* src = bytes > 0 ? V + (int64_t)(k0 + col) * ldv + row : V;
+          cp_async16(sV + col * BM_SV + part * 2, src, bytes);
+        }
+      } else {
+        for (int id = tid; id < BM_KC * BM_RT; id += BM_THREADS) {
+          const int col = id / BM_RT, part = id % BM_RT;
+          const int64_t row = row0 + part;
+          const int bytes = (k0 + col < p && row < n) ? 8 : 0;
+          const double* src = bytes > 0 ? V + (int64_t)(k0 + col) * ldv + row : V;
+          cp_async8(sV + col * BM_SV + part, src, bytes);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int s = 0; s < BM_STAGES - 1; ++s) issue(s);
+
+  double acc[2][NQT][2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < NQT; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+
+  const int a_off = (lane & 3) * BM_SV + warp * 16 + (lane >> 2);
+  const int b_off = (lane >> 2) * PS + (lane & 3);
+  int kc = 0;
+  int64_t ti = 0;
+  for (int64_t c = 0; c < my_chunks; ++c) {
+    cp_async_wait<BM_STAGES - 2>();
+    __syncthreads();
+    issue(c + BM_STAGES - 1);
+    const double* sV = ring + (c % BM_STAGES) * STAGE;
+    const double* sCk = sC + kc * BM_KC + b_off;
+#pragma unroll
+    for (int k4 = 0; k4 < BM_KC / 4; ++k4) {
+      double a[2], b[NQT];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * BM_SV + a_off + r * 8];
+#pragma unroll
+      for (int cc = 0; cc < NQT; ++cc) b[cc] = sCk[cc * 8 * PS + k4 * 4];
+      if (!tri) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int cc = 0; cc < NQT; ++cc) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
+      } else {
+        // C upper triangular: rows k >= 8*(cc+1) of tile column cc are zero, skip them
+        const int kbase = kc * BM_KC + k4 * 4;
+#pragma unroll
+        for (int cc = 0; cc < NQT; ++cc)
+          if (kbase < (cc + 1) * 8) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
+          }
+      }
+    }
+    if (++kc == nk) {
+      const int64_t row0 = (blockIdx.x + ti * gridDim.x) * BM_RT;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int64_t row = row0 + warp * 16 + r * 8 + (lane >> 2);
+#pragma unroll
+        for (int cc = 0; cc < NQT; ++cc) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = cc * 8 + (lane & 3) * 2 + e;
+            if (row < n && col < q) {
+              double* dst = Y + row + (int64_t)col * ldy;
+              double v = alpha * acc[r][cc][e];
+              if (beta != 0.0) v += beta * (*dst);
+              *dst = v;
+            }
+            acc[r][cc][e] = 0.0;
+          }
+        }
+      }
+      kc = 0;
+      ++ti;
+    }
+  }
+  cp_async_wait<0>();
+}
+
 template <int NQT>
 void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc,
-                     int q, double alpha, double beta, double* Y, int64_t ldy) {
+                     int q, double alpha, double beta, double* Y, int64_t ldy, bool tri) {
   constexpr int QB = NQT * 8;
   constexpr size_t smem = (size_t)BM_STAGES * (BM_KC * BM_SV + QB * BM_SC) * sizeof(double);
   static bool attr_set = false;
+  static int num_sms = 0, occ_a = 0, occ_u = 0;
   if (!attr_set) {
     DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_kernel<NQT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_kernel<NQT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_persistent_kernel<NQT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_persistent_kernel<NQT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int dev = 0;
+    DLB_CUDA_CHECK(cudaGetDevice(&dev));
+    DLB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
   const bool al16 = aligned16(V) && (ldv % 2 == 0);
-  const unsigned grid = (unsigned)((n + BM_RT - 1) / BM_RT);
+  const int64_t ntiles = (n + BM_RT - 1) / BM_RT;
+  // persistent path: C resident in shared memory
+  const int p16 = (p + 15) / 16 * 16;
+  const int PS = p16 + 4;
+  const size_t smem_p = ((size_t)QB * PS + (size_t)BM_STAGES * BM_KC * BM_SV) * sizeof(double);
+  if (smem_p <= 110 * 1024 && ntiles >= 2) {
+    int occ = 0;
+    if (al16)
+      DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blockmul_persistent_kernel<NQT, true>, BM_THREADS, smem_p));
+    else
+      DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blockmul_persistent_kernel<NQT, false>, BM_THREADS, smem_p));
+    (void)occ_a; (void)occ_u;
+    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * std::max(1, occ));
+    if (al16)
+      blockmul_persistent_kernel<NQT, true><<<grid, BM_THREADS, smem_p, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0);
+    else
+      blockmul_persistent_kernel<NQT, false><<<grid, BM_THREADS, smem_p, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0);
+    ++g_launches;
+    return;
+  }
+  const unsigned grid = (unsigned)ntiles;
   if (al16)
     blockmul_kernel<NQT, true><<<grid, BM_THREADS, smem, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy);
   else
@@ -397,18 +586,18 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
 }  // namespace
 
 void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc, int q,
-               double alpha, double beta, double* Y, int64_t ldy) {
+               double alpha, double beta, double* Y, int64_t ldy, bool upper_tri) {
   if (n <= 0 || q <= 0) return;
   for (int q0 = 0; q0 < q; q0 += 128) {
     const int qb = std::min(128, q - q0);
     const double* Cb = C + (size_t)q0 * ldc;
     double* Yb = Y + (int64_t)q0 * ldy;
     if (qb <= 40)
-      launch_blockmul<5>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy);
+      launch_blockmul<5>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy, upper_tri && q0 == 0);
     else if (qb <= 80)
-      launch_blockmul<10>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy);
+      launch_blockmul<10>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy, upper_tri && q0 == 0);
     else
-      launch_blockmul<16>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy);
+      launch_blockmul<16>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy, upper_tri && q0 == 0);
   }
   DLB_CUDA_CHECK(cudaGetLastError());
 }
@@ -419,13 +608,13 @@ void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, 
 // not been overwritten yet (U_new(:,j) depends on U(:,0..j) only).
 void block_trmm_inplace(cudaStream_t st, int64_t n, double* U, int64_t ldu, int m, const double* T) {
   if (m <= 128) {
-    block_mul(st, n, U, ldu, m, T, m, m, 1.0, 0.0, U, ldu);
+    block_mul(st, n, U, ldu, m, T, m, m, 1.0, 0.0, U, ldu, true);
     return;
   }
   const int nblk = (m + 127) / 128;
   for (int b = nblk - 1; b >= 0; --b) {
     const int q0 = b * 128, qb = std::min(128, m - q0);
-    block_mul(st, n, U, ldu, q0 + qb, T + (size_t)q0 * m, m, qb, 1.0, 0.0, U + (int64_t)q0 * ldu, ldu);
+    block_mul(st, n, U, ldu, q0 + qb, T + (size_t)q0 * m, m, qb, 1.0, 0.0, U + (int64_t)q0 * ldu, ldu, false);
   }
 }
 

@@ -25,7 +25,7 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
 // diaglib.f90:322,324,420,421,495,497,1717,1721,3544 and dtrmm('r','l','t','n') at 3327
 // (with C = L^-T stored as a full matrix with an explicit zero triangle).
 void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc, int q,
-               double alpha, double beta, double* Y, int64_t ldy);
+               double alpha, double beta, double* Y, int64_t ldy, bool upper_tri = false);
 
 // U <- U * T, T upper triangular m x m (ld m), in place (dtrmm at diaglib.f90:3327).
 void block_trmm_inplace(cudaStream_t st, int64_t n, double* U, int64_t ldu, int m, const double* T);

@@ -1,0 +1,71 @@
+"""Times (and, under ncu, exposes) the two dominant kernel families at the C3 shapes.
+usage: python tools/kernel_bench.py [log2n=22] [reps=3]"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import diaglib_b200 as D  # noqa: E402
+from diaglib_b200 import kernels as K  # noqa: E402
+
+
+def main():
+    log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 22
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    n = 1 << log2n
+    D.init(0)
+    lib = D.lib()
+    v = K.DeviceArray((n, 111))
+    w = K.DeviceArray((n, 111))
+    lib.diaglib_b200_k_fill_uniform(v.ptr, n, 111, n, 1)
+    lib.diaglib_b200_k_fill_uniform(w.ptr, n, 111, n, 777)
+    out = {}
+
+    def t_gram(p, q, sym, a, b, tag):
+        c = K.DeviceArray((p, q))
+        lib.diaglib_b200_k_gram(n, a.ptr, n, p, b.ptr, n, q, c.ptr, p, sym)
+        lib.diaglib_b200_sync()
+        K.timer_start()
+        for _ in range(reps):
+            lib.diaglib_b200_k_gram(n, a.ptr, n, p, b.ptr, n, q, c.ptr, p, sym)
+        ms = K.timer_stop_ms() / reps
+        fl = n * p * (p + 1) if sym else 2.0 * n * p * q
+        by = 8.0 * n * ((p if a is b else p + q))
+        out[tag] = dict(ms=round(ms, 4), tflops=round(fl / ms / 1e9, 2), gbs=round(by / ms / 1e6, 1))
+        c.free()
+
+    def t_bmul(p, q, tag, inplace=False, tri=False):
+        cm = np.asfortranarray(np.triu(np.random.default_rng(0).standard_normal((p, q))) if tri
+                               else np.random.default_rng(0).standard_normal((p, q)))
+        cd = K.DeviceArray.from_numpy(cm)
+        y = v if inplace else K.DeviceArray((n, q))
+        lib.diaglib_b200_k_block_mul(n, v.ptr, n, p, cd.ptr, p, q, 1.0, 0.0, y.ptr, n)
+        lib.diaglib_b200_sync()
+        K.timer_start()
+        for _ in range(reps):
+            lib.diaglib_b200_k_block_mul(n, v.ptr, n, p, cd.ptr, p, q, 1.0, 0.0, y.ptr, n)
+        ms = K.timer_stop_ms() / reps
+        fl = 2.0 * n * p * q
+        by = 8.0 * n * (p + q)
+        out[tag] = dict(ms=round(ms, 4), tflops=round(fl / ms / 1e9, 2), gbs=round(by / ms / 1e6, 1))
+        cd.free()
+        if not inplace:
+            y.free()
+
+    t_gram(111, 111, 1, v, w, "gram_sym_111")
+    t_gram(74, 74, 1, v, w, "gram_sym_74")
+    t_gram(37, 37, 1, v, v, "gram_sym_37_same")
+    t_gram(74, 37, 0, v, w, "gram_74x37")
+    t_gram(111, 37, 0, v, w, "gram_111x37")
+    t_bmul(111, 37, "bmul_111x37")
+    t_bmul(111, 74, "bmul_111x74")
+    t_bmul(74, 37, "bmul_74x37")
+    t_bmul(37, 37, "bmul_37x37")
+    print(json.dumps(dict(n=n, **out)))
+
+
+if __name__ == "__main__":
+    main()
