@@ -32,8 +32,46 @@ constexpr int GR_MAXB = 128;       // max p / q handled by one launch
 // so that all 16 warps have work even for narrow blocks, and balances the tasks over the
 // four SM sub-partitions (warp id mod 4), which matters for the triangular (sym_lower) case.
 struct GramTask {
-  uint8_t ti0, tj0, tmask, pad;
+  uint8_t ti0, tj0;
+  uint8_t nc0, nc1;  // number of tiles computed in frame row 0 / row 1 (a prefix tj0 .. tj0+nc-1)
 };
+
+// All k-steps of one stage for one task, specialised on the tile counts of the two frame rows
+// so that the inner loop is branch free (the counts are warp-uniform but only known at run time;
+// the dispatch happens once per stage, outside the k loop).
+template <int NC0, int NC1>
+__device__ __forceinline__ void gram_task(double (&acc)[2][4][2], const double* pa, const double* pb, int KT, int S) {
+  constexpr int NB = NC0 > NC1 ? NC0 : NC1;
+  for (int k8 = 0; k8 < KT; k8 += 16) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int k = k8 + ks * 4;
+      double a0 = 0.0, a1 = 0.0, b[NB > 0 ? NB : 1];
+      if (NC0 > 0) a0 = pa[k];
+      if (NC1 > 0) a1 = pa[8 * S + k];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) b[c] = pb[c * 8 * S + k];
+#pragma unroll
+      for (int c = 0; c < NC0; ++c) dmma884(acc[0][c][0], acc[0][c][1], a0, b[c]);
+#pragma unroll
+      for (int c = 0; c < NC1; ++c) dmma884(acc[1][c][0], acc[1][c][1], a1, b[c]);
+    }
+  }
+}
+
+__device__ __forceinline__ void gram_task_dispatch(int nc0, int nc1, double (&acc)[2][4][2], const double* pa,
+                                                   const double* pb, int KT, int S) {
+#define DLB_CASE(A, B) case (A) * 5 + (B): gram_task<A, B>(acc, pa, pb, KT, S); break;
+  switch (nc0 * 5 + nc1) {
+    DLB_CASE(0, 1) DLB_CASE(0, 2) DLB_CASE(0, 3) DLB_CASE(0, 4)
+    DLB_CASE(1, 0) DLB_CASE(1, 1) DLB_CASE(1, 2) DLB_CASE(1, 3) DLB_CASE(1, 4)
+    DLB_CASE(2, 0) DLB_CASE(2, 1) DLB_CASE(2, 2) DLB_CASE(2, 3) DLB_CASE(2, 4)
+    DLB_CASE(3, 0) DLB_CASE(3, 1) DLB_CASE(3, 2) DLB_CASE(3, 3) DLB_CASE(3, 4)
+    DLB_CASE(4, 0) DLB_CASE(4, 1) DLB_CASE(4, 2) DLB_CASE(4, 3) DLB_CASE(4, 4)
+    default: break;
+  }
+#undef DLB_CASE
+}
 struct GramSched {
   GramTask t[GR_WARPS][2];
 };
@@ -111,43 +149,8 @@ gram_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const d
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const GramTask t = s == 0 ? t0 : t1;
-      if (t.tmask == 0) continue;
-      const double* pa = sA + (t.ti0 * 8) * S + frag_off;
-      const double* pb = sB + (t.tj0 * 8) * S + frag_off;
-      if (t.tmask == 0xFF) {
-        for (int k8 = 0; k8 < KT; k8 += 16) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            double a[2], b[4];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) a[r] = pa[r * 8 * S + k8 + ks * 4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) b[c] = pb[c * 8 * S + k8 + ks * 4];
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-              for (int c = 0; c < 4; ++c) dmma884(acc[s][r][c][0], acc[s][r][c][1], a[r], b[c]);
-          }
-        }
-      } else {
-        const bool ra0 = (t.tmask & 0x0F) != 0, ra1 = (t.tmask & 0xF0) != 0;
-        for (int k8 = 0; k8 < KT; k8 += 16) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            double a[2] = {0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
-            if (ra0) a[0] = pa[k8 + ks * 4];
-            if (ra1) a[1] = pa[8 * S + k8 + ks * 4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (t.tmask & (0x11 << c)) b[c] = pb[c * 8 * S + k8 + ks * 4];
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if (t.tmask & (1 << (r * 4 + c))) dmma884(acc[s][r][c][0], acc[s][r][c][1], a[r], b[c]);
-          }
-        }
-      }
+      if ((t.nc0 | t.nc1) == 0) continue;
+      gram_task_dispatch(t.nc0, t.nc1, acc[s], sA + (t.ti0 * 8) * S + frag_off, sB + (t.tj0 * 8) * S + frag_off, KT, S);
     }
   }
   cp_async_wait<0>();
@@ -161,7 +164,7 @@ gram_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const d
     for (int r = 0; r < 2; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        if (t.tmask & (1 << (r * 4 + c))) {
+        if (c < (r == 0 ? t.nc0 : t.nc1)) {
           const int i = (t.ti0 + r) * 8 + (lane >> 2);
           const int j = (t.tj0 + c) * 8 + (lane & 3) * 2;
           out[i + (size_t)j * PB] = acc[s][r][c][0];
@@ -196,7 +199,7 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, int ncta,
 
 // Build a balanced task schedule for a p x q block (tile counts ntp x ntq).
 GramSched make_sched(int ntp, int ntq, bool sym_lower) {
-  struct T { int ti0, tj0, mask, cnt; };
+  struct T { int ti0, tj0, nc0, nc1, cnt; };
   const int shapes[4][2] = {{2, 4}, {2, 2}, {1, 2}, {1, 1}};
   std::vector<T> tasks;
   for (int sh = 0; sh < 4; ++sh) {
@@ -204,13 +207,13 @@ GramSched make_sched(int ntp, int ntq, bool sym_lower) {
     tasks.clear();
     for (int ti0 = 0; ti0 < ntp; ti0 += tr)
       for (int tj0 = 0; tj0 < ntq; tj0 += tc) {
-        int mask = 0, cnt = 0;
+        int nc[2] = {0, 0};
         for (int r = 0; r < tr; ++r)
           for (int c = 0; c < tc; ++c) {
             const int ti = ti0 + r, tj = tj0 + c;
-            if (ti < ntp && tj < ntq && (!sym_lower || tj <= ti)) { mask |= 1 << (r * 4 + c); ++cnt; }
+            if (ti < ntp && tj < ntq && (!sym_lower || tj <= ti)) nc[r] = c + 1;  // valid tiles form a prefix
           }
-        if (cnt) tasks.push_back({ti0, tj0, mask, cnt});
+        if (nc[0] + nc[1]) tasks.push_back({ti0, tj0, nc[0], nc[1], nc[0] + nc[1]});
       }
     // the coarsest shape that keeps every warp busy; finer shapes only if they still fit 32 slots
     if ((int)tasks.size() >= GR_WARPS || sh == 3) break;
@@ -243,7 +246,7 @@ GramSched make_sched(int ntp, int ntq, bool sym_lower) {
     int bw = -1;
     for (int w = bq; w < GR_WARPS; w += 4)
       if (nslot[w] < 2 && (bw < 0 || load_w[w] < load_w[bw])) bw = w;
-    s.t[bw][nslot[bw]] = GramTask{(uint8_t)t.ti0, (uint8_t)t.tj0, (uint8_t)t.mask, 0};
+    s.t[bw][nslot[bw]] = GramTask{(uint8_t)t.ti0, (uint8_t)t.tj0, (uint8_t)t.nc0, (uint8_t)t.nc1};
     ++nslot[bw];
     load_w[bw] += t.cnt;
     load_q[bq] += t.cnt;

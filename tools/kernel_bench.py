@@ -55,6 +55,12 @@ def main():
         if not inplace:
             y.free()
 
+    only = sys.argv[3] if len(sys.argv) > 3 else ""
+    if only == "bmul":
+        t_bmul(111, 37, "bmul_111x37")
+        t_bmul(37, 37, "bmul_37x37")
+        print(json.dumps(dict(n=n, **out)))
+        return
     t_gram(111, 111, 1, v, w, "gram_sym_111")
     t_gram(74, 74, 1, v, w, "gram_sym_74")
     t_gram(37, 37, 1, v, v, "gram_sym_37_same")
