@@ -14,6 +14,8 @@
 
 namespace dlb {
 
+bool g_disable_ws = false;  // DIAGLIB_B200_NO_WS=1: fall back to the cp.async kernels (A/B testing)
+
 // =====================================================================================
 // gram_tn
 // =====================================================================================
@@ -173,6 +175,107 @@ gram_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const d
   }
 }
 
+// Warp-specialised variant of gram_kernel: a 17th warp is the producer and feeds the ring with
+// 1-D bulk async copies (TMA engine; one KT*8-byte column segment per copy, completion counted
+// on full[stage]); the 16 consumer warps never meet at a CTA-wide barrier.
+constexpr int GRW_THREADS = GR_THREADS;   // 15 consumer warps + 1 producer warp
+constexpr int GRW_CONS = GR_WARPS - 1;
+
+__global__ void __launch_bounds__(GRW_THREADS, 1)
+gram_ws_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const double* __restrict__ B, int64_t ldb,
+               int q, int same, int KT, const __grid_constant__ GramSched sched, double* __restrict__ partial, int PB,
+               int QB) {
+  extern __shared__ __align__(16) double smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + GR_STAGES;
+  double* ring = smem + 2 * GR_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = KT + 4;
+  const int stage_doubles = (PB + (same ? 0 : QB)) * S;
+  const int64_t nchunks = (n + KT - 1) / KT;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t my_chunks = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < GR_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GRW_CONS); }
+    mbar_fence_init();
+  }
+  // columns p..PB-1 (q..QB-1) are never loaded: keep them finite
+  for (int id = tid; id < GR_STAGES * stage_doubles; id += GRW_THREADS) ring[id] = 0.0;
+  fence_proxy_async();
+  __syncthreads();
+
+  if (warp == GRW_CONS) {
+    // ---------------- producer ----------------
+    int s = 0;
+    uint32_t ph = 0;
+    const int ncopy = p + (same ? 0 : q);
+    for (int64_t it = 0; it < my_chunks; ++it) {
+      const int64_t k0 = (first + it * stride) * KT;
+      const int64_t rem = n - k0;
+      const uint32_t rows = rem < KT ? (uint32_t)rem : (uint32_t)KT;
+      double* st = ring + (size_t)s * stage_doubles;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (rows < (uint32_t)KT) {
+        // last chunk of the block: rows beyond n must contribute zero
+        for (int c = lane; c < ncopy; c += 32) {
+          double* d = st + (c < p ? c : PB + (c - p)) * S;
+          for (int r = rows; r < KT; ++r) d[r] = 0.0;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)ncopy * rows * 8u);
+      __syncwarp();
+      for (int c = lane; c < ncopy; c += 32) {
+        if (c < p) bulk_g2s(st + c * S, A + (int64_t)c * lda + k0, rows * 8u, &full[s]);
+        else bulk_g2s(st + (PB + (c - p)) * S, B + (int64_t)(c - p) * ldb + k0, rows * 8u, &full[s]);
+      }
+      if (++s == GR_STAGES) { s = 0; ph ^= 1; }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const GramTask t0 = sched.t[warp][0], t1 = sched.t[warp][1];
+  double acc[2][2][4][2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[s][r][c][0] = acc[s][r][c][1] = 0.0;
+  const int frag_off = (lane >> 2) * S + (lane & 3);
+  int s = 0;
+  uint32_t ph = 0;
+  for (int64_t it = 0; it < my_chunks; ++it) {
+    mbar_wait(&full[s], ph);
+    const double* sA = ring + (size_t)s * stage_doubles;
+    const double* sB = same ? sA : sA + PB * S;
+    if ((t0.nc0 | t0.nc1) != 0)
+      gram_task_dispatch(t0.nc0, t0.nc1, acc[0], sA + (t0.ti0 * 8) * S + frag_off, sB + (t0.tj0 * 8) * S + frag_off, KT, S);
+    if ((t1.nc0 | t1.nc1) != 0)
+      gram_task_dispatch(t1.nc0, t1.nc1, acc[1], sA + (t1.ti0 * 8) * S + frag_off, sB + (t1.tj0 * 8) * S + frag_off, KT, S);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == GR_STAGES) { s = 0; ph ^= 1; }
+  }
+  double* out = partial + (size_t)blockIdx.x * PB * QB;
+#pragma unroll
+  for (int sl = 0; sl < 2; ++sl) {
+    const GramTask t = sl == 0 ? t0 : t1;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < (r == 0 ? t.nc0 : t.nc1)) {
+          const int i = (t.ti0 + r) * 8 + (lane >> 2);
+          const int j = (t.tj0 + c) * 8 + (lane & 3) * 2;
+          out[i + (size_t)j * PB] = acc[sl][r][c][0];
+          out[i + (size_t)(j + 1) * PB] = acc[sl][r][c][1];
+        }
+  }
+}
+
 // deterministic (fixed-order) sum of the per-CTA partials; mirrors the lower triangle if sym
 __global__ void gram_reduce_kernel(const double* __restrict__ partial, int ncta, int PB, int QB, int p, int q,
                                    int sym, double* __restrict__ C, int ldc, double* __restrict__ Ct) {
@@ -198,7 +301,7 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, int ncta,
 }
 
 // Build a balanced task schedule for a p x q block (tile counts ntp x ntq).
-GramSched make_sched(int ntp, int ntq, bool sym_lower) {
+GramSched make_sched(int ntp, int ntq, bool sym_lower, int nwarps) {
   struct T { int ti0, tj0, nc0, nc1, cnt; };
   const int shapes[4][2] = {{2, 4}, {2, 2}, {1, 2}, {1, 1}};
   std::vector<T> tasks;
@@ -216,7 +319,7 @@ GramSched make_sched(int ntp, int ntq, bool sym_lower) {
         if (nc[0] + nc[1]) tasks.push_back({ti0, tj0, nc[0], nc[1], nc[0] + nc[1]});
       }
     // the coarsest shape that keeps every warp busy; finer shapes only if they still fit 32 slots
-    if ((int)tasks.size() >= GR_WARPS || sh == 3) break;
+    if ((int)tasks.size() >= nwarps || sh == 3) break;
     // peek: would the next finer shape overflow the 2 slots per warp?
     const int ntr = shapes[sh + 1][0], ntc = shapes[sh + 1][1];
     int nxt = 0;
@@ -228,7 +331,7 @@ GramSched make_sched(int ntp, int ntq, bool sym_lower) {
             any = (ti0 + r < ntp && tj0 + c < ntq && (!sym_lower || tj0 + c <= ti0 + r));
         nxt += any;
       }
-    if (nxt > 2 * GR_WARPS) break;
+    if (nxt > 2 * nwarps) break;
   }
   std::stable_sort(tasks.begin(), tasks.end(), [](const T& a, const T& b) { return a.cnt > b.cnt; });
   GramSched s{};
@@ -240,12 +343,14 @@ GramSched make_sched(int ntp, int ntq, bool sym_lower) {
     int bq = -1;
     for (int qd = 0; qd < 4; ++qd) {
       bool has_free = false;
-      for (int w = qd; w < GR_WARPS; w += 4) has_free |= nslot[w] < 2;
+      for (int w = qd; w < nwarps; w += 4) has_free |= nslot[w] < 2;
       if (has_free && (bq < 0 || load_q[qd] < load_q[bq])) bq = qd;
     }
     int bw = -1;
-    for (int w = bq; w < GR_WARPS; w += 4)
+    if (bq >= 0)
+    for (int w = bq; w < nwarps; w += 4)
       if (nslot[w] < 2 && (bw < 0 || load_w[w] < load_w[bw])) bw = w;
+    if (bw < 0) { std::fprintf(stderr, "diaglib_b200: gram schedule overflow\n"); std::abort(); }
     s.t[bw][nslot[bw]] = GramTask{(uint8_t)t.ti0, (uint8_t)t.tj0, (uint8_t)t.nc0, (uint8_t)t.nc1};
     ++nslot[bw];
     load_w[bw] += t.cnt;
@@ -290,13 +395,22 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
       const double* Ab = A + (int64_t)p0 * lda;
       const double* Bb = B + (int64_t)q0 * ldb;
       const int same = (Ab == Bb && lda == ldb && pb == qb) ? 1 : 0;
-      const GramSched sched = make_sched(ntp, ntq, diag_blk);
+      const bool use_ws = al16 && (n % 2 == 0) && !g_disable_ws && ((ntp + 1) / 2) * ((ntq + 3) / 4) <= 2 * GRW_CONS;
+      const GramSched sched = make_sched(ntp, ntq, diag_blk, use_ws ? GRW_CONS : GR_WARPS);
       const int cols = PB + (same ? 0 : QB);
       const int KT = pick_kt(cols);
       const int64_t nchunks = (n + KT - 1) / KT;
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, nchunks));
       const size_t smem = (size_t)GR_STAGES * cols * (KT + 4) * sizeof(double);
-      if (al16)
+      if (use_ws) {
+        static bool ws_attr = false;
+        if (!ws_attr) {
+          DLB_CUDA_CHECK(cudaFuncSetAttribute(gram_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          ws_attr = true;
+        }
+        gram_ws_kernel<<<grid, GRW_THREADS, smem + 2 * GR_STAGES * sizeof(double), st>>>(n, Ab, lda, pb, Bb, ldb, qb, same,
+                                                                                        KT, sched, partial, PB, QB);
+      } else if (al16)
         gram_kernel<true><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
       else
         gram_kernel<false><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
@@ -540,6 +654,127 @@ blockmul_persistent_kernel(int64_t n, const double* __restrict__ V, int64_t ldv,
   cp_async_wait<0>();
 }
 
+// Warp-specialised variant: one producer warp feeds the shared-memory ring with 1-D bulk async
+// copies (TMA engine, one 1 KB column segment per copy, completion counted on an mbarrier) and
+// eight consumer warps run the DMMA loop.  There is no CTA-wide barrier in the main loop:
+// consumers wait on full[stage], release the stage on empty[stage], and drift freely, which
+// keeps the FP64 tensor pipe busy while other warps wait for data.
+constexpr int BMW_CONS = 8;                       // consumer warps (16 rows each)
+constexpr int BMW_THREADS = (BMW_CONS + 1) * 32;  // + producer warp
+constexpr int BMW_STAGES = 4;
+
+template <int NQT>
+__global__ void __launch_bounds__(BMW_THREADS)
+blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, const double* __restrict__ C, int ldc,
+                   int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int QB = NQT * 8;
+  constexpr int STAGE = BM_KC * BM_SV;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // BMW_STAGES
+  uint64_t* empty = full + BMW_STAGES;                   // BMW_STAGES
+  double* sC = smem + 2 * BMW_STAGES;                    // [QB][PS], zero padded
+  double* ring = sC + (size_t)QB * PS;                   // BMW_STAGES x STAGE
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nk = (p + BM_KC - 1) / BM_KC;
+  const int64_t ntiles = (n + BM_RT - 1) / BM_RT;
+  const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < BMW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BMW_CONS); }
+    mbar_fence_init();
+  }
+  for (int id = tid; id < QB * PS; id += BMW_THREADS) {
+    const int j = id / PS, k = id - j * PS;
+    sC[id] = (j < q && k < p) ? C[(size_t)j * ldc + k] : 0.0;
+  }
+  for (int id = tid; id < BMW_STAGES * STAGE; id += BMW_THREADS) ring[id] = 0.0;  // stale data must stay finite
+  fence_proxy_async();
+  __syncthreads();
+
+  if (warp == BMW_CONS) {
+    // ---------------- producer ----------------
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t ti = 0; ti < my_tiles; ++ti) {
+      const int64_t row0 = (blockIdx.x + ti * gridDim.x) * BM_RT;
+      const int64_t rem = n - row0;
+      const uint32_t rows = rem < BM_RT ? (uint32_t)rem : (uint32_t)BM_RT;
+      for (int kc = 0; kc < nk; ++kc) {
+        const int k0 = kc * BM_KC;
+        const int ncols = (p - k0) < BM_KC ? (p - k0) : BM_KC;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)ncols * rows * 8u);
+        __syncwarp();
+        if (lane < ncols)
+          bulk_g2s(ring + (size_t)s * STAGE + lane * BM_SV, V + (int64_t)(k0 + lane) * ldv + row0, rows * 8u, &full[s]);
+        if (++s == BMW_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ---------------- consumers ----------------
+    double acc[2][NQT][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < NQT; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+    const int a_off = (lane & 3) * BM_SV + warp * 16 + (lane >> 2);
+    const int b_off = (lane >> 2) * PS + (lane & 3);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t ti = 0; ti < my_tiles; ++ti) {
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(&full[s], ph);
+        const double* sV = ring + (size_t)s * STAGE;
+        const double* sCk = sC + kc * BM_KC + b_off;
+#pragma unroll
+        for (int k4 = 0; k4 < BM_KC / 4; ++k4) {
+          double a[2], b[NQT];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * BM_SV + a_off + r * 8];
+#pragma unroll
+          for (int cc = 0; cc < NQT; ++cc) b[cc] = sCk[cc * 8 * PS + k4 * 4];
+          if (!tri) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int cc = 0; cc < NQT; ++cc) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
+          } else {
+            const int kbase = kc * BM_KC + k4 * 4;
+#pragma unroll
+            for (int cc = 0; cc < NQT; ++cc)
+              if (kbase < (cc + 1) * 8) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
+              }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == BMW_STAGES) { s = 0; ph ^= 1; }
+      }
+      const int64_t row0 = (blockIdx.x + ti * gridDim.x) * BM_RT;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int64_t row = row0 + warp * 16 + r * 8 + (lane >> 2);
+#pragma unroll
+        for (int cc = 0; cc < NQT; ++cc) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = cc * 8 + (lane & 3) * 2 + e;
+            if (row < n && col < q) {
+              double* dst = Y + row + (int64_t)col * ldy;
+              double v = alpha * acc[r][cc][e];
+              if (beta != 0.0) v += beta * (*dst);
+              *dst = v;
+            }
+            acc[r][cc][e] = 0.0;
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int NQT>
 void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc,
                      int q, double alpha, double beta, double* Y, int64_t ldy, bool tri) {
@@ -563,6 +798,20 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
   const int p16 = (p + 15) / 16 * 16;
   const int PS = p16 + 4;
   const size_t smem_p = ((size_t)QB * PS + (size_t)BM_STAGES * BM_KC * BM_SV) * sizeof(double);
+  const size_t smem_w = (2 * BMW_STAGES + (size_t)QB * PS + (size_t)BMW_STAGES * BM_KC * BM_SV) * sizeof(double);
+  if (al16 && (n % 2 == 0) && smem_w <= 110 * 1024 && ntiles >= 2 && !g_disable_ws) {
+    static bool ws_attr = false;
+    static int occ_ws = 1;
+    if (!ws_attr) {
+      DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_ws_kernel<NQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      ws_attr = true;
+    }
+    DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ws, blockmul_ws_kernel<NQT>, BMW_THREADS, smem_w));
+    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * std::max(1, occ_ws));
+    blockmul_ws_kernel<NQT><<<grid, BMW_THREADS, smem_w, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0);
+    ++g_launches;
+    return;
+  }
   if (smem_p <= 110 * 1024 && ntiles >= 2) {
     int occ = 0;
     if (al16)
