@@ -66,6 +66,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// makes the calling thread's prior cp.async copies arrive on the mbarrier when they land
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 // contiguous global -> shared copy of `bytes` (multiple of 16, both addresses 16-byte aligned),
 // completion is signalled on the mbarrier as transaction bytes
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

@@ -78,14 +78,14 @@ struct GramSched {
   GramTask t[GR_WARPS][2];
 };
 
-template <bool ALIGN16>
+template <bool ALIGN16, int NT = GR_THREADS>
 __device__ __forceinline__ void gram_load_stage(double* s, const double* __restrict__ M, int64_t ld, int ncols,
                                                 int64_t k0, int64_t n, int tid, int KT) {
   const int S = KT + 4;
   if (ALIGN16) {
     const int half = KT >> 1;
     const int total = ncols * half;
-    for (int id = tid; id < total; id += GR_THREADS) {
+    for (int id = tid; id < total; id += NT) {
       const int col = id / half, part = id - col * half;
       const int64_t row = k0 + part * 2;
       int64_t rem = (n - row) * 8;
@@ -95,7 +95,7 @@ __device__ __forceinline__ void gram_load_stage(double* s, const double* __restr
     }
   } else {
     const int total = ncols * KT;
-    for (int id = tid; id < total; id += GR_THREADS) {
+    for (int id = tid; id < total; id += NT) {
       const int col = id / KT, part = id - col * KT;
       const int64_t row = k0 + part;
       const int bytes = row < n ? 8 : 0;
@@ -276,6 +276,95 @@ gram_ws_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, cons
   }
 }
 
+// Warp-specialised variant with cp.async producers: two producer warps issue the 16-byte
+// LDGSTS copies of a stage and signal full[stage] through cp.async.mbarrier.arrive; fourteen
+// consumer warps run the DMMA tasks.  Used for wide blocks, where the column segments of a
+// stage are too short (256-512 B) for the bulk-copy engine to reach HBM bandwidth.
+constexpr int GRC_PROD = 2;
+constexpr int GRC_CONS = GR_WARPS - GRC_PROD;
+
+template <bool ALIGN16>
+__global__ void __launch_bounds__(GR_THREADS, 1)
+gram_wsc_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const double* __restrict__ B, int64_t ldb,
+                int q, int same, int KT, const __grid_constant__ GramSched sched, double* __restrict__ partial, int PB,
+                int QB) {
+  extern __shared__ __align__(16) double smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + GR_STAGES;
+  double* ring = smem + 2 * GR_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = KT + 4;
+  const int stage_doubles = (PB + (same ? 0 : QB)) * S;
+  const int64_t nchunks = (n + KT - 1) / KT;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t my_chunks = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < GR_STAGES; ++s) { mbar_init(&full[s], GRC_PROD * 32); mbar_init(&empty[s], GRC_CONS); }
+    mbar_fence_init();
+  }
+  for (int id = tid; id < GR_STAGES * stage_doubles; id += GR_THREADS) ring[id] = 0.0;
+  __syncthreads();
+
+  if (warp >= GRC_CONS) {
+    // ---------------- producers ----------------
+    const int ptid = tid - GRC_CONS * 32;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t it = 0; it < my_chunks; ++it) {
+      const int64_t k0 = (first + it * stride) * KT;
+      double* st = ring + (size_t)s * stage_doubles;
+      mbar_wait(&empty[s], ph ^ 1);
+      gram_load_stage<ALIGN16, GRC_PROD * 32>(st, A, lda, p, k0, n, ptid, KT);
+      if (!same) gram_load_stage<ALIGN16, GRC_PROD * 32>(st + PB * S, B, ldb, q, k0, n, ptid, KT);
+      cp_async_mbar_arrive_noinc(&full[s]);
+      if (++s == GR_STAGES) { s = 0; ph ^= 1; }
+    }
+    cp_async_wait<0>();
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const GramTask t0 = sched.t[warp][0], t1 = sched.t[warp][1];
+  double acc[2][2][4][2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[s][r][c][0] = acc[s][r][c][1] = 0.0;
+  const int frag_off = (lane >> 2) * S + (lane & 3);
+  int s = 0;
+  uint32_t ph = 0;
+  for (int64_t it = 0; it < my_chunks; ++it) {
+    mbar_wait(&full[s], ph);
+    const double* sA = ring + (size_t)s * stage_doubles;
+    const double* sB = same ? sA : sA + PB * S;
+    if ((t0.nc0 | t0.nc1) != 0)
+      gram_task_dispatch(t0.nc0, t0.nc1, acc[0], sA + (t0.ti0 * 8) * S + frag_off, sB + (t0.tj0 * 8) * S + frag_off, KT, S);
+    if ((t1.nc0 | t1.nc1) != 0)
+      gram_task_dispatch(t1.nc0, t1.nc1, acc[1], sA + (t1.ti0 * 8) * S + frag_off, sB + (t1.tj0 * 8) * S + frag_off, KT, S);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == GR_STAGES) { s = 0; ph ^= 1; }
+  }
+  double* out = partial + (size_t)blockIdx.x * PB * QB;
+#pragma unroll
+  for (int sl = 0; sl < 2; ++sl) {
+    const GramTask t = sl == 0 ? t0 : t1;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < (r == 0 ? t.nc0 : t.nc1)) {
+          const int i = (t.ti0 + r) * 8 + (lane >> 2);
+          const int j = (t.tj0 + c) * 8 + (lane & 3) * 2;
+          out[i + (size_t)j * PB] = acc[sl][r][c][0];
+          out[i + (size_t)(j + 1) * PB] = acc[sl][r][c][1];
+        }
+  }
+}
+
 // deterministic (fixed-order) sum of the per-CTA partials; mirrors the lower triangle if sym
 __global__ void gram_reduce_kernel(const double* __restrict__ partial, int ncta, int PB, int QB, int p, int q,
                                    int sym, double* __restrict__ C, int ldc, double* __restrict__ Ct) {
@@ -395,22 +484,32 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
       const double* Ab = A + (int64_t)p0 * lda;
       const double* Bb = B + (int64_t)q0 * ldb;
       const int same = (Ab == Bb && lda == ldb && pb == qb) ? 1 : 0;
-      const bool use_ws = al16 && (n % 2 == 0) && !g_disable_ws && ((ntp + 1) / 2) * ((ntq + 3) / 4) <= 2 * GRW_CONS;
-      const GramSched sched = make_sched(ntp, ntq, diag_blk, use_ws ? GRW_CONS : GR_WARPS);
       const int cols = PB + (same ? 0 : QB);
       const int KT = pick_kt(cols);
+      const int ncoarse = ((ntp + 1) / 2) * ((ntq + 3) / 4);
+      // bulk-copy producer: only when a column segment of a stage is >= 1 KB (narrow blocks);
+      // cp.async producers otherwise; the barrier-synchronised kernel is the fallback
+      const bool use_bulk = al16 && (n % 2 == 0) && !g_disable_ws && KT >= 128 && ncoarse <= 2 * GRW_CONS;
+      const bool use_wsc = !use_bulk && !g_disable_ws && ncoarse <= 2 * GRC_CONS;
+      const GramSched sched = make_sched(ntp, ntq, diag_blk, use_bulk ? GRW_CONS : (use_wsc ? GRC_CONS : GR_WARPS));
       const int64_t nchunks = (n + KT - 1) / KT;
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, nchunks));
       const size_t smem = (size_t)GR_STAGES * cols * (KT + 4) * sizeof(double);
-      if (use_ws) {
-        static bool ws_attr = false;
-        if (!ws_attr) {
-          DLB_CUDA_CHECK(cudaFuncSetAttribute(gram_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-          ws_attr = true;
-        }
-        gram_ws_kernel<<<grid, GRW_THREADS, smem + 2 * GR_STAGES * sizeof(double), st>>>(n, Ab, lda, pb, Bb, ldb, qb, same,
-                                                                                        KT, sched, partial, PB, QB);
-      } else if (al16)
+      const size_t smem_ws = smem + 2 * GR_STAGES * sizeof(double);
+      static bool ws_attr = false;
+      if (!ws_attr) {
+        DLB_CUDA_CHECK(cudaFuncSetAttribute(gram_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DLB_CUDA_CHECK(cudaFuncSetAttribute(gram_wsc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DLB_CUDA_CHECK(cudaFuncSetAttribute(gram_wsc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ws_attr = true;
+      }
+      if (use_bulk)
+        gram_ws_kernel<<<grid, GRW_THREADS, smem_ws, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
+      else if (use_wsc && al16)
+        gram_wsc_kernel<true><<<grid, GR_THREADS, smem_ws, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
+      else if (use_wsc)
+        gram_wsc_kernel<false><<<grid, GR_THREADS, smem_ws, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
+      else if (al16)
         gram_kernel<true><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
       else
         gram_kernel<false><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
