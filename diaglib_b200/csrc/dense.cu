@@ -9,12 +9,15 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is resolved through the runtime)
+
 #include <algorithm>
 #include <vector>
 
 namespace dlb {
 
-bool g_disable_ws = false;  // DIAGLIB_B200_NO_WS=1: fall back to the cp.async kernels (A/B testing)
+bool g_disable_ws = false;
+bool g_disable_tma = false;  // DIAGLIB_B200_NO_TMA=1: skip the cp.async.bulk.tensor gram kernel  // DIAGLIB_B200_NO_WS=1: fall back to the cp.async kernels (A/B testing)
 
 // =====================================================================================
 // gram_tn
@@ -365,6 +368,180 @@ gram_wsc_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, con
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// TMA-tiled variant (cp.async.bulk.tensor, SASS UTMALDG).  One elected producer lane issues
+// a 2-D box load per 16 rows of n per operand: box = {16 rows (128 B, the swizzle span), all
+// columns of the block}, SWIZZLE_128B, out-of-bounds rows/columns zero-filled by the hardware
+// (so the tail of n and the padding columns need no code).  Shared-memory image of a box:
+// column c occupies the 128-byte line c; its 16-byte chunk j (rows 2j, 2j+1) sits at chunk
+// j ^ (c & 7).  DMMA k-step s of a box uses rows {2s, 2s+1, 8+2s, 9+2s}: with that row choice
+// the 16 lanes of a half-warp hit 16 distinct 8-byte banks, i.e. fragment loads are conflict
+// free without any padding.  (Any row permutation is legal: both operands use the same one.)
+// ---------------------------------------------------------------------------------------
+constexpr int GT_BOX_ROWS = 16;
+constexpr int GT_LINE = 16;  // doubles per 128-byte line
+
+template <int NC0, int NC1>
+__device__ __forceinline__ void gram_task_tma(double (&acc)[2][4][2], const double* pa, const double* pb, int nbox,
+                                              int boxA, int boxB, const int (&koff)[4]) {
+  constexpr int NB = NC0 > NC1 ? NC0 : NC1;
+  for (int bx = 0; bx < nbox; ++bx) {
+    const double* a_ = pa + bx * boxA;
+    const double* b_ = pb + bx * boxB;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      double a0 = 0.0, a1 = 0.0, b[NB > 0 ? NB : 1];
+      if (NC0 > 0) a0 = a_[koff[s]];
+      if (NC1 > 0) a1 = a_[8 * GT_LINE + koff[s]];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) b[c] = b_[c * 8 * GT_LINE + koff[s]];
+#pragma unroll
+      for (int c = 0; c < NC0; ++c) dmma884(acc[0][c][0], acc[0][c][1], a0, b[c]);
+#pragma unroll
+      for (int c = 0; c < NC1; ++c) dmma884(acc[1][c][0], acc[1][c][1], a1, b[c]);
+    }
+  }
+}
+__device__ __forceinline__ void gram_task_tma_dispatch(int nc0, int nc1, double (&acc)[2][4][2], const double* pa,
+                                                       const double* pb, int nbox, int boxA, int boxB,
+                                                       const int (&koff)[4]) {
+#define DLB_CASE(A, B) case (A) * 5 + (B): gram_task_tma<A, B>(acc, pa, pb, nbox, boxA, boxB, koff); break;
+  switch (nc0 * 5 + nc1) {
+    DLB_CASE(0, 1) DLB_CASE(0, 2) DLB_CASE(0, 3) DLB_CASE(0, 4)
+    DLB_CASE(1, 0) DLB_CASE(1, 1) DLB_CASE(1, 2) DLB_CASE(1, 3) DLB_CASE(1, 4)
+    DLB_CASE(2, 0) DLB_CASE(2, 1) DLB_CASE(2, 2) DLB_CASE(2, 3) DLB_CASE(2, 4)
+    DLB_CASE(3, 0) DLB_CASE(3, 1) DLB_CASE(3, 2) DLB_CASE(3, 3) DLB_CASE(3, 4)
+    DLB_CASE(4, 0) DLB_CASE(4, 1) DLB_CASE(4, 2) DLB_CASE(4, 3) DLB_CASE(4, 4)
+    default: break;
+  }
+#undef DLB_CASE
+}
+
+__global__ void __launch_bounds__(GR_THREADS, 1)
+gram_tma_kernel(int64_t n, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int same,
+                int KT, const __grid_constant__ GramSched sched, double* __restrict__ partial, int PB, int QB) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // [ring: GR_STAGES x (nbox x (PB + QB) lines of 128 B)] [barriers]
+  const int nbox = KT / GT_BOX_ROWS;
+  const int boxA = PB * GT_LINE, boxB = QB * GT_LINE;                 // doubles per box
+  const int stage_doubles = nbox * (boxA + (same ? 0 : boxB));
+  // SWIZZLE_128B needs 1024-byte aligned boxes: align the ring explicitly (1 KB of slack is allocated)
+  double* ring = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)GR_STAGES * stage_doubles);
+  uint64_t* empty = full + GR_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t nchunks = (n + KT - 1) / KT;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t my_chunks = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < GR_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GRW_CONS); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+    if (!same) tma_prefetch_desc(&tmB);
+  }
+  __syncthreads();
+
+  if (warp == GRW_CONS) {
+    // ---------------- producer: one elected lane ----------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t bytes = (uint32_t)stage_doubles * 8u;
+      for (int64_t it = 0; it < my_chunks; ++it) {
+        const int64_t k0 = (first + it * stride) * KT;
+        double* st = ring + (size_t)s * stage_doubles;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], bytes);
+        for (int bx = 0; bx < nbox; ++bx) {
+          tma_load_2d(st + bx * boxA, &tmA, (int)(k0 + bx * GT_BOX_ROWS), 0, &full[s]);
+          if (!same) tma_load_2d(st + nbox * boxA + bx * boxB, &tmB, (int)(k0 + bx * GT_BOX_ROWS), 0, &full[s]);
+        }
+        if (++s == GR_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const GramTask t0 = sched.t[warp][0], t1 = sched.t[warp][1];
+  double acc[2][2][4][2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[s][r][c][0] = acc[s][r][c][1] = 0.0;
+  // per-lane fragment offsets (doubles) inside a box: column line i = lane>>2 of the 8-column
+  // tile, rows {2s, 2s+1, 8+2s, 9+2s}[lane&3], 16-byte chunks swizzled by the line index
+  const int i8 = lane >> 2, kk = lane & 3;
+  int koff[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) koff[s] = i8 * GT_LINE + ((((s + 4 * (kk >> 1)) ^ i8) << 1) | (kk & 1));
+  int s = 0;
+  uint32_t ph = 0;
+  for (int64_t it = 0; it < my_chunks; ++it) {
+    mbar_wait(&full[s], ph);
+    const double* sA = ring + (size_t)s * stage_doubles;
+    const double* sB = same ? sA : sA + nbox * boxA;
+    const int bB = same ? boxA : boxB;
+    if ((t0.nc0 | t0.nc1) != 0)
+      gram_task_tma_dispatch(t0.nc0, t0.nc1, acc[0], sA + t0.ti0 * 8 * GT_LINE, sB + t0.tj0 * 8 * GT_LINE, nbox, boxA, bB, koff);
+    if ((t1.nc0 | t1.nc1) != 0)
+      gram_task_tma_dispatch(t1.nc0, t1.nc1, acc[1], sA + t1.ti0 * 8 * GT_LINE, sB + t1.tj0 * 8 * GT_LINE, nbox, boxA, bB, koff);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == GR_STAGES) { s = 0; ph ^= 1; }
+  }
+  double* out = partial + (size_t)blockIdx.x * PB * QB;
+#pragma unroll
+  for (int sl = 0; sl < 2; ++sl) {
+    const GramTask t = sl == 0 ? t0 : t1;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < (r == 0 ? t.nc0 : t.nc1)) {
+          const int i = (t.ti0 + r) * 8 + (lane >> 2);
+          const int j = (t.tj0 + c) * 8 + (lane & 3) * 2;
+          out[i + (size_t)j * PB] = acc[sl][r][c][0];
+          out[i + (size_t)(j + 1) * PB] = acc[sl][r][c][1];
+        }
+  }
+}
+
+// host side: tensor map for an n x ncols column-major block (ld), box = {16 rows, box_cols}
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encoder() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+bool make_tmap(CUtensorMap* tm, const double* base, int64_t n, int ncols, int64_t ld, int box_cols) {
+  PFN_encodeTiled enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)ncols};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  cuuint32_t box[2] = {(cuuint32_t)GT_BOX_ROWS, (cuuint32_t)box_cols};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 // deterministic (fixed-order) sum of the per-CTA partials; mirrors the lower triangle if sym
 __global__ void gram_reduce_kernel(const double* __restrict__ partial, int ncta, int PB, int QB, int p, int q,
                                    int sym, double* __restrict__ C, int ldc, double* __restrict__ Ct) {
@@ -503,6 +680,34 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
         DLB_CUDA_CHECK(cudaFuncSetAttribute(gram_wsc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ws_attr = true;
       }
+      bool launched = false;
+      if (al16 && !g_disable_ws && !g_disable_tma && ncoarse <= 2 * GRW_CONS && n < (int64_t)1 << 31) {
+        // TMA-tiled kernel: stage length from the unpadded box footprint
+        int kt = 128;
+        while (kt > 16 && (size_t)GR_STAGES * cols * kt * 8 > 200 * 1024) kt >>= 1;
+        CUtensorMap tmA, tmB;
+        if (make_tmap(&tmA, Ab, n, pb, lda, PB) && (same || make_tmap(&tmB, Bb, n, qb, ldb, QB))) {
+          static bool tma_attr = false;
+          if (!tma_attr) {
+            DLB_CUDA_CHECK(cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            tma_attr = true;
+          }
+          if (same) tmB = tmA;
+          const GramSched sch = make_sched(ntp, ntq, diag_blk, GRW_CONS);
+          const int64_t nch = (n + kt - 1) / kt;
+          const int g = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, nch));
+          const size_t sm = (size_t)GR_STAGES * cols * kt * 8 + 2 * GR_STAGES * sizeof(uint64_t) + 1024;
+          gram_tma_kernel<<<g, GR_THREADS, sm, st>>>(n, tmA, tmB, same, kt, sch, partial, PB, QB);
+          ++g_launches;
+          const int tot = pb * qb;
+          double* Cblk = C + p0 + (size_t)q0 * ldc;
+          double* Cmir = (sym_lower && !diag_blk) ? C + q0 + (size_t)p0 * ldc : nullptr;
+          gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, g, PB, QB, pb, qb, diag_blk ? 1 : 0, Cblk, ldc, Cmir);
+          ++g_launches;
+          launched = true;
+        }
+      }
+      if (launched) continue;
       if (use_bulk)
         gram_ws_kernel<<<grid, GRW_THREADS, smem_ws, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
       else if (use_wsc && al16)

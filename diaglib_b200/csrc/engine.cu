@@ -105,6 +105,13 @@ struct Engine {
   int rank = 0, nranks = 1;
 
   DevBuf partial, smallws, resid_scratch, scal;
+  // driver workspaces, cached across calls (the reference allocates per call, 251-276 / 1600-1618;
+  // cudaMalloc/cudaFree of tens of GB costs ~0.5 s, so they are kept until finalize or
+  // diaglib_b200_release_workspace)
+  DevBuf ws_space, ws_aspace, ws_r, ws_xnew, ws_axnew, ws_evec, ws_red;
+  void release_workspace() {
+    for (DevBuf* b : {&ws_space, &ws_aspace, &ws_r, &ws_xnew, &ws_axnew, &ws_evec, &ws_red}) b->release();
+  }
   void* h_pin = nullptr;  // pinned staging for small read-backs
   size_t h_pin_bytes = 0;
 
@@ -454,9 +461,11 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
   // branch and are not allocated; space/aspace are not zero-filled (284-286) because every
   // column is written before it is read in the standard branch.
   const size_t blk = (size_t)nn * n_max * sizeof(double);
-  DevBuf b_space, b_aspace, b_r, b_xnew, b_axnew, b_evec, b_red;
+  DevBuf &b_space = ws_space, &b_aspace = ws_aspace, &b_r = ws_r, &b_xnew = ws_xnew, &b_axnew = ws_axnew,
+         &b_evec = ws_evec, &b_red = ws_red;
   const bool evec_on_dev = is_device_ptr(evec);
   const bool eig_on_dev = is_device_ptr(eig);
+  if (b_space.cap < 3 * blk || b_r.cap < blk || b_xnew.cap < blk) release_workspace();  // regrow from scratch
   bool okm = b_space.ensure(3 * blk) && b_aspace.ensure(3 * blk) && b_r.ensure(blk) && b_xnew.ensure(blk) &&
              b_axnew.ensure(blk);
   if (!evec_on_dev) okm = okm && b_evec.ensure(blk);
@@ -467,8 +476,7 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
   if (okm) ensure_small(n_max, 2 * n_max);
   okm = okm && resid_scratch.ensure(residual_scratch_bytes(n_max, num_sms));
   auto cleanup = [&]() {
-    b_space.release(); b_aspace.release(); b_r.release(); b_xnew.release(); b_axnew.release(); b_evec.release();
-    b_red.release();
+    if (status == DIAGLIB_B200_EALLOC) release_workspace();  // keep the cache otherwise
   };
   if (!okm || status) {
     fail(DIAGLIB_B200_EALLOC, "memory allocation failed. (lobpcg workspaces)");
@@ -680,9 +688,10 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
   PhaseHandle ph_tot = ph_open(PH_TOTAL);
   const size_t blk = (size_t)nn * n_max * sizeof(double);
   const size_t big = (size_t)nn * lda * sizeof(double);
-  DevBuf b_space, b_aspace, b_r, b_evec, b_red;
+  DevBuf &b_space = ws_space, &b_aspace = ws_aspace, &b_r = ws_r, &b_evec = ws_evec, &b_red = ws_red;
   const bool evec_on_dev = is_device_ptr(evec);
   const bool eig_on_dev = is_device_ptr(eig);
+  if (b_space.cap < big || b_r.cap < blk) release_workspace();  // regrow from scratch
   bool okm = b_space.ensure(big) && b_aspace.ensure(big) && b_r.ensure(blk);
   if (!evec_on_dev) okm = okm && b_evec.ensure(blk);
   const size_t eigw = eig_work_doubles(lda);
@@ -690,7 +699,9 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
   okm = okm && b_red.ensure(red_doubles * sizeof(double));
   if (okm) ensure_small(n_max, lda);
   okm = okm && resid_scratch.ensure(residual_scratch_bytes(n_max, num_sms));
-  auto cleanup = [&]() { b_space.release(); b_aspace.release(); b_r.release(); b_evec.release(); b_red.release(); };
+  auto cleanup = [&]() {
+    if (status == DIAGLIB_B200_EALLOC) release_workspace();
+  };
   if (!okm || status) {
     fail(DIAGLIB_B200_EALLOC, "memory allocation failed. (davidson workspaces)");
     cleanup();
@@ -948,6 +959,7 @@ int32_t diaglib_b200_init(int32_t device) {
   if (!g.sw0) { DLB_CUDA_CHECK(cudaEventCreate(&g.sw0)); DLB_CUDA_CHECK(cudaEventCreate(&g.sw1)); }
   if (!g.partial.ensure(gram_scratch_bytes(128, 128, g.num_sms))) return DIAGLIB_B200_EALLOC;
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_WS")) g_disable_ws = ev[0] == '1';
+  if (const char* ev = std::getenv("DIAGLIB_B200_NO_TMA")) g_disable_tma = ev[0] == '1';
   g.inited = true;
   g.status = 0;
   return DIAGLIB_B200_OK;
@@ -960,6 +972,7 @@ void diaglib_b200_finalize(void) {
   g.comm = nullptr;
   g.nranks = 1;
   g.rank = 0;
+  g.release_workspace();
   for (DevBuf* b : {&g.partial, &g.smallws, &g.resid_scratch, &g.scal, &g.b_rowptr, &g.b_col, &g.b_val, &g.b_diag,
                     &g.b_send, &g.b_recv, &g.b_halo})
     b->release();
@@ -967,6 +980,9 @@ void diaglib_b200_finalize(void) {
   g.inited = false;
 }
 
+void diaglib_b200_release_workspace(void) {
+  if (g.inited) { cudaStreamSynchronize(g.st); g.release_workspace(); }
+}
 void* diaglib_b200_stream(void) { return g.st; }
 int32_t diaglib_b200_last_status(void) { return g.status; }
 const char* diaglib_b200_last_message(void) { return g.msg.c_str(); }

@@ -11,6 +11,7 @@ namespace dlb {
 // number of kernels launched by this library since load (bench.py reports it as gpu_launches)
 extern int64_t g_launches;
 extern bool g_disable_ws;
+extern bool g_disable_tma;
 
 // ---- dense.cu -------------------------------------------------------------------------
 // C(p x q, ldc) = A(n x p, lda)^T * B(n x q, ldb).  Replaces dgemm('t','n',p,q,n,...) at

@@ -90,6 +90,9 @@ void diaglib_b200_diag_precnd(const int32_t* n, const int32_t* m, const double* 
 /* bind the library to a CUDA device and create its stream.  Returns a DIAGLIB_B200_* code. */
 int32_t diaglib_b200_init(int32_t device);
 void diaglib_b200_finalize(void);
+/* the drivers keep their n-long workspaces cached between calls (the reference allocates and
+ * frees them per call, diaglib.f90:251-276,550-552); this returns them to the device */
+void diaglib_b200_release_workspace(void);
 /* cudaStream_t on which callbacks must enqueue their work */
 void* diaglib_b200_stream(void);
 int32_t diaglib_b200_last_status(void);

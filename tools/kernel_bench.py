@@ -61,6 +61,11 @@ def main():
         t_bmul(37, 37, "bmul_37x37")
         print(json.dumps(dict(n=n, **out)))
         return
+    if only == "gram":
+        t_gram(111, 111, 1, v, w, "gram_sym_111")
+        t_gram(74, 37, 0, v, w, "gram_74x37")
+        print(json.dumps(dict(n=n, **out)))
+        return
     t_gram(111, 111, 1, v, w, "gram_sym_111")
     t_gram(74, 74, 1, v, w, "gram_sym_74")
     t_gram(37, 37, 1, v, v, "gram_sym_37_same")
