@@ -465,9 +465,11 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
          &b_evec = ws_evec, &b_red = ws_red;
   const bool evec_on_dev = is_device_ptr(evec);
   const bool eig_on_dev = is_device_ptr(eig);
-  if (b_space.cap < 3 * blk || b_r.cap < blk || b_xnew.cap < blk) release_workspace();  // regrow from scratch
-  bool okm = b_space.ensure(3 * blk) && b_aspace.ensure(3 * blk) && b_r.ensure(blk) && b_xnew.ensure(blk) &&
-             b_axnew.ensure(blk);
+  // space/aspace are double buffered: X_new, P and W of an iteration are written into the other
+  // buffer and the two are swapped, which removes the reference's block copies (466, 510-511)
+  if (b_space.cap < 3 * blk || b_r.cap < blk || b_xnew.cap < 3 * blk) release_workspace();  // regrow from scratch
+  bool okm = b_space.ensure(3 * blk) && b_aspace.ensure(3 * blk) && b_r.ensure(blk) && b_xnew.ensure(3 * blk) &&
+             b_axnew.ensure(3 * blk);
   if (!evec_on_dev) okm = okm && b_evec.ensure(blk);
   const size_t eigw = eig_work_doubles(len_a);
   const size_t cfw = coeffs_work_doubles(len_a, n_max, n_max);
@@ -489,8 +491,8 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
   double* space = b_space.as<double>();
   double* aspace = b_aspace.as<double>();
   double* r = b_r.as<double>();
-  double* x_new = b_xnew.as<double>();
-  double* ax_new = b_axnew.as<double>();
+  double* space2 = b_xnew.as<double>();   // the other half of the double buffer
+  double* aspace2 = b_axnew.as<double>();
   double* d_evec = evec_on_dev ? evec : b_evec.as<double>();
   double* a_red = b_red.as<double>();  // kept compact: leading dimension = current len_u
   double* e_red = a_red + (size_t)len_a * len_a;
@@ -569,6 +571,8 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
     sym_eig(st, len_u, a_red, len_u, false, e_red, eig_work, d_eigst);                 // 406
     ph_close(h);
     h = ph_open(PH_RITZ);
+    double* x_new = space2;    // x_new / ax_new are the first n_max columns of the next space / aspace
+    double* ax_new = aspace2;
     kbmul(nn, space, nn, len_u, a_red, len_u, n_max, 1.0, 0.0, x_new, nn);     // 420
     kbmul(nn, aspace, nn, len_u, a_red, len_u, n_max, 1.0, 0.0, ax_new, nn);   // 421
     ph_close(h);
@@ -627,14 +631,14 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
     h = ph_open(PH_DIAG);
     get_coeffs(st, len_u, len_u, n_max, n_act, a_red, u_p, cf_work, d_cfst);            // 488
     ph_close(h);
-    // p = space u_p, ap = aspace u_p (495-498).  The products are row-local, so they are
-    // written straight into the p columns of space/aspace instead of going through evec.
+    // p = space u_p, ap = aspace u_p (495-498), written straight into the p columns of the next
+    // space / aspace; x_new / ax_new already sit in its first n_max columns (510-511 need no copy)
     h = ph_open(PH_RITZ);
-    kbmul(nn, space, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(space, ind_p), nn);
-    kbmul(nn, aspace, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(aspace, ind_p), nn);
-    kcopy(nn, n_max, x_new, nn, space, nn);                                    // 510
-    kcopy(nn, n_max, ax_new, nn, aspace, nn);                                  // 511
+    kbmul(nn, space, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(space2, ind_p), nn);
+    kbmul(nn, aspace, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(aspace2, ind_p), nn);
     ph_close(h);
+    std::swap(space, space2);
+    std::swap(aspace, aspace2);
     h = ph_open(PH_RESID);
     {
       int32_t m32 = n_act;
