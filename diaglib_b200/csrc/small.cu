@@ -216,35 +216,45 @@ sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, in
         rc[tid] = c; rs[tid] = s; rp[2 * tid] = p; rp[2 * tid + 1] = q;
       }
       __syncthreads();
-      // phase 2: column rotations  A <- A J,  Z <- Z J
-      for (int e = tid; e < half * kp; e += nt) {
-        const int pr = e / kp, i = e % kp;
-        const double s = rs[pr];
-        if (s != 0.0) {
+      // phase 2: column rotations  A <- A J,  Z <- Z J.  One warp per pair (strided), lanes
+      // over the rows: no index division, rotation parameters read once per pair.
+      {
+        const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
+        for (int pr = warp; pr < half; pr += nwarp) {
+          const double s = rs[pr];
+          if (s == 0.0) continue;
           const double c = rc[pr];
-          const int p = rp[2 * pr], q = rp[2 * pr + 1];
-          const double ap = A[i + (size_t)p * lds], aq = A[i + (size_t)q * lds];
-          A[i + (size_t)p * lds] = c * ap - s * aq;
-          A[i + (size_t)q * lds] = s * ap + c * aq;
-          const double zp = Z[i + (size_t)p * lds], zq = Z[i + (size_t)q * lds];
-          Z[i + (size_t)p * lds] = c * zp - s * zq;
-          Z[i + (size_t)q * lds] = s * zp + c * zq;
+          double* Ap = A + (size_t)rp[2 * pr] * lds;
+          double* Aq = A + (size_t)rp[2 * pr + 1] * lds;
+          double* Zp = Z + (size_t)rp[2 * pr] * lds;
+          double* Zq = Z + (size_t)rp[2 * pr + 1] * lds;
+          for (int i = lane; i < kp; i += 32) {
+            const double ap = Ap[i], aq = Aq[i], zp = Zp[i], zq = Zq[i];
+            Ap[i] = c * ap - s * aq;
+            Aq[i] = s * ap + c * aq;
+            Zp[i] = c * zp - s * zq;
+            Zq[i] = s * zp + c * zq;
+          }
         }
       }
       __syncthreads();
       // phase 3: row rotations  A <- J^T A ; the rotated pivot is set to exactly zero
-      for (int e = tid; e < half * kp; e += nt) {
-        const int pr = e / kp, j = e % kp;
-        const double s = rs[pr];
-        if (s != 0.0) {
+      {
+        const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
+        for (int pr = warp; pr < half; pr += nwarp) {
+          const double s = rs[pr];
+          if (s == 0.0) continue;
           const double c = rc[pr];
           const int p = rp[2 * pr], q = rp[2 * pr + 1];
-          const double ap = A[p + (size_t)j * lds], aq = A[q + (size_t)j * lds];
-          double np_ = c * ap - s * aq, nq_ = s * ap + c * aq;
-          if (j == q) np_ = 0.0;
-          if (j == p) nq_ = 0.0;
-          A[p + (size_t)j * lds] = np_;
-          A[q + (size_t)j * lds] = nq_;
+          for (int j = lane; j < kp; j += 32) {
+            double* col = A + (size_t)j * lds;
+            const double ap = col[p], aq = col[q];
+            double np_ = c * ap - s * aq, nq_ = s * ap + c * aq;
+            if (j == q) np_ = 0.0;
+            if (j == p) nq_ = 0.0;
+            col[p] = np_;
+            col[q] = nq_;
+          }
         }
       }
       __syncthreads();
