@@ -17,7 +17,8 @@
 namespace dlb {
 
 bool g_disable_ws = false;
-bool g_disable_tma = false;  // DIAGLIB_B200_NO_TMA=1: skip the cp.async.bulk.tensor gram kernel  // DIAGLIB_B200_NO_WS=1: fall back to the cp.async kernels (A/B testing)
+bool g_disable_tma = false;
+bool g_bmul_small_tiles = false;  // DIAGLIB_B200_BMUL_RT128=1: keep 128-row tiles (A/B testing)  // DIAGLIB_B200_NO_TMA=1: skip the cp.async.bulk.tensor gram kernel  // DIAGLIB_B200_NO_WS=1: fall back to the cp.async kernels (A/B testing)
 
 // =====================================================================================
 // gram_tn
@@ -625,12 +626,14 @@ GramSched make_sched(int ntp, int ntq, bool sym_lower, int nwarps) {
   return s;
 }
 
-// stage length: as long as three stages fit in shared memory, capped at 128 rows
-int pick_kt(int cols) {
+// stage length: as long as three stages fit in shared memory, capped at 128 rows (cp.async
+// kernels) or 256 rows (bulk-copy producer: longer column segments per copy)
+int pick_kt(int cols, int cap = 128) {
   const int budget = 200 * 1024 / (GR_STAGES * 8);  // doubles per stage
-  int kt = 128;
-  while (kt > 16 && cols * (kt + 4) > budget) kt >>= 1;
-  return kt;
+  const int cand[] = {256, 192, 128, 64, 32, 16};
+  for (int kt : cand)
+    if (kt <= cap && cols * (kt + 4) <= budget) return kt;
+  return 16;
 }
 
 }  // namespace
@@ -662,11 +665,12 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
       const double* Bb = B + (int64_t)q0 * ldb;
       const int same = (Ab == Bb && lda == ldb && pb == qb) ? 1 : 0;
       const int cols = PB + (same ? 0 : QB);
-      const int KT = pick_kt(cols);
+      int KT = pick_kt(cols);
       const int ncoarse = ((ntp + 1) / 2) * ((ntq + 3) / 4);
       // bulk-copy producer: only when a column segment of a stage is >= 1 KB (narrow blocks);
       // cp.async producers otherwise; the barrier-synchronised kernel is the fallback
       const bool use_bulk = al16 && (n % 2 == 0) && !g_disable_ws && KT >= 128 && ncoarse <= 2 * GRW_CONS;
+      if (use_bulk) KT = pick_kt(cols, 256);
       const bool use_wsc = !use_bulk && !g_disable_ws && ncoarse <= 2 * GRC_CONS;
       const GramSched sched = make_sched(ntp, ntq, diag_blk, use_bulk ? GRW_CONS : (use_wsc ? GRC_CONS : GR_WARPS));
       const int64_t nchunks = (n + KT - 1) / KT;
@@ -965,24 +969,29 @@ blockmul_persistent_kernel(int64_t n, const double* __restrict__ V, int64_t ldv,
 // eight consumer warps run the DMMA loop.  There is no CTA-wide barrier in the main loop:
 // consumers wait on full[stage], release the stage on empty[stage], and drift freely, which
 // keeps the FP64 tensor pipe busy while other warps wait for data.
-constexpr int BMW_CONS = 8;                       // consumer warps (16 rows each)
-constexpr int BMW_THREADS = (BMW_CONS + 1) * 32;  // + producer warp
 constexpr int BMW_STAGES = 4;
 
-template <int NQT>
-__global__ void __launch_bounds__(BMW_THREADS)
+// NCONS consumer warps (16 rows each) + 1 producer warp; the row tile is NCONS*16 rows, so a
+// bulk copy moves NCONS*128 bytes: 2 KB with 16 consumers, which the copy engine needs to get
+// past ~4.4 TB/s on the HBM-bound shapes (trmm, 74x37).
+template <int NQT, int NCONS>
+__global__ void __launch_bounds__((NCONS + 1) * 32)
 blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, const double* __restrict__ C, int ldc,
                    int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri) {
   extern __shared__ __align__(16) double smem[];
   constexpr int QB = NQT * 8;
-  constexpr int STAGE = BM_KC * BM_SV;
+  constexpr int BMW_CONS = NCONS;
+  constexpr int BMW_THREADS = (NCONS + 1) * 32;
+  constexpr int RT = NCONS * 16;
+  constexpr int SV = RT + 4;
+  constexpr int STAGE = BM_KC * SV;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // BMW_STAGES
   uint64_t* empty = full + BMW_STAGES;                   // BMW_STAGES
   double* sC = smem + 2 * BMW_STAGES;                    // [QB][PS], zero padded
   double* ring = sC + (size_t)QB * PS;                   // BMW_STAGES x STAGE
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nk = (p + BM_KC - 1) / BM_KC;
-  const int64_t ntiles = (n + BM_RT - 1) / BM_RT;
+  const int64_t ntiles = (n + RT - 1) / RT;
   const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
@@ -1002,9 +1011,9 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
     int s = 0;
     uint32_t ph = 0;
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
-      const int64_t row0 = (blockIdx.x + ti * gridDim.x) * BM_RT;
+      const int64_t row0 = (blockIdx.x + ti * gridDim.x) * RT;
       const int64_t rem = n - row0;
-      const uint32_t rows = rem < BM_RT ? (uint32_t)rem : (uint32_t)BM_RT;
+      const uint32_t rows = rem < RT ? (uint32_t)rem : (uint32_t)RT;
       for (int kc = 0; kc < nk; ++kc) {
         const int k0 = kc * BM_KC;
         const int ncols = (p - k0) < BM_KC ? (p - k0) : BM_KC;
@@ -1012,7 +1021,7 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
         if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)ncols * rows * 8u);
         __syncwarp();
         if (lane < ncols)
-          bulk_g2s(ring + (size_t)s * STAGE + lane * BM_SV, V + (int64_t)(k0 + lane) * ldv + row0, rows * 8u, &full[s]);
+          bulk_g2s(ring + (size_t)s * STAGE + lane * SV, V + (int64_t)(k0 + lane) * ldv + row0, rows * 8u, &full[s]);
         if (++s == BMW_STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -1023,7 +1032,7 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
     for (int r = 0; r < 2; ++r)
 #pragma unroll
       for (int c = 0; c < NQT; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
-    const int a_off = (lane & 3) * BM_SV + warp * 16 + (lane >> 2);
+    const int a_off = (lane & 3) * SV + warp * 16 + (lane >> 2);
     const int b_off = (lane >> 2) * PS + (lane & 3);
     int s = 0;
     uint32_t ph = 0;
@@ -1036,7 +1045,7 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
         for (int k4 = 0; k4 < BM_KC / 4; ++k4) {
           double a[2], b[NQT];
 #pragma unroll
-          for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * BM_SV + a_off + r * 8];
+          for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * SV + a_off + r * 8];
 #pragma unroll
           for (int cc = 0; cc < NQT; ++cc) b[cc] = sCk[cc * 8 * PS + k4 * 4];
           if (!tri) {
@@ -1058,7 +1067,7 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
         if (lane == 0) mbar_arrive(&empty[s]);
         if (++s == BMW_STAGES) { s = 0; ph ^= 1; }
       }
-      const int64_t row0 = (blockIdx.x + ti * gridDim.x) * BM_RT;
+      const int64_t row0 = (blockIdx.x + ti * gridDim.x) * RT;
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int64_t row = row0 + warp * 16 + r * 8 + (lane >> 2);
@@ -1104,19 +1113,30 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
   const int p16 = (p + 15) / 16 * 16;
   const int PS = p16 + 4;
   const size_t smem_p = ((size_t)QB * PS + (size_t)BM_STAGES * BM_KC * BM_SV) * sizeof(double);
-  const size_t smem_w = (2 * BMW_STAGES + (size_t)QB * PS + (size_t)BMW_STAGES * BM_KC * BM_SV) * sizeof(double);
-  if (al16 && (n % 2 == 0) && smem_w <= 110 * 1024 && ntiles >= 2 && !g_disable_ws) {
+  if (al16 && (n % 2 == 0) && !g_disable_ws) {
+    const size_t sc_bytes = (2 * BMW_STAGES + (size_t)QB * PS) * sizeof(double);
+    const size_t smem16 = sc_bytes + (size_t)BMW_STAGES * BM_KC * (16 * 16 + 4) * sizeof(double);
+    const size_t smem8 = sc_bytes + (size_t)BMW_STAGES * BM_KC * (8 * 16 + 4) * sizeof(double);
     static bool ws_attr = false;
-    static int occ_ws = 1;
     if (!ws_attr) {
-      DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_ws_kernel<NQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_ws_kernel<NQT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      if (NQT == 5)
+        DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_ws_kernel<5, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       ws_attr = true;
     }
-    DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ws, blockmul_ws_kernel<NQT>, BMW_THREADS, smem_w));
-    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * std::max(1, occ_ws));
-    blockmul_ws_kernel<NQT><<<grid, BMW_THREADS, smem_w, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0);
-    ++g_launches;
-    return;
+    if (NQT == 5 && smem16 <= 220 * 1024 && n >= 256 * 2 && !g_bmul_small_tiles) {
+      const int64_t nt16 = (n + 255) / 256;
+      const unsigned grid = (unsigned)std::min<int64_t>(nt16, (int64_t)num_sms);
+      blockmul_ws_kernel<5, 16><<<grid, 17 * 32, smem16, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0);
+      ++g_launches;
+      return;
+    }
+    if (smem8 <= 110 * 1024 && ntiles >= 2) {
+      const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * 2);
+      blockmul_ws_kernel<NQT, 8><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0);
+      ++g_launches;
+      return;
+    }
   }
   if (smem_p <= 110 * 1024 && ntiles >= 2) {
     int occ = 0;
