@@ -37,6 +37,11 @@ N_TARG, TOL, DELTA, NOISE, MAX_ITER = 32, 1e-8, 1.0, 0.1, 200
 METRIC, UNIT = "lobpcg_iters_per_s", "iterations/s"
 
 
+def workload_name(nx):
+    return (f"C3 lap3d {nx}^3 n={nx ** 3} n_targ={N_TARG} n_max={P.n_eig_rule(N_TARG)} LOBPCG tol={TOL} "
+            f"(BASELINE.json configs[2])")
+
+
 def make_guess(diag_glob, n_glob, n_max, r0, r1):
     g = P.guess_lowest_diag(diag_glob, n_max, r0, r1)
     g += P.guess(n_glob, n_max, r0, r1) * (NOISE / np.sqrt(n_glob / 12.0))
@@ -92,20 +97,38 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def oracle_sample(nx_s, iters, threads):
-    """CPU oracle on a bounded sample of the workload: lap3d nx_s^3, `iters` LOBPCG iterations."""
+def oracle_sample(nx_s, threads, it_lo=2, it_hi=6):
+    """CPU oracle on a bounded sample of the workload (lap3d nx_s^3): two truncated LOBPCG runs
+    (it_lo and it_hi iterations) separate the set-up cost from the per-iteration cost."""
     from oracle import oracle as O
     O.set_threads(threads)
     n_s = nx_s ** 3
     n_max = P.n_eig_rule(N_TARG)
     csr = P.lap3d(nx_s, nx_s, nx_s, delta=DELTA)
     O.set_csr(*csr)
-    ev = make_guess(csr[3], n_s, n_max, 0, n_s)
-    t0 = time.time()
-    r = O.lobpcg(ev, N_TARG, iters, TOL)
-    wall = time.time() - t0
-    its = len(r["it"])
-    return n_s, its, wall, O.get_threads()
+    g = make_guess(csr[3], n_s, n_max, 0, n_s)
+    walls = []
+    for iters in (it_lo, it_hi):
+        ev = g.copy(order="F")
+        t0 = time.time()
+        r = O.lobpcg(ev, N_TARG, iters, TOL)
+        walls.append(time.time() - t0)
+        assert len(r["it"]) == iters
+    per_it = (walls[1] - walls[0]) / (it_hi - it_lo)
+    setup = max(0.0, walls[0] - it_lo * per_it)
+    return n_s, setup, per_it, sum(walls), O.get_threads()
+
+
+def cpu_estimate(nx, nx_s, threads, iters_full):
+    """iterations/s of a full solve (set-up + iters_full iterations) at n = nx^3, extrapolated
+    linearly in n from the sample (all per-iteration and set-up work is O(n))."""
+    n_s, setup, per_it, wall, nthr = oracle_sample(nx_s, threads)
+    scale = (nx ** 3) / n_s
+    t_full = (setup + iters_full * per_it) * scale
+    desc = (f"oracle LOBPCG truncated at 2 and 6 iterations on the same workload at n={n_s} ({nx_s}^3), {wall:.1f} s of CPU "
+            f"work: set-up {setup:.2f} s + {per_it:.2f} s/iteration, scaled by n/n_sample={scale:.0f} to a {iters_full}-iteration "
+            f"solve; C++ restatement of diaglib on OpenBLAS 0.3.31 ({nthr} threads), not a gfortran build")
+    return iters_full / t_full, t_full, nthr, desc
 
 
 def run_reference(args, rank):
@@ -116,26 +139,23 @@ def run_reference(args, rank):
     threads = os.cpu_count() or 1
     n_full = args.nx ** 3
     nx_s = min(args.nx, 128)
-    it_s = 4
+    iters_full = 25  # iteration count of the full solve (GPU arm and oracle agree: 24-26)
     for _ in range(args.warmup):
-        oracle_sample(min(nx_s, 64), 2, threads)
-    t_tot, its_tot = 0.0, 0
+        oracle_sample(min(nx_s, 32), threads, 1, 2)
+    vals, t_tot = [], 0.0
     for _ in range(args.steps):
-        n_s, its, wall, nthr = oracle_sample(nx_s, it_s, threads)
-        t_tot += wall
-        its_tot += its
-    ips_sample = its_tot / t_tot
-    value = ips_sample * (n_s / n_full)
+        t0 = time.time()
+        v, t_full, nthr, desc = cpu_estimate(args.nx, nx_s, threads, iters_full)
+        t_tot += time.time() - t0
+        vals.append(v)
+    value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3 lap3d {args.nx}^3 n={n_full} n_targ={N_TARG} n_max={P.n_eig_rule(N_TARG)} LOBPCG tol={TOL}",
-                   "delta": DELTA, "guess": "lowest-diag unit + 10% noise"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthr, "kind": "port",
-                         "sample": f"{it_s} LOBPCG iterations (+ setup) of the same workload at n={n_s} ({nx_s}^3), "
-                                   f"iterations/s scaled by n_sample/n (all per-iteration work is O(n)); C++ restatement "
-                                   f"of diaglib on OpenBLAS 0.3.31 ({nthr} threads), not a gfortran build"},
+        "config": {"workload": workload_name(args.nx), "delta": DELTA, "guess": "lowest-diag unit + 10% noise"},
+        "time_to_converge_s": iters_full / value,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthr, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -292,19 +312,27 @@ def main():
         f64 = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")))
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         f64_peak = f64["dgemm_8192_tflops_burst"]
+        traffic, traffic_src = None, None
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_bmul_n24_r01.json")))
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at n = 2^24, scaled to this rank's rows
+            traffic = cap["traffic_bytes"] * (n_loc / 16777216.0)
+            traffic_src = "profiles/ncu_bmul_n24_r01.json (ncu --set full, n=2^24), scaled by rows"
+        except Exception:
+            pass
         t_hbm = bytes_alg / (hbm_peak * 1e9)
         t_f64 = flops / (f64_peak * 1e12)
         bound = "tensor" if t_f64 >= t_hbm else "hbm"
         ach_tf = flops / (bm_ms * 1e-3) / 1e12
         ach_gb = bytes_alg / (bm_ms * 1e-3) / 1e9
-        roof = {"kernel": f"blockmul_kernel Y(n x {q}) = V(n x {p}) C, n={n_loc}", "bound": bound,
+        roof = {"kernel": f"blockmul_ws_kernel Y(n x {q}) = V(n x {p}) C, n={n_loc}", "bound": bound,
                 "achieved": ach_tf if bound == "tensor" else ach_gb, "peak": f64_peak if bound == "tensor" else hbm_peak,
                 "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
                 "frac": (ach_tf / f64_peak) if bound == "tensor" else (ach_gb / hbm_peak),
                 "peak_source": ("cuBLAS DGEMM 8192^3 measured on this pool (profiles/fp64_peaks_r01.json); "
                                 "MEASURED_PEAKS.json has no FP64 figure") if bound == "tensor" else
                                ("MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"),
-                "traffic": None, "ms_per_launch": bm_ms, "achieved_gbs": ach_gb, "achieved_tflops": ach_tf,
+                "traffic": traffic, "traffic_source": traffic_src, "ms_per_launch": bm_ms, "achieved_gbs": ach_gb, "achieved_tflops": ach_tf,
                 "hbm_frac": ach_gb / hbm_peak, "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops}
         # second family: symmetric Gram at len_u = 3 n_max
         w = K.DeviceArray((n_loc, p))
@@ -319,7 +347,7 @@ def main():
         gr_ms = K.timer_stop_ms() / reps
         gflops = 1.0 * n_loc * p * (p + 1)  # lower triangle only
         gbytes = 8.0 * n_loc * 2 * p
-        roof["gram"] = {"kernel": f"gram_kernel sym {p}x{p}, n={n_loc}", "ms_per_launch": gr_ms,
+        roof["gram"] = {"kernel": f"gram_tma_kernel sym {p}x{p}, n={n_loc}", "ms_per_launch": gr_ms,
                         "achieved_tflops": gflops / (gr_ms * 1e-3) / 1e12, "achieved_gbs": gbytes / (gr_ms * 1e-3) / 1e9,
                         "frac_tensor": gflops / (gr_ms * 1e-3) / 1e12 / f64_peak, "frac_hbm": gbytes / (gr_ms * 1e-3) / 1e9 / hbm_peak}
         for a in (v, y, cd, w, cg):
@@ -329,11 +357,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        nx_s = min(nx, 128)
-        n_s, its_s, wall_s, nthr = oracle_sample(nx_s, 4, threads)
-        cpu = {"value": (its_s / wall_s) * (n_s / n), "unit": UNIT, "cores": nthr, "kind": "port",
-               "sample": f"{its_s} LOBPCG iterations (+ setup) of the same workload at n={n_s} ({nx_s}^3) in {wall_s:.1f} s, "
-                         f"scaled by n_sample/n; C++ restatement of diaglib on OpenBLAS ({nthr} threads), not a gfortran build"}
+        v, t_full, nthr, desc = cpu_estimate(nx, min(nx, 128), threads, int(round(tot_its / args.steps)))
+        cpu = {"value": v, "unit": UNIT, "cores": nthr, "kind": "port", "time_to_converge_s": t_full, "sample": desc}
 
     if rank == 0:
         res_max = float(hist["rms"][-1][:N_TARG].max()) if len(hist["it"]) else None
@@ -341,8 +366,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C3 lap3d {nx}^3 n={n} n_targ={N_TARG} n_max={n_max} LOBPCG tol={TOL} (BASELINE.json configs[2])",
-                       "delta": DELTA, "guess": "lowest-diag unit + 10% noise", "rows_per_gpu": n_loc,
+            "config": {"workload": workload_name(nx), "delta": DELTA, "guess": "lowest-diag unit + 10% noise", "rows_per_gpu": n_loc,
                        "l2": "inputs larger than L2 (every block >= 4.9 GB at N=1)", "parallelism": f"row-partition x{world}"},
             "time_to_converge_s": ms_per_step * 1e-3, "iterations": tot_its / args.steps, "converged": True,
             "final_rms_residual_max": res_max, "eig_lowest": [float(x) for x in eig[:4]],

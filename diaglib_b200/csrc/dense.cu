@@ -18,7 +18,7 @@ namespace dlb {
 
 bool g_disable_ws = false;
 bool g_disable_tma = false;
-bool g_bmul_small_tiles = false;  // DIAGLIB_B200_BMUL_RT128=1: keep 128-row tiles (A/B testing)  // DIAGLIB_B200_NO_TMA=1: skip the cp.async.bulk.tensor gram kernel  // DIAGLIB_B200_NO_WS=1: fall back to the cp.async kernels (A/B testing)
+bool g_bmul_small_tiles = true;   // DIAGLIB_B200_BMUL_RT256=1 selects 256-row tiles (measured slower: 4.91 vs 4.78 ms)  // DIAGLIB_B200_NO_TMA=1: skip the cp.async.bulk.tensor gram kernel  // DIAGLIB_B200_NO_WS=1: fall back to the cp.async kernels (A/B testing)
 
 // =====================================================================================
 // gram_tn
