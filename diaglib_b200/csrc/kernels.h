@@ -13,6 +13,7 @@ extern int64_t g_launches;
 extern bool g_disable_ws;
 extern bool g_disable_tma;
 extern bool g_bmul_small_tiles;
+extern bool g_eig_two_sided;
 
 // ---- dense.cu -------------------------------------------------------------------------
 // C(p x q, ldc) = A(n x p, lda)^T * B(n x q, ldb).  Replaces dgemm('t','n',p,q,n,...) at

@@ -164,24 +164,30 @@ chol_inv_kernel(int m, const double* G, int ldg, double* T, double* work, CholSt
 }
 
 // ---------------------------------------------------------------------------------------
-// Symmetric eigensolver: parallel-order cyclic Jacobi (two-sided), all in one CTA.
-// A and Z live in shared memory when 2*kp*lds doubles fit, else in `work` (L2 resident).
+// Symmetric eigensolver (dsyev replacement), all in one CTA, A and the eigenvector matrix in
+// shared memory when 2*kp*lds doubles fit, else in `work` (L2 resident).
+//
+//  1. one-sided (Hestenes) Jacobi on G = A, V = I: column rotations only, chosen so that the
+//     rotated columns of G become orthogonal; at convergence G = A V has orthogonal columns
+//     g_i = lambda_i v_i.  A half-warp owns a pair: three dot products by shuffle, one
+//     rotation, ONE block barrier per round (the two-sided form needs three and a serial
+//     angle phase).  No shift is applied, so graded positive definite reduced matrices (the
+//     LOBPCG / Davidson case) keep their relative accuracy.
+//  2. verification |g_i - (v_i.g_i) v_i| <= tol |A|_F.  It fails only when +lambda and -lambda
+//     are both eigenvalues (their columns are then any orthogonal pair of the 2-D singular
+//     subspace); in that case
+//  3. the two-sided parallel-order cyclic Jacobi re-solves from the original matrix.
+// Eigenvalues ascending, eigenvectors with their largest component positive.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SM_THREADS)
-sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, int use_smem, EigStatus* st) {
-  extern __shared__ __align__(16) double dyn[];
-  __shared__ int s_flag;
-  const int kp = (k + 1) & ~1;
-  const int lds = kp | 1;  // odd stride: row accesses are bank-conflict free
-  const int half = kp / 2;
-  double* A = use_smem ? dyn : work;
-  double* Z = A + (size_t)kp * lds;
-  double* rc = Z + (size_t)kp * lds;   // half cosines
-  double* rs = rc + half;              // half sines
-  int* rp = reinterpret_cast<int*>(rs + half);  // 2*half ints (p, q)
-  const int tid = threadIdx.x, nt = blockDim.x;
+__device__ __forceinline__ void rr_pair(int r, int idx, int kp, int& p, int& q) {
+  // round-robin tournament: round r (0..kp-2), pair idx (0..kp/2-1)
+  if (idx == 0) { p = kp - 1; q = r; }
+  else { p = (r + idx) % (kp - 1); q = (r - idx + (kp - 1)) % (kp - 1); }
+  if (p > q) { const int t = p; p = q; q = t; }
+}
 
-  for (int e = tid; e < kp * kp; e += nt) {
+__device__ void eig_load(int k, int kp, int lds, const double* a, int lda, int upper, double* A, double* Z) {
+  for (int e = threadIdx.x; e < kp * kp; e += blockDim.x) {
     const int i = e % kp, j = e / kp;
     double v = 0.0;
     if (i < k && j < k) {
@@ -191,19 +197,100 @@ sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, in
     A[i + (size_t)j * lds] = v;
     Z[i + (size_t)j * lds] = (i == j) ? 1.0 : 0.0;
   }
-  if (tid == 0) s_flag = 0;
   __syncthreads();
+}
 
-  int sweeps = 0, converged = 0;
-  const int max_sweeps = 40;
-  while (sweeps < max_sweeps) {
+// returns the number of sweeps (>0) when converged AND verified, 0 otherwise
+__device__ int jacobi_one_sided(int k, int kp, int lds, double* G, double* V, double* ev, int* s_flag, double* s_red) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int half = kp / 2;
+  const int ngroups = nt >> 4;
+  const int group = tid >> 4, gl = tid & 15;
+  int sweeps = 0;
+  bool conv = false;
+  while (sweeps < 40 && !conv) {
     for (int r = 0; r < kp - 1; ++r) {
-      // phase 1: rotation angles for the kp/2 disjoint pairs of this round
+      for (int base = 0; base < half; base += ngroups) {
+        const int pr = base + group;
+        const bool valid = pr < half;
+        int p, q;
+        rr_pair(r, valid ? pr : 0, kp, p, q);
+        double* gp = G + (size_t)p * lds;
+        double* gq = G + (size_t)q * lds;
+        double al = 0.0, be = 0.0, ga = 0.0;
+        if (valid)
+          for (int i = gl; i < kp; i += 16) {
+            const double x = gp[i], y = gq[i];
+            al = fma(x, x, al);
+            be = fma(y, y, be);
+            ga = fma(x, y, ga);
+          }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          al += __shfl_xor_sync(0xffffffffu, al, o);
+          be += __shfl_xor_sync(0xffffffffu, be, o);
+          ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        }
+        const double nrm = sqrt(al * be);
+        if (valid && fabs(ga) > EPS * nrm && nrm > 1e-300) {
+          const double zeta = (be - al) / (2.0 * ga);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = rsqrt(1.0 + t * t);
+          const double sn = t * c;
+          double* vp = V + (size_t)p * lds;
+          double* vq = V + (size_t)q * lds;
+          for (int i = gl; i < kp; i += 16) {
+            const double x = gp[i], y = gq[i];
+            gp[i] = c * x - sn * y;
+            gq[i] = sn * x + c * y;
+            const double u = vp[i], v = vq[i];
+            vp[i] = c * u - sn * v;
+            vq[i] = sn * u + c * v;
+          }
+          if (gl == 0) *s_flag = 1;
+        }
+      }
+      __syncthreads();
+    }
+    ++sweeps;
+    const int any = *s_flag;
+    __syncthreads();
+    if (tid == 0) *s_flag = 0;
+    __syncthreads();
+    if (!any) conv = true;
+  }
+  if (!conv) return 0;
+  // eigenvalues = Rayleigh quotients v_i.g_i ; verification of g_i = lambda_i v_i
+  double fro = 0.0, worst = 0.0;
+  for (int i = tid; i < kp; i += nt) {
+    const double* g = G + (size_t)i * lds;
+    const double* v = V + (size_t)i * lds;
+    double rho = 0.0, gg = 0.0;
+    for (int rr = 0; rr < kp; ++rr) { rho = fma(v[rr], g[rr], rho); gg = fma(g[rr], g[rr], gg); }
+    double err = 0.0;
+    for (int rr = 0; rr < kp; ++rr) { const double d = g[rr] - rho * v[rr]; err = fma(d, d, err); }
+    ev[i] = rho;
+    fro += gg;
+    worst = fmax(worst, err);
+  }
+  const double fro2 = cta_sum(fro, s_red);
+  const double w2 = cta_max(worst, s_red);
+  const double tol = 1.0e3 * EPS;
+  return (w2 <= tol * tol * fro2) ? sweeps : 0;
+}
+
+// two-sided parallel-order cyclic Jacobi; eigenvalues on the diagonal of A at exit
+__device__ int jacobi_two_sided(int kp, int lds, double* A, double* Z, double* rc, double* rs, int* rp, int* s_flag,
+                                int* converged) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int half = kp / 2;
+  int sweeps = 0;
+  *converged = 0;
+  while (sweeps < 40) {
+    for (int r = 0; r < kp - 1; ++r) {
       if (tid < half) {
         int p, q;
-        if (tid == 0) { p = kp - 1; q = r; }
-        else { p = (r + tid) % (kp - 1); q = (r - tid + (kp - 1)) % (kp - 1); }
-        if (p > q) { const int t = p; p = q; q = t; }
+        rr_pair(r, tid, kp, p, q);
         const double app = A[p + (size_t)p * lds], aqq = A[q + (size_t)q * lds], apq = A[p + (size_t)q * lds];
         double c = 1.0, s = 0.0;
         if (fabs(apq) > EPS * sqrt(fabs(app) * fabs(aqq)) && fabs(apq) > 1e-300) {
@@ -211,13 +298,11 @@ sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, in
           const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
           c = 1.0 / sqrt(1.0 + t * t);
           s = t * c;
-          s_flag = 1;
+          *s_flag = 1;
         }
         rc[tid] = c; rs[tid] = s; rp[2 * tid] = p; rp[2 * tid + 1] = q;
       }
       __syncthreads();
-      // phase 2: column rotations  A <- A J,  Z <- Z J.  One warp per pair (strided), lanes
-      // over the rows: no index division, rotation parameters read once per pair.
       {
         const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
         for (int pr = warp; pr < half; pr += nwarp) {
@@ -238,7 +323,6 @@ sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, in
         }
       }
       __syncthreads();
-      // phase 3: row rotations  A <- J^T A ; the rotated pivot is set to exactly zero
       {
         const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
         for (int pr = warp; pr < half; pr += nwarp) {
@@ -260,28 +344,70 @@ sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, in
       __syncthreads();
     }
     ++sweeps;
-    const int any = s_flag;
+    const int any = *s_flag;
+    __syncthreads();
+    if (tid == 0) *s_flag = 0;
+    __syncthreads();
+    if (!any) { *converged = 1; break; }
+  }
+  return sweeps;
+}
+
+__global__ void __launch_bounds__(SM_THREADS)
+sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, int use_smem, int force_two_sided,
+               EigStatus* st) {
+  extern __shared__ __align__(16) double dyn[];
+  __shared__ int s_flag;
+  __shared__ double s_red[32];
+  const int kp = (k + 1) & ~1;
+  const int lds = kp | 1;  // odd stride: row accesses of the two-sided form are bank-conflict free
+  const int half = kp / 2;
+  double* A = use_smem ? dyn : work;
+  double* Z = A + (size_t)kp * lds;
+  double* ev = Z + (size_t)kp * lds;   // kp eigenvalues
+  double* rc = ev + kp;                // half cosines
+  double* rs = rc + half;              // half sines
+  int* rp = reinterpret_cast<int*>(rs + half);   // 2*half ints (p, q)
+  int* rank = rp + 2 * half;                     // kp ints
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  if (tid == 0) s_flag = 0;
+  eig_load(k, kp, lds, a, lda, upper, A, Z);
+  int sweeps = force_two_sided ? 0 : jacobi_one_sided(k, kp, lds, A, Z, ev, &s_flag, s_red);
+  int converged = sweeps > 0 ? 1 : 0;
+  if (!converged) {
     __syncthreads();
     if (tid == 0) s_flag = 0;
-    __syncthreads();
-    if (!any) { converged = 1; break; }
+    eig_load(k, kp, lds, a, lda, upper, A, Z);
+    int conv2 = 0;
+    sweeps = 100 + jacobi_two_sided(kp, lds, A, Z, rc, rs, rp, &s_flag, &conv2);
+    converged = conv2;
+    for (int i = tid; i < kp; i += nt) ev[i] = A[i + (size_t)i * lds];
   }
+  __syncthreads();
 
-  // ascending sort by rank, largest-magnitude component made positive, write back into a
+  // ascending order by rank, largest-magnitude component made positive, write back into a
   for (int i = tid; i < k; i += nt) {
-    const double di = A[i + (size_t)i * lds];
-    int rank = 0;
+    const double di = ev[i];
+    int rk = 0;
     for (int j = 0; j < k; ++j) {
-      const double dj = A[j + (size_t)j * lds];
-      rank += (dj < di || (dj == di && j < i)) ? 1 : 0;
+      const double dj = ev[j];
+      rk += (dj < di || (dj == di && j < i)) ? 1 : 0;
     }
     double best = 0.0, sign = 1.0;
     for (int rr = 0; rr < k; ++rr) {
       const double v = Z[rr + (size_t)i * lds];
       if (fabs(v) > best) { best = fabs(v); sign = v < 0.0 ? -1.0 : 1.0; }
     }
-    w[rank] = di;
-    for (int rr = 0; rr < k; ++rr) a[rr + (size_t)rank * lda] = sign * Z[rr + (size_t)i * lds];
+    w[rk] = di;
+    rank[i] = sign < 0.0 ? -(rk + 1) : (rk + 1);
+  }
+  __syncthreads();
+  for (int e = tid; e < k * k; e += nt) {
+    const int rr = e % k, i = e / k;
+    const int rk = rank[i];
+    const double sg = rk < 0 ? -1.0 : 1.0;
+    a[rr + (size_t)((rk < 0 ? -rk : rk) - 1) * lda] = sg * Z[rr + (size_t)i * lds];
   }
   if (tid == 0) { st->sweeps = sweeps; st->converged = converged; }
 }
@@ -447,8 +573,10 @@ void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, 
 
 size_t eig_work_doubles(int k) {
   const int kp = (k + 1) & ~1, lds = kp | 1;
-  return 2 * (size_t)kp * lds + 2 * (size_t)kp + 8;
+  return 2 * (size_t)kp * lds + 4 * (size_t)kp + 8;
 }
+
+bool g_eig_two_sided = false;  // DIAGLIB_B200_EIG_TWO_SIDED=1: skip the one-sided solver (A/B testing)
 
 void sym_eig(cudaStream_t st, int k, double* a, int lda, bool upper, double* w, double* work, EigStatus* status_dev) {
   static bool attr_set = false;
@@ -458,7 +586,8 @@ void sym_eig(cudaStream_t st, int k, double* a, int lda, bool upper, double* w, 
   }
   const size_t need = eig_work_doubles(k) * sizeof(double);
   const int use_smem = need <= 224 * 1024 ? 1 : 0;
-  sym_eig_kernel<<<1, SM_THREADS, use_smem ? need : 0, st>>>(k, a, lda, upper ? 1 : 0, w, work, use_smem, status_dev);
+  sym_eig_kernel<<<1, SM_THREADS, use_smem ? need : 0, st>>>(k, a, lda, upper ? 1 : 0, w, work, use_smem,
+                                                              g_eig_two_sided ? 1 : 0, status_dev);
   ++g_launches;
   DLB_CUDA_CHECK(cudaGetLastError());
 }

@@ -150,6 +150,48 @@ def test_sym_eig_lobpcg_like_matrix(K, oracle):
     assert np.all(z[np.abs(z).argmax(axis=0), np.arange(k)] > 0)
 
 
+def test_sym_eig_indefinite_and_plus_minus_pairs(K, oracle):
+    """indefinite input works in the one-sided solver; exact +-lambda pairs make its verification
+    fail and exercise the two-sided fallback (sweeps reported as 100 + n)"""
+    rng = np.random.default_rng(11)
+    k = 40
+    q, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    lam = np.linspace(-3.0, 5.0, k)
+    a = (q * lam) @ q.T
+    a = 0.5 * (a + a.T)
+    w, z, sweeps = K.sym_eig(a)
+    assert sweeps < 100
+    assert np.abs(w - np.sort(lam)).max() < 1e-13 * 10
+    assert np.abs(a @ z - z * w).max() < 1e-13 * 10
+    lam2 = np.concatenate([np.linspace(1.0, 2.0, k // 2), -np.linspace(1.0, 2.0, k // 2)])
+    b = (q * lam2) @ q.T
+    b = 0.5 * (b + b.T)
+    w2, z2, sweeps2 = K.sym_eig(b)
+    assert np.abs(w2 - np.sort(lam2)).max() < 1e-13 * 10
+    assert np.abs(b @ z2 - z2 * w2).max() < 1e-13 * 10
+    assert np.abs(z2.T @ z2 - np.eye(k)).max() < 1e-13
+    c = np.array([[0.0, 1.0], [1.0, 0.0]])
+    w3, z3, sweeps3 = K.sym_eig(c)
+    assert sweeps3 >= 100 and np.allclose(w3, [-1.0, 1.0]) and np.abs(c @ z3 - z3 * w3).max() < 1e-15
+
+
+def test_sym_eig_graded_matrix_relative_accuracy(K, oracle):
+    """LOBPCG-like reduced matrix: Ritz values 7..44 next to 1e6-1e7 (W block): the small
+    eigenvalues must keep ~1e-13 RELATIVE accuracy (the parity bar is 1e-10 relative)"""
+    rng = np.random.default_rng(12)
+    k = 111
+    d = np.concatenate([np.arange(7.0, 44.0), 50 + 1e3 * rng.random(37), 1e6 + 1e7 * rng.random(37)])
+    cpl = rng.standard_normal((k, k))
+    cpl = 1e-3 * (cpl + cpl.T) * np.sqrt(np.outer(d, d)) / d.max() ** 0.5
+    a = np.diag(d) + cpl
+    np.fill_diagonal(a, d)
+    w, z, sweeps = K.sym_eig(a)
+    w_lapack, _ = oracle.dsyev(a)
+    # agree with LAPACK to 1e-12 relative on the small eigenvalues
+    assert (np.abs(w[:37] - w_lapack[:37]) / np.abs(w_lapack[:37])).max() < 1e-12
+    assert np.abs(a @ z[:, :37] - z[:, :37] * w[:37]).max() < 1e-8
+
+
 # ---- Cholesky factor + inverse + norm estimates (one ortho_cd pass) ---------------------------
 @pytest.mark.parametrize("m", [1, 5, 15, 37, 64, 100, 133])
 def test_chol_inv(K, oracle, m):
