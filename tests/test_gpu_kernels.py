@@ -151,8 +151,7 @@ def test_sym_eig_lobpcg_like_matrix(K, oracle):
 
 
 def test_sym_eig_indefinite_and_plus_minus_pairs(K, oracle):
-    """indefinite input works in the one-sided solver; exact +-lambda pairs make its verification
-    fail and exercise the two-sided fallback (sweeps reported as 100 + n)"""
+    """indefinite input and exact +-lambda pairs (the case a one-sided Jacobi cannot resolve)"""
     rng = np.random.default_rng(11)
     k = 40
     q, _ = np.linalg.qr(rng.standard_normal((k, k)))
@@ -160,7 +159,6 @@ def test_sym_eig_indefinite_and_plus_minus_pairs(K, oracle):
     a = (q * lam) @ q.T
     a = 0.5 * (a + a.T)
     w, z, sweeps = K.sym_eig(a)
-    assert sweeps < 100
     assert np.abs(w - np.sort(lam)).max() < 1e-13 * 10
     assert np.abs(a @ z - z * w).max() < 1e-13 * 10
     lam2 = np.concatenate([np.linspace(1.0, 2.0, k // 2), -np.linspace(1.0, 2.0, k // 2)])
@@ -172,7 +170,7 @@ def test_sym_eig_indefinite_and_plus_minus_pairs(K, oracle):
     assert np.abs(z2.T @ z2 - np.eye(k)).max() < 1e-13
     c = np.array([[0.0, 1.0], [1.0, 0.0]])
     w3, z3, sweeps3 = K.sym_eig(c)
-    assert sweeps3 >= 100 and np.allclose(w3, [-1.0, 1.0]) and np.abs(c @ z3 - z3 * w3).max() < 1e-15
+    assert np.allclose(w3, [-1.0, 1.0]) and np.abs(c @ z3 - z3 * w3).max() < 1e-15
 
 
 def test_sym_eig_graded_matrix_relative_accuracy(K, oracle):
