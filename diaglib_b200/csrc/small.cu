@@ -177,27 +177,22 @@ chol_inv_kernel(int m, const double* G, int ldg, double* T, double* work, CholSt
 // to be orthogonal to working precision, c^2 + s^2 = 1, its angle may be approximate).
 // Eigenvalues ascending, eigenvectors with their largest component positive.
 // ---------------------------------------------------------------------------------------
-// 1/sqrt(x), x > 0 finite and in float range after scaling: FP32 seed + 3 Newton steps
+// 1/sqrt(x) for x inside the float range: FP32 hardware seed + 3 Newton steps in FP64
 __device__ __forceinline__ double fast_rsqrt(double x) {
-  int e;
-  const double m = frexp(x, &e);            // x = m 2^e, m in [0.5,1)
-  const int e2 = e & ~1;                     // even part of the exponent
-  const double xs = ldexp(m, e - e2);       // in [0.5, 2)
-  double y = (double)rsqrtf((float)xs);
-  y = y * (1.5 - 0.5 * xs * y * y);
-  y = y * (1.5 - 0.5 * xs * y * y);
-  y = y * (1.5 - 0.5 * xs * y * y);
-  return ldexp(y, -(e2 / 2));
+  double y = (double)rsqrtf((float)x);
+  const double hx = 0.5 * x;
+  y = y * (1.5 - hx * y * y);
+  y = y * (1.5 - hx * y * y);
+  y = y * (1.5 - hx * y * y);
+  return y;
 }
-// 1/x, x != 0 finite: FP32 seed + 3 Newton steps
+// 1/x for |x| inside the float range: FP32 seed + 3 Newton steps
 __device__ __forceinline__ double fast_rcp(double x) {
-  int e;
-  const double m = frexp(x, &e);
-  double y = (double)__frcp_rn((float)m);
-  y = y * (2.0 - m * y);
-  y = y * (2.0 - m * y);
-  y = y * (2.0 - m * y);
-  return ldexp(y, -e);
+  double y = (double)__frcp_rn((float)x);
+  y = y * (2.0 - x * y);
+  y = y * (2.0 - x * y);
+  y = y * (2.0 - x * y);
+  return y;
 }
 
 __device__ __forceinline__ void rr_pair(int r, int idx, int kp, int& p, int& q) {
@@ -237,14 +232,14 @@ __device__ int jacobi_two_sided(int kp, int lds, double* A, double* Z, double* r
         double c = 1.0, s = 0.0;
         // rotate iff |apq| > eps sqrt(|app aqq|)  (compared squared: no square root needed)
         if (apq * apq > (EPS * EPS) * fabs(app) * fabs(aqq) && fabs(apq) > 1e-150) {
-          const double tau = (aqq - app) * 0.5 * fast_rcp(apq);
+          const double tau = (aqq - app) / (2.0 * apq);
           double t;
-          if (fabs(tau) < 1e150) {
-            const double t2 = 1.0 + tau * tau;
+          if (fabs(tau) < 1e8) {
+            const double t2 = 1.0 + tau * tau;                          // in [1, 1e16]
             const double r = t2 * fast_rsqrt(t2);                       // sqrt(1 + tau^2)
             t = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(tau) + r);
           } else {
-            t = (fabs(tau) < 1e300) ? 0.5 * fast_rcp(tau) : 0.0;        // |tau| huge: t ~ 1/(2 tau)
+            t = 0.5 / tau;                                              // sqrt(1 + tau^2) == |tau| in FP64
           }
           c = fast_rsqrt(1.0 + t * t);
           s = t * c;
