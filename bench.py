@@ -186,6 +186,8 @@ def main():
     from diaglib_b200 import dist as DD, kernels as K, partition
 
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
