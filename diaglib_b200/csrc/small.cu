@@ -10,6 +10,9 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cooperative_groups.h>
+
+#include <algorithm>
 #include <cfloat>
 
 namespace dlb {
@@ -350,6 +353,158 @@ sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, in
 }
 
 // ---------------------------------------------------------------------------------------
+// Multi-CTA symmetric eigensolver for reduced problems that do not fit one SM's shared memory
+// (k > 118: Davidson subspaces, LOBPCG with many roots).  Same two-sided parallel-order Jacobi,
+// reformulated so that every pass over the matrix is a coalesced COLUMN access:
+//     A' = J^T A J  ==>  A'(:,p) = R (c a_p - s a_q),  A'(:,q) = R (s a_p + c a_q)
+// where R applies the row rotations of ALL pairs of the round to a k-vector (entry i is combined
+// with its partner entry).  A and Z live in global memory (L2 resident: 2 k^2 doubles), the pairs
+// of a round are spread over the warps of a cooperative grid, and a round is
+//     angles (needs a_pp, a_qq, a_pq) -> grid.sync -> column updates -> grid.sync.
+// Replicated per rank like the single-CTA solver; deterministic (no atomics in the data path).
+// ---------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+
+__global__ void __launch_bounds__(256)
+sym_eig_coop_kernel(int k, const double* a, int lda, int upper, double* A, double* Z, double* rot_c, double* rot_s,
+                    int* partner, int* flags, int max_sweeps, EigStatus* st) {
+  extern __shared__ __align__(16) double stash[];  // per warp: 2*kp doubles (b_p, b_q)
+  cg::grid_group grid = cg::this_grid();
+  const int kp = (k + 1) & ~1;
+  const int half = kp / 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int gwarp = blockIdx.x * nwarp + warp, gwarps = gridDim.x * nwarp;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gthreads = (size_t)gridDim.x * blockDim.x;
+  double* bp = stash + (size_t)warp * 2 * kp;
+  double* bq = bp + kp;
+
+  for (size_t e = gtid; e < (size_t)kp * kp; e += gthreads) {
+    const int i = (int)(e % kp), j = (int)(e / kp);
+    double v = 0.0;
+    if (i < k && j < k) {
+      const int lo = i < j ? i : j, hi = i < j ? j : i;
+      v = upper ? a[lo + (size_t)hi * lda] : a[hi + (size_t)lo * lda];
+    }
+    A[e] = v;
+    Z[e] = (i == j) ? 1.0 : 0.0;
+  }
+  if (gtid == 0) { flags[0] = 0; flags[1] = 0; }
+  grid.sync();
+
+  int sweeps = 0, converged = 0;
+  while (sweeps < max_sweeps) {
+    for (int r = 0; r < kp - 1; ++r) {
+      // ---- angles: one thread per pair
+      for (size_t pr = gtid; pr < (size_t)half; pr += gthreads) {
+        int p, q;
+        rr_pair(r, (int)pr, kp, p, q);
+        const double app = __ldcg(&A[p + (size_t)p * kp]), aqq = __ldcg(&A[q + (size_t)q * kp]),
+                     apq = __ldcg(&A[p + (size_t)q * kp]);
+        double c = 1.0, s = 0.0;
+        if (apq * apq > (EPS * EPS) * fabs(app) * fabs(aqq) && fabs(apq) > 1e-150) {
+          const double tau = (aqq - app) / (2.0 * apq);
+          double t;
+          if (fabs(tau) < 1e8) {
+            const double t2 = 1.0 + tau * tau;
+            const double rr = t2 * fast_rsqrt(t2);
+            t = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(tau) + rr);
+          } else {
+            t = 0.5 / tau;
+          }
+          c = fast_rsqrt(1.0 + t * t);
+          s = t * c;
+          flags[0] = 1;
+        }
+        // v'[p] = c v[p] - s v[q] ; v'[q] = s v[p] + c v[q]
+        rot_c[p] = c; rot_s[p] = -s; partner[p] = q;
+        rot_c[q] = c; rot_s[q] = s;  partner[q] = p;
+      }
+      grid.sync();
+      // ---- column updates: one warp per pair
+      for (int pr = gwarp; pr < half; pr += gwarps) {
+        int p, q;
+        rr_pair(r, pr, kp, p, q);
+        const double c = __ldcg(&rot_c[q]), s = __ldcg(&rot_s[q]);
+        if (s != 0.0) {
+          double* Ap = A + (size_t)p * kp;
+          double* Aq = A + (size_t)q * kp;
+          double* Zp = Z + (size_t)p * kp;
+          double* Zq = Z + (size_t)q * kp;
+          for (int i = lane; i < kp; i += 32) {
+            const double x = __ldcg(&Ap[i]), y = __ldcg(&Aq[i]);
+            bp[i] = c * x - s * y;
+            bq[i] = s * x + c * y;
+            const double u = __ldcg(&Zp[i]), v = __ldcg(&Zq[i]);
+            Zp[i] = c * u - s * v;
+            Zq[i] = s * u + c * v;
+          }
+          __syncwarp();
+          for (int i = lane; i < kp; i += 32) {
+            const int pi = __ldcg(&partner[i]);
+            const double ci = __ldcg(&rot_c[i]), si = __ldcg(&rot_s[i]);
+            double vp = ci * bp[i] + si * bp[pi];
+            double vq = ci * bq[i] + si * bq[pi];
+            if (i == q) vp = 0.0;   // the rotated pivot is exactly zero
+            if (i == p) vq = 0.0;
+            Ap[i] = vp;
+            Aq[i] = vq;
+          }
+          __syncwarp();
+        } else {
+          // this pair is not rotated, but its columns still receive the row rotations of the others
+          double* Ap = A + (size_t)p * kp;
+          double* Aq = A + (size_t)q * kp;
+          for (int i = lane; i < kp; i += 32) { bp[i] = __ldcg(&Ap[i]); bq[i] = __ldcg(&Aq[i]); }
+          __syncwarp();
+          for (int i = lane; i < kp; i += 32) {
+            const int pi = __ldcg(&partner[i]);
+            const double ci = __ldcg(&rot_c[i]), si = __ldcg(&rot_s[i]);
+            Ap[i] = ci * bp[i] + si * bp[pi];
+            Aq[i] = ci * bq[i] + si * bq[pi];
+          }
+          __syncwarp();
+        }
+      }
+      grid.sync();
+    }
+    ++sweeps;
+    const int any = __ldcg(&flags[0]);
+    grid.sync();
+    if (gtid == 0) flags[0] = 0;
+    grid.sync();
+    if (!any) { converged = 1; break; }
+  }
+  if (gtid == 0) { st->sweeps = sweeps; st->converged = converged; }
+}
+
+// eigenvalues = diag(A), ascending order, largest component positive, eigenvectors written to a
+__global__ void __launch_bounds__(1024)
+eig_finish_kernel(int k, int kp, const double* A, const double* Z, double* a, int lda, double* w, int* rank) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < k; i += nt) {
+    const double di = A[i + (size_t)i * kp];
+    int rk = 0;
+    for (int j = 0; j < k; ++j) {
+      const double dj = A[j + (size_t)j * kp];
+      rk += (dj < di || (dj == di && j < i)) ? 1 : 0;
+    }
+    double best = 0.0, sign = 1.0;
+    for (int rr = 0; rr < k; ++rr) {
+      const double v = Z[rr + (size_t)i * kp];
+      if (fabs(v) > best) { best = fabs(v); sign = v < 0.0 ? -1.0 : 1.0; }
+    }
+    w[rk] = di;
+    rank[i] = sign < 0.0 ? -(rk + 1) : (rk + 1);
+  }
+  __syncthreads();
+  for (int e = tid; e < k * k; e += nt) {
+    const int rr = e % k, i = e / k;
+    const int rk = rank[i];
+    a[rr + (size_t)((rk < 0 ? -rk : rk) - 1) * lda] = (rk < 0 ? -1.0 : 1.0) * Z[rr + (size_t)i * kp];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // get_coeffs (diaglib.f90:3686-3732) in one CTA: u_p = u_x(:,active) - e_i, then
 // ortho_vs_x(len_u, n_max, n_act, u_x, u_p) (3481-3574) with ortho_cd (3185-3341) inside.
 // ---------------------------------------------------------------------------------------
@@ -510,19 +665,56 @@ void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, 
 
 size_t eig_work_doubles(int k) {
   const int kp = (k + 1) & ~1, lds = kp | 1;
-  return 2 * (size_t)kp * lds + 4 * (size_t)kp + 8;
+  // single-CTA layout: A, Z (kp x lds) + eigenvalues + rotation tables;
+  // cooperative layout: A, Z (kp x kp) + rot_c, rot_s (kp) + partner, rank (kp ints) + flags
+  return 2 * (size_t)kp * lds + 6 * (size_t)kp + 16;
 }
 
-bool g_eig_two_sided = false;  // DIAGLIB_B200_EIG_TWO_SIDED=1: skip the one-sided solver (A/B testing)
+bool g_eig_two_sided = false;  // unused (kept for ABI of the A/B switch)
+int g_eig_coop_min_k = 119;    // DIAGLIB_B200_EIG_COOP_MIN_K: reduced problems at least this large use the multi-CTA solver
 
 void sym_eig(cudaStream_t st, int k, double* a, int lda, bool upper, double* w, double* work, EigStatus* status_dev) {
   static bool attr_set = false;
+  static int num_sms = 0, coop_ok = 0;
   if (!attr_set) {
     DLB_CUDA_CHECK(cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(sym_eig_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int dev = 0;
+    DLB_CUDA_CHECK(cudaGetDevice(&dev));
+    DLB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    DLB_CUDA_CHECK(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev));
     attr_set = true;
   }
+  const int kp = (k + 1) & ~1;
   const size_t need = eig_work_doubles(k) * sizeof(double);
-  const int use_smem = need <= 224 * 1024 ? 1 : 0;
+  const bool fits = need <= 224 * 1024;
+  if (coop_ok && (k >= g_eig_coop_min_k || !fits)) {
+    // multi-CTA solver: warps per CTA limited by the per-warp stash (2 kp doubles)
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * 2 * kp * sizeof(double) > 200 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * 2 * kp * sizeof(double);
+    if (smem <= 200 * 1024) {
+      const int half = kp / 2;
+      int grid = std::max(1, std::min(num_sms, (half + warps - 1) / warps));
+      double* A = work;
+      double* Z = A + (size_t)kp * kp;
+      double* rot_c = Z + (size_t)kp * kp;
+      double* rot_s = rot_c + kp;
+      int* partner = reinterpret_cast<int*>(rot_s + kp);
+      int* rank = partner + kp;
+      int* flags = rank + kp;
+      int max_sweeps = 40, ki = k, ldai = lda, up = upper ? 1 : 0;
+      const double* ain = a;
+      void* args[] = {&ki, &ain, &ldai, &up, &A, &Z, &rot_c, &rot_s, &partner, &flags, &max_sweeps, &status_dev};
+      DLB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sym_eig_coop_kernel, dim3(grid), dim3(warps * 32), args, smem, st));
+      ++g_launches;
+      eig_finish_kernel<<<1, 1024, 0, st>>>(k, kp, A, Z, a, lda, w, rank);
+      ++g_launches;
+      DLB_CUDA_CHECK(cudaGetLastError());
+      return;
+    }
+  }
+  const int use_smem = fits ? 1 : 0;
   sym_eig_kernel<<<1, SM_THREADS, use_smem ? need : 0, st>>>(k, a, lda, upper ? 1 : 0, w, work, use_smem,
                                                               g_eig_two_sided ? 1 : 0, status_dev);
   ++g_launches;

@@ -118,7 +118,7 @@ def test_residual_norms(K):
 
 
 # ---- symmetric eigensolver (dsyev replacement) ------------------------------------------------
-@pytest.mark.parametrize("k", [1, 2, 3, 15, 30, 45, 74, 111, 112, 150, 300])
+@pytest.mark.parametrize("k", [1, 2, 3, 15, 30, 45, 74, 111, 112, 118, 119, 133, 150, 300, 399, 700])
 def test_sym_eig_vs_lapack(K, oracle, k):
     rng = np.random.default_rng(k)
     s = rng.standard_normal((k, k))
