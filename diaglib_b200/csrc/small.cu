@@ -373,9 +373,9 @@ sym_eig_coop_kernel(int k, const double* a, int lda, int upper, double* A, doubl
   const int kp = (k + 1) & ~1;
   const int half = kp / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  const int gwarp = blockIdx.x * nwarp + warp, gwarps = gridDim.x * nwarp;
+  (void)lane; (void)warp; (void)nwarp;
   const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gthreads = (size_t)gridDim.x * blockDim.x;
-  double* bp = stash + (size_t)warp * 2 * kp;
+  double* bp = stash;       // b_p, b_q of the pair this CTA is updating
   double* bq = bp + kp;
 
   for (size_t e = gtid; e < (size_t)kp * kp; e += gthreads) {
@@ -420,50 +420,43 @@ sym_eig_coop_kernel(int k, const double* a, int lda, int upper, double* A, doubl
         rot_c[q] = c; rot_s[q] = s;  partner[q] = p;
       }
       grid.sync();
-      // ---- column updates: one warp per pair
-      for (int pr = gwarp; pr < half; pr += gwarps) {
+      // ---- column updates: one CTA per pair (all threads over the rows: the loads of a column
+      //      are all in flight at once, the L2 latency is paid once per sub-phase)
+      for (int pr = blockIdx.x; pr < half; pr += gridDim.x) {
         int p, q;
         rr_pair(r, pr, kp, p, q);
         const double c = __ldcg(&rot_c[q]), s = __ldcg(&rot_s[q]);
+        double* Ap = A + (size_t)p * kp;
+        double* Aq = A + (size_t)q * kp;
         if (s != 0.0) {
-          double* Ap = A + (size_t)p * kp;
-          double* Aq = A + (size_t)q * kp;
           double* Zp = Z + (size_t)p * kp;
           double* Zq = Z + (size_t)q * kp;
-          for (int i = lane; i < kp; i += 32) {
+          for (int i = tid; i < kp; i += blockDim.x) {
             const double x = __ldcg(&Ap[i]), y = __ldcg(&Aq[i]);
+            const double u = __ldcg(&Zp[i]), v = __ldcg(&Zq[i]);
             bp[i] = c * x - s * y;
             bq[i] = s * x + c * y;
-            const double u = __ldcg(&Zp[i]), v = __ldcg(&Zq[i]);
             Zp[i] = c * u - s * v;
             Zq[i] = s * u + c * v;
           }
-          __syncwarp();
-          for (int i = lane; i < kp; i += 32) {
-            const int pi = __ldcg(&partner[i]);
-            const double ci = __ldcg(&rot_c[i]), si = __ldcg(&rot_s[i]);
-            double vp = ci * bp[i] + si * bp[pi];
-            double vq = ci * bq[i] + si * bq[pi];
+        } else {
+          // not rotated itself, but its columns still receive the row rotations of the other pairs
+          for (int i = tid; i < kp; i += blockDim.x) { bp[i] = __ldcg(&Ap[i]); bq[i] = __ldcg(&Aq[i]); }
+        }
+        __syncthreads();
+        for (int i = tid; i < kp; i += blockDim.x) {
+          const int pi = __ldcg(&partner[i]);
+          const double ci = __ldcg(&rot_c[i]), si = __ldcg(&rot_s[i]);
+          double vp = ci * bp[i] + si * bp[pi];
+          double vq = ci * bq[i] + si * bq[pi];
+          if (s != 0.0) {
             if (i == q) vp = 0.0;   // the rotated pivot is exactly zero
             if (i == p) vq = 0.0;
-            Ap[i] = vp;
-            Aq[i] = vq;
           }
-          __syncwarp();
-        } else {
-          // this pair is not rotated, but its columns still receive the row rotations of the others
-          double* Ap = A + (size_t)p * kp;
-          double* Aq = A + (size_t)q * kp;
-          for (int i = lane; i < kp; i += 32) { bp[i] = __ldcg(&Ap[i]); bq[i] = __ldcg(&Aq[i]); }
-          __syncwarp();
-          for (int i = lane; i < kp; i += 32) {
-            const int pi = __ldcg(&partner[i]);
-            const double ci = __ldcg(&rot_c[i]), si = __ldcg(&rot_s[i]);
-            Ap[i] = ci * bp[i] + si * bp[pi];
-            Aq[i] = ci * bq[i] + si * bq[pi];
-          }
-          __syncwarp();
+          Ap[i] = vp;
+          Aq[i] = vq;
         }
+        __syncthreads();
       }
       grid.sync();
     }
@@ -689,13 +682,13 @@ void sym_eig(cudaStream_t st, int k, double* a, int lda, bool upper, double* w, 
   const size_t need = eig_work_doubles(k) * sizeof(double);
   const bool fits = need <= 224 * 1024;
   if (coop_ok && (k >= g_eig_coop_min_k || !fits)) {
-    // multi-CTA solver: warps per CTA limited by the per-warp stash (2 kp doubles)
-    int warps = 8;
-    while (warps > 1 && (size_t)warps * 2 * kp * sizeof(double) > 200 * 1024) warps >>= 1;
-    const size_t smem = (size_t)warps * 2 * kp * sizeof(double);
+    // multi-CTA solver: one CTA per pair and round, stash = 2 kp doubles
+    const int threads = kp <= 128 ? 128 : 256;
+    const int warps = threads / 32;
+    const size_t smem = (size_t)2 * kp * sizeof(double);
     if (smem <= 200 * 1024) {
       const int half = kp / 2;
-      int grid = std::max(1, std::min(num_sms, (half + warps - 1) / warps));
+      int grid = std::max(1, std::min(num_sms, half));
       double* A = work;
       double* Z = A + (size_t)kp * kp;
       double* rot_c = Z + (size_t)kp * kp;

@@ -129,6 +129,29 @@ def test_sparse_configs_small(gpu_lib, oracle, driver, gen):
     assert_history(ro, hg, n_targ, upto=5 if gen == "lap3d_32roots" else None)
 
 
+@pytest.mark.parametrize("driver", ["lobpcg", "davidson"])
+def test_many_roots_c5_scaled(gpu_lib, oracle, driver):
+    """scaled-down C5 (many-root stress): 128 roots of 133.  LOBPCG reduced problems reach
+    len_u = 399, Davidson lda = 1330 with a restart: exercises the multi-CTA reduced eigensolver,
+    ortho_cd at m = 133 (in-place trmm in column blocks) and block products wider than one tile."""
+    csr = P.toy_sparse(1 << 13)
+    ro, ok, eig_g, ev_g, hg, _ = run_both(gpu_lib, oracle, driver, csr, 128, 133, max_iter=200, max_dav=10)
+    assert ok and ro["ok"]
+    assert_parity(ro, ok, eig_g, hg, 128)
+    check_solution(csr, eig_g, ev_g, 128, 1e-8)
+
+
+def test_c2_full_size(gpu_lib, oracle):
+    """config C2 at its full size: sparsified toy matrix, n = 2^20, 8 roots of 13, LOBPCG"""
+    n = 1 << 20
+    csr = P.toy_sparse(n)
+    ro, ok, eig_g, ev_g, hg, _ = run_both(gpu_lib, oracle, "lobpcg", csr, 8, 13, max_iter=100)
+    assert ok and ro["ok"]
+    assert_parity(ro, ok, eig_g, hg, 8)
+    check_solution(csr, eig_g, ev_g, 8, 1e-8)
+    assert_history(ro, hg, 8)
+
+
 def test_slow_random_start_long_run(gpu_lib, oracle):
     """A hard start (random guess on a disordered Laplacian) needs ~100 iterations and its
     iteration count is chaotic: the ORACLE ITSELF moves by +-15% when the guess is scaled by
