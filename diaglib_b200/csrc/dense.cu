@@ -1166,6 +1166,17 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
 void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc, int q,
                double alpha, double beta, double* Y, int64_t ldy, bool upper_tri) {
   if (n <= 0 || q <= 0) return;
+  if (q > 128) {
+    // column blocks of Y are produced one launch at a time: Y must not overlap the columns of V
+    const double* v0 = V;
+    const double* v1 = V + (int64_t)(p - 1) * ldv + n;
+    const double* y0 = Y;
+    const double* y1 = Y + (int64_t)(q - 1) * ldy + n;
+    if (y0 < v1 && v0 < y1) {
+      std::fprintf(stderr, "diaglib_b200: block_mul called in place with q = %d > 128 columns\n", q);
+      std::abort();
+    }
+  }
   for (int q0 = 0; q0 < q; q0 += 128) {
     const int qb = std::min(128, q - q0);
     const double* Cb = C + (size_t)q0 * ldc;

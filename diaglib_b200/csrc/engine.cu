@@ -531,8 +531,12 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
   sym_eig(st, n_max, a_red, n_max, false, e_red, eig_work, d_eigst);                   // 315
   ph_close(h);
   h = ph_open(PH_RITZ);
-  kbmul(nn, space, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, space, nn);       // 322-323 (row-local, in place)
-  kbmul(nn, aspace, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, aspace, nn);     // 324-325
+  // 322-325: Ritz rotation of X and AX, written into the other half of the double buffer (an
+  // in-place product is only row-local for q <= 128 columns; n_max may be larger)
+  kbmul(nn, space, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, space2, nn);
+  kbmul(nn, aspace, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, aspace2, nn);
+  std::swap(space, space2);
+  std::swap(aspace, aspace2);
   ph_close(h);
   h = ph_open(PH_RESID);
   DLB_CUDA_CHECK(cudaMemcpyAsync(d_active, h_active.data(), n_max * sizeof(int), cudaMemcpyHostToDevice, st));
