@@ -1,0 +1,34 @@
+"""Davidson-Liu on the C3 matrix at reduced size (one GPU): time to converge and phase split."""
+import json
+import sys
+import time
+import numpy as np
+sys.path.insert(0, ".")
+import diaglib_b200 as D
+from diaglib_b200 import kernels as K, problems as P
+
+nx = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+max_dav = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+n = nx ** 3
+n_targ, n_max = 32, 37
+D.init(0)
+csr = P.lap3d(nx, nx, nx, delta=1.0)
+D.set_csr(*csr)
+g = np.asfortranarray(P.guess_lowest_diag(csr[3], n_max) + P.guess(n, n_max) * (0.1 / np.sqrt(n / 12.0)))
+dg = K.DeviceArray.from_numpy(g)
+dev = K.DeviceArray((n, n_max))
+eig = np.zeros(n_max)
+out = {}
+for drv in ("davidson", "lobpcg"):
+    for rep in range(2):
+        D.lib().diaglib_b200_d2d(dev.ptr, dg.ptr, g.nbytes)
+        K.timer_start()
+        if drv == "davidson":
+            ok = D.davidson_driver(False, n, n_targ, n_max, 200, 1e-8, max_dav, 0.0, None, None, eig, dev)
+        else:
+            ok = D.lobpcg_driver(False, False, n, n_targ, n_max, 200, 1e-8, 0.0, None, None, None, eig, dev)
+        ms = K.timer_stop_ms()
+    its = len(D.last_history(n_max)["it"])
+    out[drv] = dict(ok=ok, its=its, ms=round(ms, 1), phases={k: round(float(v), 4) for k, v in D.last_timers().items()},
+                    stats=D.last_stats())
+print(json.dumps(dict(n=n, max_dav=max_dav, **out)))
