@@ -968,8 +968,7 @@ int32_t diaglib_b200_init(int32_t device) {
   if (!g.partial.ensure(gram_scratch_bytes(128, 128, g.num_sms))) return DIAGLIB_B200_EALLOC;
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_WS")) g_disable_ws = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_TMA")) g_disable_tma = ev[0] == '1';
-  if (const char* ev = std::getenv("DIAGLIB_B200_EIG_MULTI_MIN_K")) g_eig_multi_min_k = std::atoi(ev);
-  if (const char* ev = std::getenv("DIAGLIB_B200_EIG_CLUSTER_MAX_K")) g_eig_cluster_max_k = std::atoi(ev);
+  if (const char* ev = std::getenv("DIAGLIB_B200_EIG_COOP_MIN_K")) g_eig_coop_min_k = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_BMUL_RT256")) g_bmul_small_tiles = ev[0] != '1';
   g.inited = true;
   g.status = 0;

@@ -353,43 +353,30 @@ sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, in
 }
 
 // ---------------------------------------------------------------------------------------
-// Multi-CTA symmetric eigensolver: the same two-sided parallel-order Jacobi, reformulated so that
-// every pass over the matrix is a coalesced COLUMN access and a round needs ONE barrier:
+// Multi-CTA symmetric eigensolver for reduced problems that do not fit one SM's shared memory
+// (k > 118: Davidson subspaces, LOBPCG with many roots).  Same two-sided parallel-order Jacobi,
+// reformulated so that every pass over the matrix is a coalesced COLUMN access:
 //     A' = J^T A J  ==>  A'(:,p) = R (c a_p - s a_q),  A'(:,q) = R (s a_p + c a_q)
 // where R applies the row rotations of ALL pairs of the round to a k-vector (entry i is combined
-// with its partner entry).  Round t stores only the column-rotated "raw" columns; the row
-// rotations R_t are applied lazily in round t+1 by whichever warp loads a column (every column is
-// loaded exactly once per round).  A warp owns a pair: load raw columns -> apply pending R ->
-// angle from its own columns -> publish (c,s) -> rotate and store -> barrier.
-// A and Z live in global memory (L2 resident).  Two launch forms of the same code:
-//   * one thread-block cluster of 8 CTAs with the hardware cluster barrier (k <= 256: the
-//     LOBPCG reduced problems; a round costs ~1.4 us instead of ~3.9 us in one CTA), and
-//   * a cooperative grid with grid.sync for larger k (Davidson subspaces, many roots).
-// Replicated per rank like the single-CTA solver; deterministic.
+// with its partner entry).  A and Z live in global memory (L2 resident: 2 k^2 doubles), the pairs
+// of a round are spread over the warps of a cooperative grid, and a round is
+//     angles (needs a_pp, a_qq, a_pq) -> grid.sync -> column updates -> grid.sync.
+// Replicated per rank like the single-CTA solver; deterministic (no atomics in the data path).
 // ---------------------------------------------------------------------------------------
 namespace cg = cooperative_groups;
 
-template <bool CLUSTER>
-__device__ __forceinline__ void multi_sync() {
-  if (CLUSTER) cg::this_cluster().sync();
-  else cg::this_grid().sync();
-}
-
-template <bool CLUSTER>
 __global__ void __launch_bounds__(256)
-sym_eig_multi_kernel(int k, const double* a, int lda, int upper, double* A, double* Z, double* rot, int* flags,
-                     int max_sweeps, EigStatus* st) {
-  extern __shared__ __align__(16) double stash[];  // per warp: 4*kp doubles (raw p, raw q, rotated p, rotated q)
+sym_eig_coop_kernel(int k, const double* a, int lda, int upper, double* A, double* Z, double* rot_c, double* rot_s,
+                    int* partner, int* flags, int max_sweeps, EigStatus* st) {
+  extern __shared__ __align__(16) double stash[];  // per warp: 2*kp doubles (b_p, b_q)
+  cg::grid_group grid = cg::this_grid();
   const int kp = (k + 1) & ~1;
   const int half = kp / 2;
-  const int km1 = kp - 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  const int gwarp = blockIdx.x * nwarp + warp, gwarps = gridDim.x * nwarp;
+  (void)lane; (void)warp; (void)nwarp;
   const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gthreads = (size_t)gridDim.x * blockDim.x;
-  double* bp = stash + (size_t)warp * 4 * kp;
+  double* bp = stash;       // b_p, b_q of the pair this CTA is updating
   double* bq = bp + kp;
-  double* vp = bq + kp;
-  double* vq = vp + kp;
 
   for (size_t e = gtid; e < (size_t)kp * kp; e += gthreads) {
     const int i = (int)(e % kp), j = (int)(e / kp);
@@ -401,98 +388,83 @@ sym_eig_multi_kernel(int k, const double* a, int lda, int upper, double* A, doub
     A[e] = v;
     Z[e] = (i == j) ? 1.0 : 0.0;
   }
-  if (gtid == 0) flags[0] = 0;
-  multi_sync<CLUSTER>();
+  if (gtid == 0) { flags[0] = 0; flags[1] = 0; }
+  grid.sync();
 
   int sweeps = 0, converged = 0;
-  long long t = 0;  // global round counter
   while (sweeps < max_sweeps) {
-    for (int r = 0; r < km1; ++r, ++t) {
-      double* rc_cur = rot + (size_t)(t & 1) * kp;          // [half] cosines, [half] sines
-      double* rs_cur = rc_cur + half;
-      const double* rc_prev = rot + (size_t)((t + 1) & 1) * kp;
-      const double* rs_prev = rc_prev + half;
-      const int rprev = (r == 0) ? km1 - 1 : r - 1;
-      for (int pr = gwarp; pr < half; pr += gwarps) {
+    for (int r = 0; r < kp - 1; ++r) {
+      // ---- angles: one thread per pair
+      for (size_t pr = gtid; pr < (size_t)half; pr += gthreads) {
         int p, q;
-        rr_pair(r, pr, kp, p, q);
-        double* Ap = A + (size_t)p * kp;
-        double* Aq = A + (size_t)q * kp;
-        for (int i = lane; i < kp; i += 32) { bp[i] = __ldcg(&Ap[i]); bq[i] = __ldcg(&Aq[i]); }
-        __syncwarp();
-        if (t > 0) {
-          // pending row rotations of the previous round
-          for (int i = lane; i < kp; i += 32) {
-            int partner, pidx;
-            if (i == km1) { partner = rprev; pidx = 0; }
-            else {
-              int d = i - rprev;
-              if (d < 0) d += km1;
-              if (d == 0) { partner = km1; pidx = 0; }
-              else {
-                pidx = d < km1 - d ? d : km1 - d;
-                partner = 2 * rprev - i;
-                partner %= km1;
-                if (partner < 0) partner += km1;
-              }
-            }
-            const double c = __ldcg(&rc_prev[pidx]), sn = __ldcg(&rs_prev[pidx]);
-            if (i < partner) {   // i is the 'p' of its pair: v'[p] = c v[p] - s v[q]
-              vp[i] = c * bp[i] - sn * bp[partner];
-              vq[i] = c * bq[i] - sn * bq[partner];
-            } else {             // i is the 'q': v'[q] = s v[p] + c v[q]
-              vp[i] = sn * bp[partner] + c * bp[i];
-              vq[i] = sn * bq[partner] + c * bq[i];
-            }
-          }
-        } else {
-          for (int i = lane; i < kp; i += 32) { vp[i] = bp[i]; vq[i] = bq[i]; }
-        }
-        __syncwarp();
-        // rotation angle from the pair's own (now current) columns
-        const double app = vp[p], aqq = vq[q], apq = vq[p];
-        double c = 1.0, sn = 0.0;
+        rr_pair(r, (int)pr, kp, p, q);
+        const double app = __ldcg(&A[p + (size_t)p * kp]), aqq = __ldcg(&A[q + (size_t)q * kp]),
+                     apq = __ldcg(&A[p + (size_t)q * kp]);
+        double c = 1.0, s = 0.0;
         if (apq * apq > (EPS * EPS) * fabs(app) * fabs(aqq) && fabs(apq) > 1e-150) {
           const double tau = (aqq - app) / (2.0 * apq);
-          double tt;
+          double t;
           if (fabs(tau) < 1e8) {
             const double t2 = 1.0 + tau * tau;
             const double rr = t2 * fast_rsqrt(t2);
-            tt = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(tau) + rr);
+            t = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(tau) + rr);
           } else {
-            tt = 0.5 / tau;
+            t = 0.5 / tau;
           }
-          c = fast_rsqrt(1.0 + tt * tt);
-          sn = tt * c;
+          c = fast_rsqrt(1.0 + t * t);
+          s = t * c;
+          flags[0] = 1;
         }
-        if (lane == 0) {
-          rc_cur[pr] = c;
-          rs_cur[pr] = sn;
-          if (sn != 0.0) flags[0] = 1;
-        }
-        if (sn != 0.0) {
+        // v'[p] = c v[p] - s v[q] ; v'[q] = s v[p] + c v[q]
+        rot_c[p] = c; rot_s[p] = -s; partner[p] = q;
+        rot_c[q] = c; rot_s[q] = s;  partner[q] = p;
+      }
+      grid.sync();
+      // ---- column updates: one CTA per pair (all threads over the rows: the loads of a column
+      //      are all in flight at once, the L2 latency is paid once per sub-phase)
+      for (int pr = blockIdx.x; pr < half; pr += gridDim.x) {
+        int p, q;
+        rr_pair(r, pr, kp, p, q);
+        const double c = __ldcg(&rot_c[q]), s = __ldcg(&rot_s[q]);
+        double* Ap = A + (size_t)p * kp;
+        double* Aq = A + (size_t)q * kp;
+        if (s != 0.0) {
           double* Zp = Z + (size_t)p * kp;
           double* Zq = Z + (size_t)q * kp;
-          for (int i = lane; i < kp; i += 32) {
-            const double x = vp[i], y = vq[i];
-            Ap[i] = c * x - sn * y;
-            Aq[i] = sn * x + c * y;
+          for (int i = tid; i < kp; i += blockDim.x) {
+            const double x = __ldcg(&Ap[i]), y = __ldcg(&Aq[i]);
             const double u = __ldcg(&Zp[i]), v = __ldcg(&Zq[i]);
-            Zp[i] = c * u - sn * v;
-            Zq[i] = sn * u + c * v;
+            bp[i] = c * x - s * y;
+            bq[i] = s * x + c * y;
+            Zp[i] = c * u - s * v;
+            Zq[i] = s * u + c * v;
           }
-        } else if (t > 0) {
-          for (int i = lane; i < kp; i += 32) { Ap[i] = vp[i]; Aq[i] = vq[i]; }
+        } else {
+          // not rotated itself, but its columns still receive the row rotations of the other pairs
+          for (int i = tid; i < kp; i += blockDim.x) { bp[i] = __ldcg(&Ap[i]); bq[i] = __ldcg(&Aq[i]); }
         }
-        __syncwarp();
+        __syncthreads();
+        for (int i = tid; i < kp; i += blockDim.x) {
+          const int pi = __ldcg(&partner[i]);
+          const double ci = __ldcg(&rot_c[i]), si = __ldcg(&rot_s[i]);
+          double vp = ci * bp[i] + si * bp[pi];
+          double vq = ci * bq[i] + si * bq[pi];
+          if (s != 0.0) {
+            if (i == q) vp = 0.0;   // the rotated pivot is exactly zero
+            if (i == p) vq = 0.0;
+          }
+          Ap[i] = vp;
+          Aq[i] = vq;
+        }
+        __syncthreads();
       }
-      multi_sync<CLUSTER>();
+      grid.sync();
     }
     ++sweeps;
     const int any = __ldcg(&flags[0]);
-    multi_sync<CLUSTER>();
+    grid.sync();
     if (gtid == 0) flags[0] = 0;
-    multi_sync<CLUSTER>();
+    grid.sync();
     if (!any) { converged = 1; break; }
   }
   if (gtid == 0) { st->sweeps = sweeps; st->converged = converged; }
@@ -692,16 +664,14 @@ size_t eig_work_doubles(int k) {
 }
 
 bool g_eig_two_sided = false;  // unused (kept for ABI of the A/B switch)
-int g_eig_multi_min_k = 16;     // DIAGLIB_B200_EIG_MULTI_MIN_K: reduced problems at least this large use the multi-CTA solver
-int g_eig_cluster_max_k = 256;  // DIAGLIB_B200_EIG_CLUSTER_MAX_K: up to this size one 8-CTA cluster, beyond a cooperative grid
+int g_eig_coop_min_k = 119;    // DIAGLIB_B200_EIG_COOP_MIN_K: reduced problems at least this large use the multi-CTA solver
 
 void sym_eig(cudaStream_t st, int k, double* a, int lda, bool upper, double* w, double* work, EigStatus* status_dev) {
   static bool attr_set = false;
   static int num_sms = 0, coop_ok = 0;
   if (!attr_set) {
     DLB_CUDA_CHECK(cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    DLB_CUDA_CHECK(cudaFuncSetAttribute(sym_eig_multi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DLB_CUDA_CHECK(cudaFuncSetAttribute(sym_eig_multi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(sym_eig_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int dev = 0;
     DLB_CUDA_CHECK(cudaGetDevice(&dev));
     DLB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -711,53 +681,30 @@ void sym_eig(cudaStream_t st, int k, double* a, int lda, bool upper, double* w, 
   const int kp = (k + 1) & ~1;
   const size_t need = eig_work_doubles(k) * sizeof(double);
   const bool fits = need <= 224 * 1024;
-  if (k >= g_eig_multi_min_k || !fits) {
-    const int half = kp / 2;
-    int warps = 8;
-    while (warps > 1 && (size_t)warps * 4 * kp * sizeof(double) > 200 * 1024) warps >>= 1;
-    const size_t smem = (size_t)warps * 4 * kp * sizeof(double);
-    double* A = work;
-    double* Z = A + (size_t)kp * kp;
-    double* rot = Z + (size_t)kp * kp;                       // 2 x (half cosines + half sines)
-    int* rank = reinterpret_cast<int*>(rot + 2 * (size_t)kp);
-    int* flags = rank + kp;
-    int max_sweeps = 40;
+  if (coop_ok && (k >= g_eig_coop_min_k || !fits)) {
+    // multi-CTA solver: one CTA per pair and round, stash = 2 kp doubles
+    const int threads = kp <= 128 ? 128 : 256;
+    const int warps = threads / 32;
+    const size_t smem = (size_t)2 * kp * sizeof(double);
     if (smem <= 200 * 1024) {
-      if (kp <= g_eig_cluster_max_k) {
-        // one cluster of 8 CTAs, hardware cluster barrier
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(8);
-        cfg.blockDim = dim3(warps * 32);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 8;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        DLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sym_eig_multi_kernel<true>, k, (const double*)a, lda, upper ? 1 : 0, A, Z, rot,
-                                          flags, max_sweeps, status_dev));
-        ++g_launches;
-        eig_finish_kernel<<<1, 1024, 0, st>>>(k, kp, A, Z, a, lda, w, rank);
-        ++g_launches;
-        DLB_CUDA_CHECK(cudaGetLastError());
-        return;
-      }
-      if (coop_ok) {
-        int grid = std::max(1, std::min(num_sms, (half + warps - 1) / warps));
-        int ki = k, ldai = lda, up = upper ? 1 : 0;
-        const double* ain = a;
-        void* args[] = {&ki, &ain, &ldai, &up, &A, &Z, &rot, &flags, &max_sweeps, &status_dev};
-        DLB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sym_eig_multi_kernel<false>, dim3(grid), dim3(warps * 32), args,
-                                                   smem, st));
-        ++g_launches;
-        eig_finish_kernel<<<1, 1024, 0, st>>>(k, kp, A, Z, a, lda, w, rank);
-        ++g_launches;
-        DLB_CUDA_CHECK(cudaGetLastError());
-        return;
-      }
+      const int half = kp / 2;
+      int grid = std::max(1, std::min(num_sms, half));
+      double* A = work;
+      double* Z = A + (size_t)kp * kp;
+      double* rot_c = Z + (size_t)kp * kp;
+      double* rot_s = rot_c + kp;
+      int* partner = reinterpret_cast<int*>(rot_s + kp);
+      int* rank = partner + kp;
+      int* flags = rank + kp;
+      int max_sweeps = 40, ki = k, ldai = lda, up = upper ? 1 : 0;
+      const double* ain = a;
+      void* args[] = {&ki, &ain, &ldai, &up, &A, &Z, &rot_c, &rot_s, &partner, &flags, &max_sweeps, &status_dev};
+      DLB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sym_eig_coop_kernel, dim3(grid), dim3(warps * 32), args, smem, st));
+      ++g_launches;
+      eig_finish_kernel<<<1, 1024, 0, st>>>(k, kp, A, Z, a, lda, w, rank);
+      ++g_launches;
+      DLB_CUDA_CHECK(cudaGetLastError());
+      return;
     }
   }
   const int use_smem = fits ? 1 : 0;
