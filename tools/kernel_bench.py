@@ -61,6 +61,27 @@ def main():
         t_bmul(37, 37, "bmul_37x37")
         print(json.dumps(dict(n=n, **out)))
         return
+    if only == "spmm":
+        import ctypes as C
+        from diaglib_b200 import problems as P
+        nx = round(n ** (1 / 3))
+        csr = P.lap3d(nx, nx, nx, delta=1.0)
+        D.set_csr(*csr)
+        nnz = len(csr[1])
+        for m in (40, 37, 32, 24, 16, 8):
+            ax = K.DeviceArray((n, m))
+            i32 = lambda v_: C.byref(C.c_int32(v_))
+            lib.diaglib_b200_csr_matvec(i32(n), i32(m), C.c_void_p(v.ptr), C.c_void_p(ax.ptr))
+            lib.diaglib_b200_sync()
+            K.timer_start()
+            for _ in range(reps):
+                lib.diaglib_b200_csr_matvec(i32(n), i32(m), C.c_void_p(v.ptr), C.c_void_p(ax.ptr))
+            ms = K.timer_stop_ms() / reps
+            by = 12.0 * nnz + 8.0 * (n + 1) + 16.0 * n * m
+            out["spmm_m%d" % m] = dict(ms=round(ms, 4), gbs=round(by / ms / 1e6, 1), bytes=by)
+            ax.free()
+        print(json.dumps(dict(n=n, **out)))
+        return
     if only == "gram":
         t_gram(111, 111, 1, v, w, "gram_sym_111")
         t_gram(74, 37, 0, v, w, "gram_74x37")
