@@ -62,6 +62,9 @@ def lib():
                                           C.c_void_p, C.c_int32, C.c_int32]
         L.diaglib_b200_k_block_mul.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
                                                C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_int64]
+        L.diaglib_b200_k_block_mul_gram.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                                    C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_int32,
+                                                    C.c_void_p, C.c_int32]
         L.diaglib_b200_k_residual.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.diaglib_b200_k_sym_eig.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]

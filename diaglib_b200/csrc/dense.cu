@@ -18,6 +18,7 @@ namespace dlb {
 
 bool g_disable_ws = false;
 bool g_disable_tma = false;
+bool g_disable_fused_gram = false;  // DIAGLIB_B200_NO_FUSED_GRAM=1
 bool g_bmul_small_tiles = true;   // DIAGLIB_B200_BMUL_RT256=1 selects 256-row tiles (measured slower: 4.91 vs 4.78 ms)  // DIAGLIB_B200_NO_TMA=1: skip the cp.async.bulk.tensor gram kernel  // DIAGLIB_B200_NO_WS=1: fall back to the cp.async kernels (A/B testing)
 
 // =====================================================================================
@@ -974,10 +975,14 @@ constexpr int BMW_STAGES = 4;
 // NCONS consumer warps (16 rows each) + 1 producer warp; the row tile is NCONS*16 rows, so a
 // bulk copy moves NCONS*128 bytes: 2 KB with 16 consumers, which the copy engine needs to get
 // past ~4.4 TB/s on the HBM-bound shapes (trmm, 74x37).
-template <int NQT, int NCONS>
+// GRAM = true additionally accumulates G = Y'^T Y' of the stored block (lower tiles), the metric
+// the next ortho_cd pass needs (diaglib.f90:3256), so that U is not read again: the finished
+// 16 x 40 accumulator tile of a warp is re-used as DMMA operands through warp shuffles (the
+// C-fragment of lane (row g, columns 2t,2t+1) becomes the A/B fragment of lane (column, row)).
+template <int NQT, int NCONS, bool GRAM>
 __global__ void __launch_bounds__((NCONS + 1) * 32)
 blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, const double* __restrict__ C, int ldc,
-                   int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri) {
+                   int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri, double* gpartial) {
   extern __shared__ __align__(16) double smem[];
   constexpr int QB = NQT * 8;
   constexpr int BMW_CONS = NCONS;
@@ -1034,6 +1039,10 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
       for (int c = 0; c < NQT; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
     const int a_off = (lane & 3) * SV + warp * 16 + (lane >> 2);
     const int b_off = (lane >> 2) * PS + (lane & 3);
+    constexpr int NGT = GRAM ? NQT * (NQT + 1) / 2 : 1;   // lower tiles of the QB x QB metric
+    double gacc[NGT][2];
+#pragma unroll
+    for (int g = 0; g < NGT; ++g) gacc[g][0] = gacc[g][1] = 0.0;
     int s = 0;
     uint32_t ph = 0;
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
@@ -1076,15 +1085,67 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int col = cc * 8 + (lane & 3) * 2 + e;
+            double v = 0.0;
             if (row < n && col < q) {
               double* dst = Y + row + (int64_t)col * ldy;
-              double v = alpha * acc[r][cc][e];
+              v = alpha * acc[r][cc][e];
               if (beta != 0.0) v += beta * (*dst);
               *dst = v;
             }
-            acc[r][cc][e] = 0.0;
+            acc[r][cc][e] = GRAM ? v : 0.0;
           }
         }
+      }
+      if (GRAM) {
+        // G += Y'^T Y' over this warp's 16 rows: 4 k-steps of 4 rows
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const int r = ks >> 1;
+          const int src = ((4 * (ks & 1) + (lane & 3)) << 2) + (lane >> 3);   // lane holding (row, column pair)
+          double f[NQT];
+#pragma unroll
+          for (int cc = 0; cc < NQT; ++cc) {
+            const double x0 = __shfl_sync(0xffffffffu, acc[r][cc][0], src);
+            const double x1 = __shfl_sync(0xffffffffu, acc[r][cc][1], src);
+            f[cc] = ((lane >> 2) & 1) ? x1 : x0;
+          }
+          int g = 0;
+#pragma unroll
+          for (int ti2 = 0; ti2 < NQT; ++ti2)
+#pragma unroll
+            for (int tj2 = 0; tj2 <= ti2; ++tj2) {
+              dmma884(gacc[g][0], gacc[g][1], f[ti2], f[tj2]);
+              ++g;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int cc = 0; cc < NQT; ++cc) acc[r][cc][0] = acc[r][cc][1] = 0.0;
+      }
+    }
+    if (GRAM) {
+      // reduce the 8 warps' accumulators in a fixed order through the (drained) ring, one partial per CTA
+      asm volatile("bar.sync 1, %0;\n" ::"r"(BMW_CONS * 32));
+      double* red = ring;   // [warp][tile][lane][2]
+#pragma unroll
+      for (int g = 0; g < NGT; ++g) {
+        red[(((size_t)warp * NGT + g) * 32 + lane) * 2 + 0] = gacc[g][0];
+        red[(((size_t)warp * NGT + g) * 32 + lane) * 2 + 1] = gacc[g][1];
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"r"(BMW_CONS * 32));
+      double* out = gpartial + (size_t)blockIdx.x * QB * QB;
+      for (int id = tid; id < NGT * 64; id += BMW_CONS * 32) {
+        const int g = id >> 6, l = (id >> 1) & 31, e = id & 1;
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < BMW_CONS; ++w) sum += red[(((size_t)w * NGT + g) * 32 + l) * 2 + e];
+        // tile g -> (ti2, tj2) of the lower triangle
+        int ti2 = 0, acc_g = 0;
+        while (acc_g + ti2 + 1 <= g) { acc_g += ti2 + 1; ++ti2; }
+        const int tj2 = g - acc_g;
+        const int i = ti2 * 8 + (l >> 2), j = tj2 * 8 + (l & 3) * 2 + e;
+        out[i + (size_t)j * QB] = sum;
       }
     }
   }
@@ -1119,21 +1180,21 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
     const size_t smem8 = sc_bytes + (size_t)BMW_STAGES * BM_KC * (8 * 16 + 4) * sizeof(double);
     static bool ws_attr = false;
     if (!ws_attr) {
-      DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_ws_kernel<NQT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_ws_kernel<NQT, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       if (NQT == 5)
-        DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_ws_kernel<5, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_ws_kernel<5, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       ws_attr = true;
     }
     if (NQT == 5 && smem16 <= 220 * 1024 && n >= 256 * 2 && !g_bmul_small_tiles) {
       const int64_t nt16 = (n + 255) / 256;
       const unsigned grid = (unsigned)std::min<int64_t>(nt16, (int64_t)num_sms);
-      blockmul_ws_kernel<5, 16><<<grid, 17 * 32, smem16, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0);
+      blockmul_ws_kernel<5, 16, false><<<grid, 17 * 32, smem16, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr);
       ++g_launches;
       return;
     }
     if (smem8 <= 110 * 1024 && ntiles >= 2) {
       const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * 2);
-      blockmul_ws_kernel<NQT, 8><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0);
+      blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr);
       ++g_launches;
       return;
     }
@@ -1205,6 +1266,42 @@ void block_trmm_inplace(cudaStream_t st, int64_t n, double* U, int64_t ldu, int 
     const int q0 = b * 128, qb = std::min(128, m - q0);
     block_mul(st, n, U, ldu, q0 + qb, T + (size_t)q0 * m, m, qb, 1.0, 0.0, U + (int64_t)q0 * ldu, ldu, false);
   }
+}
+
+// Y = alpha V C + beta Y fused with the metric of the result, G (q x q, ldg) = Y^T Y (both
+// triangles written).  Falls back to block_mul + gram_tn when the fused kernel does not apply
+// (q > 40, unaligned data).  Used by ortho_cd / ortho_vs_x: every metric after the first one of an
+// ortho_vs_x call comes out of the kernel that produced the block.
+void block_mul_gram(cudaStream_t st, int num_sms, int64_t n, const double* V, int64_t ldv, int p, const double* C,
+                    int ldc, int q, double alpha, double beta, double* Y, int64_t ldy, bool upper_tri, double* G,
+                    int ldg, double* partial) {
+  const bool al16 = aligned16(V) && (ldv % 2 == 0);
+  const int p16 = (p + 15) / 16 * 16;
+  const int PS = p16 + 4;
+  constexpr int NQT = 5, QB = 40;
+  const size_t smem = (2 * BMW_STAGES + (size_t)QB * PS + (size_t)BMW_STAGES * BM_KC * (8 * 16 + 4)) * sizeof(double);
+  const int64_t ntiles = (n + 127) / 128;
+  if (q <= QB && al16 && (n % 2 == 0) && !g_disable_ws && !g_disable_fused_gram && smem <= 200 * 1024 && ntiles >= 2) {
+    static bool attr = false;
+    if (!attr) {
+      DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_ws_kernel<NQT, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr = true;
+    }
+    int occ = 1;
+    DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blockmul_ws_kernel<NQT, 8, true>, 9 * 32, smem));
+    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * std::max(1, occ));
+    blockmul_ws_kernel<NQT, 8, true><<<grid, 9 * 32, smem, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS,
+                                                                  upper_tri ? 1 : 0, partial);
+    ++g_launches;
+    const int tot = q * q;
+    gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, (int)grid, QB, QB, q, q, 1, G, ldg, nullptr);
+    ++g_launches;
+    DLB_CUDA_CHECK(cudaGetLastError());
+    return;
+  }
+  if (upper_tri && V == Y) block_trmm_inplace(st, n, Y, ldy, q, C);
+  else block_mul(st, n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, upper_tri);
+  gram_tn(st, num_sms, n, Y, ldy, q, Y, ldy, q, G, ldg, true, partial);
 }
 
 }  // namespace dlb

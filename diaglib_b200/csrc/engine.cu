@@ -238,8 +238,11 @@ struct Engine {
   }
 
   // ---- ortho_cd, diaglib.f90:3185-3341 ------------------------------------------------
-  // one host synchronisation per pass (the CholStatus read-back decides macro_done).
-  bool ortho_cd(int64_t n, int m, double* u, int64_t ldu, double& growth) {
+  // one host synchronisation per pass (the CholStatus read-back decides macro_done).  When
+  // another pass is known to follow (the decision only needs the Cholesky status), the dtrmm
+  // of this pass and the metric of the next one are a single kernel (block_mul_gram); with
+  // have_metric the first metric was already produced by the kernel that wrote u.
+  bool ortho_cd(int64_t n, int m, double* u, int64_t ldu, double& growth, bool have_metric = false) {
     const int maxit = 10;
     growth = 1.0;
     for (int it = 1;; ++it) {
@@ -248,9 +251,12 @@ struct Engine {
         return false;
       }
       ++st_cd_passes;
-      kgram(n, u, ldu, m, u, ldu, m, d_metric, m, true);  // 3256
-      allreduce(d_metric, (size_t)m * m);
-      chol_inv(st, m, d_metric, m, d_T, d_cholwork, d_cholst);                                  // 3261-3316
+      if (!have_metric) {
+        kgram(n, u, ldu, m, u, ldu, m, d_metric, m, true);       // 3256
+        allreduce(d_metric, (size_t)m * m);
+      }
+      have_metric = false;
+      chol_inv(st, m, d_metric, m, d_T, d_cholwork, d_cholst);   // 3261-3316
       CholStatus cs;
       read_back(&cs, d_cholst, sizeof cs);
       st_shifts += cs.n_shifts;
@@ -261,8 +267,19 @@ struct Engine {
       }
       const double rcond = cs.l_norm * cs.linv_norm;
       growth *= cs.linv_norm;                                    // 3323
-      ktrmm(n, u, ldu, m, d_T);                 // 3327
-      if (EPS * rcond * rcond < TOL_ORTHO) return true;          // 3331-3332
+      const bool macro_done = EPS * rcond * rcond < TOL_ORTHO;   // 3331-3332
+      if (macro_done || it == maxit || m > 40) {
+        ktrmm(n, u, ldu, m, d_T);                                // 3327
+      } else {
+        // 3327 fused with the 3256 of the next pass
+        PhaseHandle h;
+        if (profile) h = ph_open(PH_KBMUL);
+        block_mul_gram(st, num_sms, n, u, ldu, m, d_T, m, m, 1.0, 0.0, u, ldu, true, d_metric, m, partial.as<double>());
+        if (profile) ph_close(h);
+        allreduce(d_metric, (size_t)m * m);
+        have_metric = true;
+      }
+      if (macro_done) return true;
     }
   }
 
@@ -306,8 +323,18 @@ struct Engine {
       ++st_sweeps;
       kgram(n, x, ldx, m, u, ldu, k, d_xu, m, false);  // 3543
       allreduce(d_xu, (size_t)m * k);
-      kbmul(n, x, ldx, m, d_xu, m, k, -1.0, 1.0, u, ldu);                            // 3544
-      ok = ortho_cd(n, k, u, ldu, growth);                                                   // 3548
+      if (k <= 40) {
+        // 3544 fused with the first metric (3256) of the ortho_cd that follows
+        PhaseHandle hh;
+        if (profile) hh = ph_open(PH_KBMUL);
+        block_mul_gram(st, num_sms, n, x, ldx, m, d_xu, m, k, -1.0, 1.0, u, ldu, false, d_metric, k, partial.as<double>());
+        if (profile) ph_close(hh);
+        allreduce(d_metric, (size_t)k * k);
+        ok = ortho_cd(n, k, u, ldu, growth, true);                                           // 3548
+      } else {
+        kbmul(n, x, ldx, m, d_xu, m, k, -1.0, 1.0, u, ldu);                          // 3544
+        ok = ortho_cd(n, k, u, ldu, growth);                                                 // 3548
+      }
       if (status) return;
       double xu_norm;
       if (!ok) {                                                                             // 3549,3558-3560
@@ -967,6 +994,7 @@ int32_t diaglib_b200_init(int32_t device) {
   if (!g.sw0) { DLB_CUDA_CHECK(cudaEventCreate(&g.sw0)); DLB_CUDA_CHECK(cudaEventCreate(&g.sw1)); }
   if (!g.partial.ensure(gram_scratch_bytes(128, 128, g.num_sms))) return DIAGLIB_B200_EALLOC;
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_WS")) g_disable_ws = ev[0] == '1';
+  if (const char* ev = std::getenv("DIAGLIB_B200_NO_FUSED_GRAM")) g_disable_fused_gram = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_TMA")) g_disable_tma = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_EIG_COOP_MIN_K")) g_eig_coop_min_k = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_BMUL_RT256")) g_bmul_small_tiles = ev[0] != '1';
@@ -1222,6 +1250,15 @@ int32_t diaglib_b200_k_block_mul(int64_t n, const double* v, int64_t ldv, int32_
                                  int32_t q, double alpha, double beta, double* y, int64_t ldy) {
   if (!require_init()) return DIAGLIB_B200_ENODEVICE;
   block_mul(g.st, n, v, ldv, p, c, ldc, q, alpha, beta, y, ldy);
+  return 0;
+}
+int32_t diaglib_b200_k_block_mul_gram(int64_t n, const double* v, int64_t ldv, int32_t p, const double* c, int32_t ldc,
+                                      int32_t q, double alpha, double beta, double* y, int64_t ldy, int32_t upper_tri,
+                                      double* g_out, int32_t ldg) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  block_mul_gram(g.st, g.num_sms, n, v, ldv, p, c, ldc, q, alpha, beta, y, ldy, upper_tri != 0, g_out, ldg,
+                 g.partial.as<double>());
+  if (g.nranks > 1) for (int j = 0; j < q; ++j) g.allreduce(g_out + (size_t)j * ldg, q);
   return 0;
 }
 int32_t diaglib_b200_k_residual(int64_t n, int32_t m, const double* ax, int64_t ldax, const double* x, int64_t ldx,

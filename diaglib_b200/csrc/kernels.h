@@ -12,6 +12,7 @@ namespace dlb {
 extern int64_t g_launches;
 extern bool g_disable_ws;
 extern bool g_disable_tma;
+extern bool g_disable_fused_gram;
 extern bool g_bmul_small_tiles;
 extern bool g_eig_two_sided;
 extern int g_eig_coop_min_k;
@@ -34,6 +35,12 @@ void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, 
 
 // U <- U * T, T upper triangular m x m (ld m), in place (dtrmm at diaglib.f90:3327).
 void block_trmm_inplace(cudaStream_t st, int64_t n, double* U, int64_t ldu, int m, const double* T);
+
+// block_mul fused with the metric of its result: G (q x q, ldg) = Y^T Y after Y = alpha V C + beta Y.
+// partial: scratch of gram_scratch_bytes(128,128,2*num_sms) (one q x q partial per CTA).
+void block_mul_gram(cudaStream_t st, int num_sms, int64_t n, const double* V, int64_t ldv, int p, const double* C,
+                    int ldc, int q, double alpha, double beta, double* Y, int64_t ldy, bool upper_tri, double* G,
+                    int ldg, double* partial);
 
 // ---- sparse.cu ------------------------------------------------------------------------
 struct CsrDevice {

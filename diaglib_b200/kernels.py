@@ -79,6 +79,22 @@ def block_mul(v: DeviceArray, p: int, cmat: np.ndarray, y: DeviceArray, alpha=1.
     cd.free()
 
 
+def block_mul_gram(v: DeviceArray, p: int, cmat: np.ndarray, y: DeviceArray, alpha=1.0, beta=0.0, upper_tri=False):
+    """Y = alpha V[:, :p] C + beta Y and G = Y^T Y in one kernel.  Returns G."""
+    n = v.shape[0]
+    cmat = np.asfortranarray(cmat, dtype=np.float64)
+    q = cmat.shape[1]
+    cd = DeviceArray.from_numpy(cmat)
+    gd = DeviceArray((q, q))
+    _check(lib().diaglib_b200_k_block_mul_gram(n, v.ptr, v.ld, p, cd.ptr, cd.ld, q, alpha, beta, y.ptr, y.ld,
+                                               1 if upper_tri else 0, gd.ptr, q), "k_block_mul_gram")
+    lib().diaglib_b200_sync()
+    out = gd.numpy()
+    cd.free()
+    gd.free()
+    return out
+
+
 def residual(ax: DeviceArray, x: DeviceArray, theta, active, r: DeviceArray):
     n, m = ax.shape
     theta = np.ascontiguousarray(theta, dtype=np.float64)

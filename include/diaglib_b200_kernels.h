@@ -36,6 +36,11 @@ int32_t diaglib_b200_k_gram(int64_t n, const double* a_dev, int64_t lda, int32_t
  * diaglib.f90:322,420,495,1717,3544 */
 int32_t diaglib_b200_k_block_mul(int64_t n, const double* v_dev, int64_t ldv, int32_t p, const double* c_dev,
                                  int32_t ldc, int32_t q, double alpha, double beta, double* y_dev, int64_t ldy);
+/* block multiply fused with the metric of its result: Y = alpha V C + beta Y, G(q x q, dev) = Y^T Y.
+ * replaces dgemm/dtrmm (diaglib.f90:3544 / 3327) followed by the dgemm('t','n') of the next ortho_cd pass (3256) */
+int32_t diaglib_b200_k_block_mul_gram(int64_t n, const double* v_dev, int64_t ldv, int32_t p, const double* c_dev,
+                                      int32_t ldc, int32_t q, double alpha, double beta, double* y_dev, int64_t ldy,
+                                      int32_t upper_tri, double* g_dev, int32_t ldg);
 /* r = ax - theta_j x, norms[0..m) = sum r^2 (all-reduced), norms[m..2m) = max|r| (all-reduced);
  * theta (m, host), active (m, host), norms (2m, host).  diaglib.f90:428-442 */
 int32_t diaglib_b200_k_residual(int64_t n, int32_t m, const double* ax_dev, int64_t ldax, const double* x_dev,

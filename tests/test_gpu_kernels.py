@@ -98,6 +98,31 @@ def test_block_mul_writes_into_own_columns(K):
     assert np.abs(out[:, 22:28] - s[:, :p] @ c).max() < 1e-11
 
 
+@pytest.mark.parametrize("n,p,q,tri,inplace", [(4096, 37, 37, True, True), (10000, 74, 37, False, False), (5002, 15, 15, True, True),
+                                                 (3000, 111, 8, False, False), (700, 37, 37, True, True), (4001, 37, 37, True, True),
+                                                 (6000, 60, 50, False, False)])
+def test_block_mul_gram_fused(K, n, p, q, tri, inplace):
+    """dtrmm / projection fused with the metric of the result (and its fallbacks: odd n, q > 40)"""
+    v, y0 = rnd(n, p, 31), rnd(n, q, 32)
+    c = rnd(p, q, 33)
+    if tri:
+        c = np.asfortranarray(np.triu(c))
+    dv = K.DeviceArray.from_numpy(v)
+    if inplace:
+        g = K.block_mul_gram(dv, p, c, dv, upper_tri=tri)
+        ref = v @ c
+        out = dv.numpy()
+    else:
+        dy = K.DeviceArray.from_numpy(y0)
+        g = K.block_mul_gram(dv, p, c, dy, alpha=-1.0, beta=1.0)
+        ref = y0 - v @ c
+        out = dy.numpy()
+    assert np.abs(out - ref).max() <= 1e-13 * p * max(1.0, np.abs(ref).max())
+    gref = ref.T @ ref
+    assert np.abs(g - gref).max() <= 1e-12 * np.sqrt(n) * np.abs(gref).max()
+    assert np.array_equal(g, g.T)
+
+
 # ---- residual + norms (dcopy/daxpy/dnrm2/maxval fusion) --------------------------------------
 def test_residual_norms(K):
     n, m = 10007, 9
