@@ -25,6 +25,7 @@
 namespace dlb {
 
 int64_t g_launches = 0;
+bool g_use_fused_gram = false;
 
 namespace {
 
@@ -238,10 +239,12 @@ struct Engine {
   }
 
   // ---- ortho_cd, diaglib.f90:3185-3341 ------------------------------------------------
-  // one host synchronisation per pass (the CholStatus read-back decides macro_done).  When
-  // another pass is known to follow (the decision only needs the Cholesky status), the dtrmm
-  // of this pass and the metric of the next one are a single kernel (block_mul_gram); with
-  // have_metric the first metric was already produced by the kernel that wrote u.
+  // one host synchronisation per pass (the CholStatus read-back decides macro_done).
+  // Optional (DIAGLIB_B200_FUSED_GRAM=1, off by default): when another pass is known to follow,
+  // the dtrmm of this pass and the metric of the next one are a single kernel (block_mul_gram).
+  // Measured in round 1: the fused kernel needs 142 registers -> one CTA per SM, and these
+  // HBM-bound shapes lose more from the halved occupancy (+0.40 s per solve) than the saved
+  // re-read of u gains (-0.12 s), so the separate kernels stay the default.
   bool ortho_cd(int64_t n, int m, double* u, int64_t ldu, double& growth, bool have_metric = false) {
     const int maxit = 10;
     growth = 1.0;
@@ -268,7 +271,7 @@ struct Engine {
       const double rcond = cs.l_norm * cs.linv_norm;
       growth *= cs.linv_norm;                                    // 3323
       const bool macro_done = EPS * rcond * rcond < TOL_ORTHO;   // 3331-3332
-      if (macro_done || it == maxit || m > 40) {
+      if (macro_done || it == maxit || m > 40 || !g_use_fused_gram) {
         ktrmm(n, u, ldu, m, d_T);                                // 3327
       } else {
         // 3327 fused with the 3256 of the next pass
@@ -323,7 +326,7 @@ struct Engine {
       ++st_sweeps;
       kgram(n, x, ldx, m, u, ldu, k, d_xu, m, false);  // 3543
       allreduce(d_xu, (size_t)m * k);
-      if (k <= 40) {
+      if (k <= 40 && g_use_fused_gram) {
         // 3544 fused with the first metric (3256) of the ortho_cd that follows
         PhaseHandle hh;
         if (profile) hh = ph_open(PH_KBMUL);
@@ -994,7 +997,7 @@ int32_t diaglib_b200_init(int32_t device) {
   if (!g.sw0) { DLB_CUDA_CHECK(cudaEventCreate(&g.sw0)); DLB_CUDA_CHECK(cudaEventCreate(&g.sw1)); }
   if (!g.partial.ensure(gram_scratch_bytes(128, 128, g.num_sms))) return DIAGLIB_B200_EALLOC;
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_WS")) g_disable_ws = ev[0] == '1';
-  if (const char* ev = std::getenv("DIAGLIB_B200_NO_FUSED_GRAM")) g_disable_fused_gram = ev[0] == '1';
+  if (const char* ev = std::getenv("DIAGLIB_B200_FUSED_GRAM")) g_use_fused_gram = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_TMA")) g_disable_tma = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_EIG_COOP_MIN_K")) g_eig_coop_min_k = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_BMUL_RT256")) g_bmul_small_tiles = ev[0] != '1';
