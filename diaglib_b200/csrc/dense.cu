@@ -1192,8 +1192,10 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
       ++g_launches;
       return;
     }
-    if (smem8 <= 110 * 1024 && ntiles >= 2) {
-      const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * 2);
+    if (smem8 <= 200 * 1024 && ntiles >= 2) {
+      // two CTAs per SM while C (p x q) is small enough to be resident twice, one beyond (Davidson:
+      // p = ldu up to ~400 with q <= 40)
+      const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * (smem8 <= 110 * 1024 ? 2 : 1));
       blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr);
       ++g_launches;
       return;
