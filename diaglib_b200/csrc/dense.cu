@@ -183,9 +183,8 @@ gram_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const d
 // Warp-specialised variant of gram_kernel: a 17th warp is the producer and feeds the ring with
 // 1-D bulk async copies (TMA engine; one KT*8-byte column segment per copy, completion counted
 // on full[stage]); the 16 consumer warps never meet at a CTA-wide barrier.
-constexpr int GRW_THREADS = GR_THREADS;   // 14 consumer warps + 2 producer warps
-constexpr int GRW_PROD = 2;               // a warp issues one bulk copy per ~70 cycles: two producers double the issue rate
-constexpr int GRW_CONS = GR_WARPS - GRW_PROD;
+constexpr int GRW_THREADS = GR_THREADS;   // 15 consumer warps + 1 producer warp
+constexpr int GRW_CONS = GR_WARPS - 1;
 
 __global__ void __launch_bounds__(GRW_THREADS, 1)
 gram_ws_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const double* __restrict__ B, int64_t ldb,
@@ -203,7 +202,7 @@ gram_ws_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, cons
   const int64_t my_chunks = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < GR_STAGES; ++s) { mbar_init(&full[s], GRW_PROD); mbar_init(&empty[s], GRW_CONS); }
+    for (int s = 0; s < GR_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GRW_CONS); }
     mbar_fence_init();
   }
   // columns p..PB-1 (q..QB-1) are never loaded: keep them finite
@@ -211,9 +210,8 @@ gram_ws_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, cons
   fence_proxy_async();
   __syncthreads();
 
-  if (warp >= GRW_CONS) {
-    // ---------------- producers: each issues the copies of every GRW_PROD-th column ----------------
-    const int pw = warp - GRW_CONS;
+  if (warp == GRW_CONS) {
+    // ---------------- producer ----------------
     int s = 0;
     uint32_t ph = 0;
     const int ncopy = p + (same ? 0 : q);
@@ -225,16 +223,15 @@ gram_ws_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, cons
       mbar_wait(&empty[s], ph ^ 1);
       if (rows < (uint32_t)KT) {
         // last chunk of the block: rows beyond n must contribute zero
-        for (int c = lane * GRW_PROD + pw; c < ncopy; c += 32 * GRW_PROD) {
+        for (int c = lane; c < ncopy; c += 32) {
           double* d = st + (c < p ? c : PB + (c - p)) * S;
           for (int r = rows; r < KT; ++r) d[r] = 0.0;
         }
       }
       __syncwarp();
-      const int mine = (ncopy - pw + GRW_PROD - 1) / GRW_PROD;   // columns pw, pw + GRW_PROD, ...
-      if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)mine * rows * 8u);
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)ncopy * rows * 8u);
       __syncwarp();
-      for (int c = lane * GRW_PROD + pw; c < ncopy; c += 32 * GRW_PROD) {
+      for (int c = lane; c < ncopy; c += 32) {
         if (c < p) bulk_g2s(st + c * S, A + (int64_t)c * lda + k0, rows * 8u, &full[s]);
         else bulk_g2s(st + (PB + (c - p)) * S, B + (int64_t)(c - p) * ldb + k0, rows * 8u, &full[s]);
       }
@@ -383,7 +380,6 @@ gram_wsc_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, con
 // the 16 lanes of a half-warp hit 16 distinct 8-byte banks, i.e. fragment loads are conflict
 // free without any padding.  (Any row permutation is legal: both operands use the same one.)
 // ---------------------------------------------------------------------------------------
-constexpr int GT_CONS = GR_WARPS - 1;   // 15 consumer warps + 1 producer warp (one elected lane issues the box loads)
 constexpr int GT_BOX_ROWS = 16;
 constexpr int GT_LINE = 16;  // doubles per 128-byte line
 
@@ -441,14 +437,14 @@ gram_tma_kernel(int64_t n, const __grid_constant__ CUtensorMap tmA, const __grid
   const int64_t my_chunks = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < GR_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GT_CONS); }
+    for (int s = 0; s < GR_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GRW_CONS); }
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
     if (!same) tma_prefetch_desc(&tmB);
   }
   __syncthreads();
 
-  if (warp == GT_CONS) {
+  if (warp == GRW_CONS) {
     // ---------------- producer: one elected lane ----------------
     if (lane == 0) {
       int s = 0;
@@ -692,7 +688,7 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
       bool launched = false;
       // (narrow blocks whose column segments reach 1 KB per stage are served better by the 1-D
       //  bulk-copy producer below: 3.9 vs 3.2 TB/s on the 37-column metric of ortho_cd)
-      if (al16 && !use_bulk && !g_disable_ws && !g_disable_tma && ncoarse <= 2 * GT_CONS && n < (int64_t)1 << 31) {
+      if (al16 && !use_bulk && !g_disable_ws && !g_disable_tma && ncoarse <= 2 * GRW_CONS && n < (int64_t)1 << 31) {
         // TMA-tiled kernel: stage length from the unpadded box footprint
         int kt = 128;
         while (kt > 16 && (size_t)GR_STAGES * cols * kt * 8 > 200 * 1024) kt >>= 1;
@@ -704,7 +700,7 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
             tma_attr = true;
           }
           if (same) tmB = tmA;
-          const GramSched sch = make_sched(ntp, ntq, diag_blk, GT_CONS);
+          const GramSched sch = make_sched(ntp, ntq, diag_blk, GRW_CONS);
           const int64_t nch = (n + kt - 1) / kt;
           const int g = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, nch));
           const size_t sm = (size_t)GR_STAGES * cols * kt * 8 + 2 * GR_STAGES * sizeof(uint64_t) + 1024;
@@ -974,8 +970,7 @@ blockmul_persistent_kernel(int64_t n, const double* __restrict__ V, int64_t ldv,
 // eight consumer warps run the DMMA loop.  There is no CTA-wide barrier in the main loop:
 // consumers wait on full[stage], release the stage on empty[stage], and drift freely, which
 // keeps the FP64 tensor pipe busy while other warps wait for data.
-constexpr int BMW_STAGES = 4;       // default depth of the ring
-constexpr int BMW_MAX_STAGES = 8;   // narrow products (few chunks per row tile) get a deeper ring
+constexpr int BMW_STAGES = 4;
 
 // NCONS consumer warps (16 rows each) + 1 producer warp; the row tile is NCONS*16 rows, so a
 // bulk copy moves NCONS*128 bytes: 2 KB with 16 consumers, which the copy engine needs to get
@@ -987,7 +982,7 @@ constexpr int BMW_MAX_STAGES = 8;   // narrow products (few chunks per row tile)
 template <int NQT, int NCONS, bool GRAM>
 __global__ void __launch_bounds__((NCONS + 1) * 32)
 blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, const double* __restrict__ C, int ldc,
-                   int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri, double* gpartial, int nstages) {
+                   int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri, double* gpartial) {
   extern __shared__ __align__(16) double smem[];
   constexpr int QB = NQT * 8;
   constexpr int BMW_CONS = NCONS;
@@ -995,24 +990,24 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
   constexpr int RT = NCONS * 16;
   constexpr int SV = RT + 4;
   constexpr int STAGE = BM_KC * SV;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // nstages (<= BMW_MAX_STAGES)
-  uint64_t* empty = full + BMW_MAX_STAGES;
-  double* sC = smem + 2 * BMW_MAX_STAGES;                // [QB][PS], zero padded
-  double* ring = sC + (size_t)QB * PS;                   // nstages x STAGE
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // BMW_STAGES
+  uint64_t* empty = full + BMW_STAGES;                   // BMW_STAGES
+  double* sC = smem + 2 * BMW_STAGES;                    // [QB][PS], zero padded
+  double* ring = sC + (size_t)QB * PS;                   // BMW_STAGES x STAGE
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nk = (p + BM_KC - 1) / BM_KC;
   const int64_t ntiles = (n + RT - 1) / RT;
   const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BMW_CONS); }
+    for (int s = 0; s < BMW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BMW_CONS); }
     mbar_fence_init();
   }
   for (int id = tid; id < QB * PS; id += BMW_THREADS) {
     const int j = id / PS, k = id - j * PS;
     sC[id] = (j < q && k < p) ? C[(size_t)j * ldc + k] : 0.0;
   }
-  for (int id = tid; id < nstages * STAGE; id += BMW_THREADS) ring[id] = 0.0;  // stale data must stay finite
+  for (int id = tid; id < BMW_STAGES * STAGE; id += BMW_THREADS) ring[id] = 0.0;  // stale data must stay finite
   fence_proxy_async();
   __syncthreads();
 
@@ -1032,7 +1027,7 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
         __syncwarp();
         if (lane < ncols)
           bulk_g2s(ring + (size_t)s * STAGE + lane * SV, V + (int64_t)(k0 + lane) * ldv + row0, rows * 8u, &full[s]);
-        if (++s == nstages) { s = 0; ph ^= 1; }
+        if (++s == BMW_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -1079,7 +1074,7 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-        if (++s == nstages) { s = 0; ph ^= 1; }
+        if (++s == BMW_STAGES) { s = 0; ph ^= 1; }
       }
       const int64_t row0 = (blockIdx.x + ti * gridDim.x) * RT;
 #pragma unroll
@@ -1180,10 +1175,9 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
   const int PS = p16 + 4;
   const size_t smem_p = ((size_t)QB * PS + (size_t)BM_STAGES * BM_KC * BM_SV) * sizeof(double);
   if (al16 && (n % 2 == 0) && !g_disable_ws) {
-    const size_t sc_bytes = (2 * BMW_MAX_STAGES + (size_t)QB * PS) * sizeof(double);
-    const size_t stage8 = (size_t)BM_KC * (8 * 16 + 4) * sizeof(double);
+    const size_t sc_bytes = (2 * BMW_STAGES + (size_t)QB * PS) * sizeof(double);
     const size_t smem16 = sc_bytes + (size_t)BMW_STAGES * BM_KC * (16 * 16 + 4) * sizeof(double);
-    const size_t smem8 = sc_bytes + BMW_STAGES * stage8;
+    const size_t smem8 = sc_bytes + (size_t)BMW_STAGES * BM_KC * (8 * 16 + 4) * sizeof(double);
     static bool ws_attr = false;
     if (!ws_attr) {
       DLB_CUDA_CHECK(cudaFuncSetAttribute(blockmul_ws_kernel<NQT, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1194,20 +1188,15 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
     if (NQT == 5 && smem16 <= 220 * 1024 && n >= 256 * 2 && !g_bmul_small_tiles) {
       const int64_t nt16 = (n + 255) / 256;
       const unsigned grid = (unsigned)std::min<int64_t>(nt16, (int64_t)num_sms);
-      blockmul_ws_kernel<5, 16, false><<<grid, 17 * 32, smem16, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr, BMW_STAGES);
+      blockmul_ws_kernel<5, 16, false><<<grid, 17 * 32, smem16, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr);
       ++g_launches;
       return;
     }
     if (smem8 <= 200 * 1024 && ntiles >= 2) {
       // two CTAs per SM while C (p x q) is small enough to be resident twice, one beyond (Davidson:
-      // p = ldu up to ~400 with q <= 40); whatever shared memory is left deepens the ring (a narrow
-      // product has only a few chunks per row tile, so four stages are barely one tile of prefetch)
-      const int per_sm = smem8 <= 110 * 1024 ? 2 : 1;
-      const size_t budget = per_sm == 2 ? 110 * 1024 : 200 * 1024;
-      int nst = (int)((budget - sc_bytes) / stage8);
-      nst = std::max(BMW_STAGES, std::min(BMW_MAX_STAGES, nst));
-      const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * per_sm);
-      blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, sc_bytes + nst * stage8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr, nst);
+      // p = ldu up to ~400 with q <= 40)
+      const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * (smem8 <= 110 * 1024 ? 2 : 1));
+      blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr);
       ++g_launches;
       return;
     }
@@ -1292,7 +1281,7 @@ void block_mul_gram(cudaStream_t st, int num_sms, int64_t n, const double* V, in
   const int p16 = (p + 15) / 16 * 16;
   const int PS = p16 + 4;
   constexpr int NQT = 5, QB = 40;
-  const size_t smem = (2 * BMW_MAX_STAGES + (size_t)QB * PS + (size_t)BMW_STAGES * BM_KC * (8 * 16 + 4)) * sizeof(double);
+  const size_t smem = (2 * BMW_STAGES + (size_t)QB * PS + (size_t)BMW_STAGES * BM_KC * (8 * 16 + 4)) * sizeof(double);
   const int64_t ntiles = (n + 127) / 128;
   if (q <= QB && al16 && (n % 2 == 0) && !g_disable_ws && !g_disable_fused_gram && smem <= 200 * 1024 && ntiles >= 2) {
     static bool attr = false;
@@ -1304,7 +1293,7 @@ void block_mul_gram(cudaStream_t st, int num_sms, int64_t n, const double* V, in
     DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blockmul_ws_kernel<NQT, 8, true>, 9 * 32, smem));
     const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * std::max(1, occ));
     blockmul_ws_kernel<NQT, 8, true><<<grid, 9 * 32, smem, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS,
-                                                                  upper_tri ? 1 : 0, partial, BMW_STAGES);
+                                                                  upper_tri ? 1 : 0, partial);
     ++g_launches;
     const int tot = q * q;
     gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, (int)grid, QB, QB, q, q, 1, G, ldg, nullptr);
