@@ -472,6 +472,7 @@ void print_timings(const char* name, const double* t) {
   std::printf("    orthogonalization:             %12.4f\n", t[PH_ORTHO]);
   std::printf("                                   ========================\n");
   std::printf("    total:                         %12.4f\n", t[PH_TOTAL]);
+  std::fflush(stdout);
 }
 
 // =======================================================================================
@@ -1000,6 +1001,7 @@ int32_t diaglib_b200_init(int32_t device) {
   if (const char* ev = std::getenv("DIAGLIB_B200_FUSED_GRAM")) g_use_fused_gram = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_TMA")) g_disable_tma = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_EIG_COOP_MIN_K")) g_eig_coop_min_k = std::atoi(ev);
+  if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_SHORT")) g_spmm_short = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_BMUL_RT256")) g_bmul_small_tiles = ev[0] != '1';
   g.inited = true;
   g.status = 0;
@@ -1132,6 +1134,9 @@ int32_t diaglib_b200_set_csr(int64_t n_loc, int64_t n_halo, const int64_t* rowpt
   g.A.n = n_loc;
   g.A.nnz = nnz;
   g.A.n_halo = n_halo;
+  int64_t longest = 0;
+  for (int64_t i = 0; i < n_loc; ++i) longest = std::max(longest, rowptr[i + 1] - rowptr[i]);
+  g.A.max_row_nnz = (int)std::min<int64_t>(longest, INT32_MAX);
   g.A.rowptr = g.b_rowptr.as<int64_t>();
   g.A.col = g.b_col.as<int32_t>();
   g.A.val = g.b_val.as<double>();

@@ -16,6 +16,7 @@ extern bool g_disable_fused_gram;
 extern bool g_bmul_small_tiles;
 extern bool g_eig_two_sided;
 extern int g_eig_coop_min_k;
+extern int g_spmm_short;
 
 // ---- dense.cu -------------------------------------------------------------------------
 // C(p x q, ldc) = A(n x p, lda)^T * B(n x q, ldb).  Replaces dgemm('t','n',p,q,n,...) at
@@ -47,6 +48,7 @@ struct CsrDevice {
   int64_t n = 0;        // local rows
   int64_t nnz = 0;
   int64_t n_halo = 0;   // columns >= n index the halo block
+  int max_row_nnz = 0;  // longest row (0 = unknown); selects the short-row SpMM
   int64_t* rowptr = nullptr;
   int32_t* col = nullptr;
   double* val = nullptr;

@@ -237,6 +237,86 @@ def test_gen_eig_is_rejected(gpu_lib):
         gpu_lib.lobpcg_driver(False, True, 100, 2, 4, 10, 1e-8, 0.0, None, None, None, np.zeros(4), ev)
 
 
+class _DevView:
+    """zero-copy torch view of a column-major (n, m) device block handed to a callback"""
+
+    def __init__(self, ptr, n, m):
+        self.__cuda_array_interface__ = dict(shape=(m, n), typestr="<f8", data=(int(ptr), False), version=2)
+
+
+@pytest.mark.parametrize("driver", ["lobpcg", "davidson"])
+def test_user_supplied_device_callbacks(gpu_lib, oracle, driver):
+    """the reference contract matvec(n,m,x,ax) / precnd(n,m,shift,x,ax) (diaglib.f90:62-72) with
+    caller-written device-aware callbacks: here torch ops enqueued on diaglib_b200_stream()"""
+    import torch
+    n, n_want, tol = 1000, 10, 1e-8
+    n_eig = P.n_eig_rule(n_want)
+    a = P.toy_dense(n)
+    csr = dense_as_csr(a)
+    ro, ok_b, eig_b, ev_b, hb, _ = run_both(gpu_lib, oracle, driver, csr, n_want, n_eig, tol=tol, max_iter=100)
+    stream = torch.cuda.ExternalStream(gpu_lib.lib().diaglib_b200_stream(), device="cuda:0")
+    a_t = torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+    d_t = torch.as_tensor(np.diag(a).copy(), device="cuda:0")
+    calls = dict(mv=0, pc=0, cols=0)
+
+    def matvec(nn, m, x, ax):
+        calls["mv"] += 1
+        calls["cols"] += m
+        with torch.cuda.stream(stream):
+            xt = torch.as_tensor(_DevView(x, nn, m), device="cuda:0")      # = X^T
+            torch.as_tensor(_DevView(ax, nn, m), device="cuda:0").copy_(xt @ a_t)   # A symmetric
+
+    def precnd(nn, m, shift, x, px):
+        calls["pc"] += 1
+        with torch.cuda.stream(stream):
+            xt = torch.as_tensor(_DevView(x, nn, m), device="cuda:0")
+            den = d_t + shift
+            den = torch.where(den.abs() > 1e-5, den, torch.ones_like(den))  # main.f90:146-171
+            torch.as_tensor(_DevView(px, nn, m), device="cuda:0").copy_(xt / den)
+
+    ev = P.guess(n, n_eig)
+    eig = np.zeros(n_eig)
+    if driver == "lobpcg":
+        ok = gpu_lib.lobpcg_driver(False, False, n, n_want, n_eig, 100, tol, 0.0, matvec, precnd, None, eig, ev)
+    else:
+        ok = gpu_lib.davidson_driver(False, n, n_want, n_eig, 100, tol, 20, 0.0, matvec, precnd, eig, ev)
+    hg = gpu_lib.last_history(n_eig)
+    assert ok and ok_b
+    assert calls["mv"] >= len(hg["it"])
+    assert calls["pc"] >= len(hg["it"]) - 1
+    assert np.abs(eig[:n_want] - eig_b[:n_want]).max() / np.abs(eig_b[:n_want]).max() < REL
+    assert np.abs(eig[:n_want] - ro["eig"][:n_want]).max() / np.abs(ro["eig"][:n_want]).max() < REL
+    assert abs(len(hg["it"]) - len(ro["it"])) <= 1
+    check_solution(csr, eig, ev, n_want, tol)
+
+
+@pytest.mark.parametrize("driver", ["lobpcg", "davidson"])
+def test_verbose_prints_iteration_table(gpu_lib, driver, capfd):
+    """verbose=.true. prints the per-iteration table of the reference (diaglib.f90:459-464,
+    1741-1749) and the timing summary (537-552)"""
+    csr = P.toy_sparse(2000)
+    gpu_lib.set_csr(*csr)
+    n, n_targ, n_max = 2000, 3, 6
+    ev = P.guess(n, n_max)
+    eig = np.zeros(n_max)
+    if driver == "lobpcg":
+        ok = gpu_lib.lobpcg_driver(True, False, n, n_targ, n_max, 200, 1e-8, 0.0, None, None, None, eig, ev)
+    else:
+        ok = gpu_lib.davidson_driver(True, n, n_targ, n_max, 200, 1e-8, 10, 0.0, None, None, eig, ev)
+    out = capfd.readouterr().out
+    assert ok
+    its = len(gpu_lib.last_history(n_max)["it"])
+    rows = [ln.split() for ln in out.splitlines() if len(ln.split()) == 6 and ln.split()[-1] in ("T", "F")]
+    assert len(rows) == its * n_targ
+    last = rows[-n_targ:]
+    assert all(r[-1] == "T" for r in last)
+    assert np.allclose([float(r[2]) for r in last], eig[:n_targ], rtol=0, atol=1e-11 * np.abs(eig[:n_targ]).max() + 1e-11)
+    assert "matrix-vector multiplications" in out and "orthogonalization" in out
+    # silent when verbose is false
+    gpu_lib.lobpcg_driver(False, False, n, n_targ, n_max, 200, 1e-8, 0.0, None, None, None, eig, P.guess(n, n_max))
+    assert capfd.readouterr().out == ""
+
+
 # ---- public block routines -------------------------------------------------------------------
 @pytest.mark.parametrize("n,m", [(1000, 15), (20000, 37), (5001, 8), (3000, 133)])
 def test_ortho_cd_vs_oracle(gpu_lib, oracle, n, m):
