@@ -14,10 +14,13 @@ from .api import (  # noqa: F401
     lib,
     lib_path,
     lobpcg_driver,
+    b_ortho,
+    b_ortho_vs_x,
     ortho,
     ortho_cd,
     ortho_vs_x,
     set_csr,
+    set_csr_b,
     last_history,
     last_stats,
     last_timers,

@@ -57,6 +57,7 @@ def lib():
         L.diaglib_b200_k_fill_uniform.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64]
         L.diaglib_b200_timer_stop_ms.restype = C.c_double
         L.diaglib_b200_set_csr.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.diaglib_b200_set_csr_b.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.diaglib_b200_set_halo.argtypes = [C.c_int32] + [C.c_void_p] * 5
         L.diaglib_b200_k_gram.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                           C.c_void_p, C.c_int32, C.c_int32]
@@ -115,10 +116,11 @@ def _callback(cb, kind):
     wrapped."""
     L = lib()
     if cb is None or isinstance(cb, str):
-        return C.cast(L.diaglib_b200_csr_matvec if kind == "matvec" else L.diaglib_b200_diag_precnd, C.c_void_p)
+        builtin = dict(matvec=L.diaglib_b200_csr_matvec, precnd=L.diaglib_b200_diag_precnd, bvec=L.diaglib_b200_csr_bvec)
+        return C.cast(builtin[kind], C.c_void_p)
     if isinstance(cb, C._CFuncPtr):
         return C.cast(cb, C.c_void_p)
-    if kind == "matvec":
+    if kind in ("matvec", "bvec"):
         f = MATVEC_T(lambda n, m, x, ax: cb(n[0], m[0], x, ax))
     else:
         f = PRECND_T(lambda n, m, s, x, px: cb(n[0], m[0], s[0], x, px))
@@ -143,13 +145,23 @@ def set_csr(rowptr, col, val, diag, n_halo: int = 0, halo_plan=None) -> None:
         _check(lib().diaglib_b200_set_halo(len(peer), _ptr(peer), *[_ptr(a) for a in arrs]), "set_halo")
 
 
+def set_csr_b(rowptr, col, val, n_halo: int = 0) -> None:
+    """Install the local rows of the metric B used by the built-in bvec (generalized problem)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    _check(lib().diaglib_b200_set_csr_b(len(rowptr) - 1, int(n_halo), _ptr(rowptr), _ptr(col), _ptr(val)), "set_csr_b")
+
+
 def lobpcg_driver(verbose, gen_eig, n, n_targ, n_max, max_iter, tol, shift, matvec, precnd, bvec, eig, evec) -> bool:
     """diaglib.f90:171-172.  eig (n_max) and evec (n, n_max; guess in, vectors out) are
-    overwritten.  Returns `ok`.  Raises DiaglibError where the reference would `stop`."""
+    overwritten.  Returns `ok`.  Raises DiaglibError where the reference would `stop`.
+    gen_eig=True solves A x = lambda B x; bvec=None selects the built-in product with the metric
+    installed by set_csr_b."""
     ok = C.c_int32(0)
     lib().diaglib_b200_lobpcg_driver(_i(verbose), _i(gen_eig), _i(n), _i(n_targ), _i(n_max), _i(max_iter), _d(tol),
-                                     _d(shift), _callback(matvec, "matvec"), _callback(precnd, "precnd"), None,
-                                     _ptr(eig), _ptr(evec), C.byref(ok))
+                                     _d(shift), _callback(matvec, "matvec"), _callback(precnd, "precnd"),
+                                     _callback(bvec, "bvec") if gen_eig else None, _ptr(eig), _ptr(evec), C.byref(ok))
     _check(lib().diaglib_b200_last_status(), "lobpcg_driver")
     return bool(ok.value)
 
@@ -177,6 +189,18 @@ def ortho_vs_x(n, m, k, x, u, ax=None, au=None) -> None:
     """diaglib.f90:3481."""
     lib().diaglib_b200_ortho_vs_x(_i(n), _i(m), _i(k), _ptr(x), _ptr(u), _ptr(ax), _ptr(au))
     _check(lib().diaglib_b200_last_status(), "ortho_vs_x")
+
+
+def b_ortho(n, m, u, bu) -> None:
+    """diaglib.f90:3094."""
+    lib().diaglib_b200_b_ortho(_i(n), _i(m), _ptr(u), _ptr(bu))
+    _check(lib().diaglib_b200_last_status(), "b_ortho")
+
+
+def b_ortho_vs_x(n, m, k, x, bx, u) -> None:
+    """diaglib.f90:3576."""
+    lib().diaglib_b200_b_ortho_vs_x(_i(n), _i(m), _i(k), _ptr(x), _ptr(bx), _ptr(u))
+    _check(lib().diaglib_b200_last_status(), "b_ortho_vs_x")
 
 
 def ortho(n, m, u, w=None) -> None:

@@ -109,9 +109,9 @@ struct Engine {
   // driver workspaces, cached across calls (the reference allocates per call, 251-276 / 1600-1618;
   // cudaMalloc/cudaFree of tens of GB costs ~0.5 s, so they are kept until finalize or
   // diaglib_b200_release_workspace)
-  DevBuf ws_space, ws_aspace, ws_r, ws_xnew, ws_axnew, ws_evec, ws_red;
+  DevBuf ws_space, ws_aspace, ws_r, ws_xnew, ws_axnew, ws_evec, ws_red, ws_bspace, ws_bspace2;
   void release_workspace() {
-    for (DevBuf* b : {&ws_space, &ws_aspace, &ws_r, &ws_xnew, &ws_axnew, &ws_evec, &ws_red}) b->release();
+    for (DevBuf* b : {&ws_space, &ws_aspace, &ws_r, &ws_xnew, &ws_axnew, &ws_evec, &ws_red, &ws_bspace, &ws_bspace2}) b->release();
   }
   void* h_pin = nullptr;  // pinned staging for small read-backs
   size_t h_pin_bytes = 0;
@@ -119,6 +119,8 @@ struct Engine {
   // installed matrix + halo plan (built-in callbacks)
   CsrDevice A;
   DevBuf b_rowptr, b_col, b_val, b_diag, b_send, b_recv, b_halo;
+  DevBuf bb_rowptr, bb_col, bb_val;   // metric B of the generalized problem (built-in bvec)
+  CsrDevice B;
   std::vector<int> peer;
   std::vector<int64_t> send_row0, send_cnt, recv_off, recv_cnt;
 
@@ -312,8 +314,28 @@ struct Engine {
     }
   }
 
-  // ---- ortho_vs_x, diaglib.f90:3481-3574 -----------------------------------------------
-  void ortho_vs_x(int64_t n, int m, int k, const double* x, int64_t ldx, double* u, int64_t ldu) {
+  // ---- b_ortho, diaglib.f90:3094-3183 (use_svd = .false.) ------------------------------
+  // u <- u L^-T, bu <- bu L^-T with L L^T = u^T bu.  The reference solves with dtrsm; here L^-T
+  // is formed once (as in ortho_cd) and both blocks are multiplied by it.  The reference does
+  // not look at dpotrf's status; a metric that is not positive definite is reported instead.
+  void b_ortho(int64_t n, int m, double* u, int64_t ldu, double* bu, int64_t ldbu) {
+    kgram(n, u, ldu, m, bu, ldbu, m, d_metric, m, true);     // 3124 (lower triangle, what dpotrf('l') reads)
+    allreduce(d_metric, (size_t)m * m);
+    chol_inv(st, m, d_metric, m, d_T, d_cholwork, d_cholst); // 3172
+    CholStatus cs;
+    read_back(&cs, d_cholst, sizeof cs);
+    if (cs.hard_fail || cs.info_first != 0) {
+      fail(DIAGLIB_B200_ECHOL, "b_ortho: u^T B u is not positive definite (dpotrf info = %d)", (int)cs.info_first);
+      return;
+    }
+    ktrmm(n, u, ldu, m, d_T);                                // 3176
+    ktrmm(n, bu, ldbu, m, d_T);                              // 3177
+  }
+
+  // ---- ortho_vs_x, diaglib.f90:3481-3574; with bx != nullptr b_ortho_vs_x, 3576-3663 ------
+  void ortho_vs_x(int64_t n, int m, int k, const double* x, int64_t ldx, double* u, int64_t ldu,
+                  const double* bx = nullptr) {
+    const double* gx = bx ? bx : x;   // the overlap is taken with B x in the generalized case (3632)
     const int maxit = 10;
     bool done = false;
     int it = 0;
@@ -324,7 +346,7 @@ struct Engine {
     while (!done) {
       ++it;
       ++st_sweeps;
-      kgram(n, x, ldx, m, u, ldu, k, d_xu, m, false);  // 3543
+      kgram(n, gx, ldx, m, u, ldu, k, d_xu, m, false);  // 3543 / 3632
       allreduce(d_xu, (size_t)m * k);
       if (k <= 40 && g_use_fused_gram) {
         // 3544 fused with the first metric (3256) of the ortho_cd that follows
@@ -342,7 +364,7 @@ struct Engine {
       double xu_norm;
       if (!ok) {                                                                             // 3549,3558-3560
         ortho_qr(n, k, u, ldu);
-        kgram(n, x, ldx, m, u, ldu, k, d_xu, m, false);
+        kgram(n, gx, ldx, m, u, ldu, k, d_xu, m, false);
         allreduce(d_xu, (size_t)m * k);
         std::vector<double> h((size_t)m * k);
         read_back(h.data(), d_xu, h.size() * sizeof(double));
@@ -381,8 +403,9 @@ struct Engine {
 
   void halo_exchange(int m, const double* x, int64_t ldx);
   void check_guess(int64_t n, int m, double* evec, int64_t ld);
-  void lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, double tol, double shift,
-              diaglib_matvec_t matvec, diaglib_precnd_t precnd, double* eig, double* evec, int32_t* ok);
+  void lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, int max_iter, double tol, double shift,
+              diaglib_matvec_t matvec, diaglib_precnd_t precnd, diaglib_matvec_t bvec, double* eig, double* evec,
+              int32_t* ok);
   void davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, double tol, int max_dav, double shift,
                 diaglib_matvec_t matvec, diaglib_precnd_t precnd, double* eig, double* evec, int32_t* ok);
   void begin_call(int n_max) {
@@ -476,10 +499,11 @@ void print_timings(const char* name, const double* t) {
 }
 
 // =======================================================================================
-// lobpcg_driver, standard branch — diaglib.f90:171-556
+// lobpcg_driver — diaglib.f90:171-556 (standard and gen_eig branches)
 // =======================================================================================
-void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, double tol, double shift,
-                    diaglib_matvec_t matvec, diaglib_precnd_t precnd, double* eig, double* evec, int32_t* ok_out) {
+void Engine::lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, int max_iter, double tol, double shift,
+                    diaglib_matvec_t matvec, diaglib_precnd_t precnd, diaglib_matvec_t bvec, double* eig,
+                    double* evec, int32_t* ok_out) {
   begin_call(n_max);
   *ok_out = 0;
   const int64_t nn = n;
@@ -489,8 +513,8 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
 
   PhaseHandle ph_tot = ph_open(PH_TOTAL);
   // workspaces (251-276).  bspace / bx_new of the reference are only used by the gen_eig
-  // branch and are not allocated; space/aspace are not zero-filled (284-286) because every
-  // column is written before it is read in the standard branch.
+  // branch and are only allocated for it; space/aspace/bspace are not zero-filled (284-286)
+  // because every column is written before it is read.
   const size_t blk = (size_t)nn * n_max * sizeof(double);
   DevBuf &b_space = ws_space, &b_aspace = ws_aspace, &b_r = ws_r, &b_xnew = ws_xnew, &b_axnew = ws_axnew,
          &b_evec = ws_evec, &b_red = ws_red;
@@ -502,6 +526,7 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
   bool okm = b_space.ensure(3 * blk) && b_aspace.ensure(3 * blk) && b_r.ensure(blk) && b_xnew.ensure(3 * blk) &&
              b_axnew.ensure(3 * blk);
   if (!evec_on_dev) okm = okm && b_evec.ensure(blk);
+  if (gen_eig) okm = okm && ws_bspace.ensure(3 * blk) && ws_bspace2.ensure(3 * blk);
   const size_t eigw = eig_work_doubles(len_a);
   const size_t cfw = coeffs_work_doubles(len_a, n_max, n_max);
   const size_t red_doubles = (size_t)len_a * len_a + len_a + (size_t)len_a * n_max + eigw + cfw + 4 * n_max + 64;
@@ -524,6 +549,8 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
   double* r = b_r.as<double>();
   double* space2 = b_xnew.as<double>();   // the other half of the double buffer
   double* aspace2 = b_axnew.as<double>();
+  double* bspace = gen_eig ? ws_bspace.as<double>() : nullptr;    // B * space, same double buffering
+  double* bspace2 = gen_eig ? ws_bspace2.as<double>() : nullptr;
   double* d_evec = evec_on_dev ? evec : b_evec.as<double>();
   double* a_red = b_red.as<double>();  // kept compact: leading dimension = current len_u
   double* e_red = a_red + (size_t)len_a * len_a;
@@ -550,6 +577,14 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
 
   check_guess(nn, n_max, d_evec, nn);                                                  // 295
   kcopy(nn, n_max, d_evec, nn, space, nn);                                    // 306
+  if (gen_eig) {                                                                       // 299-302, 307
+    h = ph_open(PH_MV);
+    { int32_t m32 = n_max; bvec(&n32, &m32, space, bspace); }
+    ph_close(h);
+    h = ph_open(PH_ORTHO);
+    b_ortho(nn, n_max, space, nn, bspace, nn);
+    ph_close(h);
+  }
   h = ph_open(PH_MV);
   { int32_t m32 = n_max; matvec(&n32, &m32, space, aspace); }                          // 309
   ph_close(h);
@@ -566,12 +601,14 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
   // in-place product is only row-local for q <= 128 columns; n_max may be larger)
   kbmul(nn, space, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, space2, nn);
   kbmul(nn, aspace, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, aspace2, nn);
+  if (gen_eig) kbmul(nn, bspace, nn, n_max, a_red, n_max, n_max, 1.0, 0.0, bspace2, nn);  // 329-332
   std::swap(space, space2);
   std::swap(aspace, aspace2);
+  std::swap(bspace, bspace2);
   ph_close(h);
   h = ph_open(PH_RESID);
   DLB_CUDA_CHECK(cudaMemcpyAsync(d_active, h_active.data(), n_max * sizeof(int), cudaMemcpyHostToDevice, st));
-  residual_norms(st, num_sms, nn, n_max, aspace, nn, space, nn, e_red, d_active, r, nn, d_norms,
+  residual_norms(st, num_sms, nn, n_max, aspace, nn, gen_eig ? bspace : space, nn, e_red, d_active, r, nn, d_norms,
                  resid_scratch.as<double>());                                          // 337-346
   read_back(h_eig.data(), e_red, n_max * sizeof(double));                              // eig = e_red(1:n_max) (318)
   int ind_x = 1, ind_w = ind_x + n_max, ind_p = 0;
@@ -582,8 +619,16 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
   }
   ph_close(h);
   h = ph_open(PH_ORTHO);
-  ortho_vs_x(nn, n_max, n_max, space, nn, COL(space, ind_w), nn);                      // 366
+  ortho_vs_x(nn, n_max, n_max, space, nn, COL(space, ind_w), nn, bspace);              // 366 / 358
   ph_close(h);
+  if (gen_eig && status == 0) {                                                        // 363-364
+    h = ph_open(PH_MV);
+    { int32_t m32 = n_max; bvec(&n32, &m32, COL(space, ind_w), COL(bspace, ind_w)); }
+    ph_close(h);
+    h = ph_open(PH_ORTHO);
+    b_ortho(nn, n_max, COL(space, ind_w), nn, COL(bspace, ind_w), nn);
+    ph_close(h);
+  }
 
   const double tol_rms = tol, tol_max = 10.0 * tol;
   const double sqrtn = std::sqrt((double)n_glob);
@@ -610,11 +655,13 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
     double* ax_new = aspace2;
     kbmul(nn, space, nn, len_u, a_red, len_u, n_max, 1.0, 0.0, x_new, nn);     // 420
     kbmul(nn, aspace, nn, len_u, a_red, len_u, n_max, 1.0, 0.0, ax_new, nn);   // 421
+    double* bx_new = bspace2;
+    if (gen_eig) kbmul(nn, bspace, nn, len_u, a_red, len_u, n_max, 1.0, 0.0, bx_new, nn);  // 423
     ph_close(h);
     h = ph_open(PH_RESID);
     for (int i = 0; i < n_max; ++i) h_active[i] = done[i] ? 0 : 1;
     DLB_CUDA_CHECK(cudaMemcpyAsync(d_active, h_active.data(), n_max * sizeof(int), cudaMemcpyHostToDevice, st));
-    residual_norms(st, num_sms, nn, n_max, ax_new, nn, x_new, nn, e_red, d_active, r, nn, d_norms,
+    residual_norms(st, num_sms, nn, n_max, ax_new, nn, gen_eig ? bx_new : x_new, nn, e_red, d_active, r, nn, d_norms,
                    resid_scratch.as<double>());                                        // 428-442
     ph_close(h);
     allreduce(d_norms, n_max, ncclSum);
@@ -671,9 +718,11 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
     h = ph_open(PH_RITZ);
     kbmul(nn, space, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(space2, ind_p), nn);
     kbmul(nn, aspace, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(aspace2, ind_p), nn);
+    if (gen_eig) kbmul(nn, bspace, nn, len_u, u_p, len_u, n_act, 1.0, 0.0, COL(bspace2, ind_p), nn);  // 500-503
     ph_close(h);
     std::swap(space, space2);
     std::swap(aspace, aspace2);
+    std::swap(bspace, bspace2);
     h = ph_open(PH_RESID);
     {
       int32_t m32 = n_act;
@@ -682,8 +731,16 @@ void Engine::lobpcg(bool verbose, int n, int n_targ, int n_max, int max_iter, do
     }
     ph_close(h);
     h = ph_open(PH_ORTHO);
-    ortho_vs_x(nn, n_max + n_act, n_act, space, nn, COL(space, ind_w), nn);             // 528
+    ortho_vs_x(nn, n_max + n_act, n_act, space, nn, COL(space, ind_w), nn, bspace);     // 528 / 524
     ph_close(h);
+    if (gen_eig && status == 0) {                                                       // 525-526
+      h = ph_open(PH_MV);
+      { int32_t m32 = n_act; bvec(&n32, &m32, COL(space, ind_w), COL(bspace, ind_w)); }
+      ph_close(h);
+      h = ph_open(PH_ORTHO);
+      b_ortho(nn, n_act, COL(space, ind_w), nn, COL(bspace, ind_w), nn);
+      ph_close(h);
+    }
     {
       CoeffStatus cs;  // checked lazily: the ortho_vs_x above has synchronised the stream
       DLB_CUDA_CHECK(cudaMemcpy(&cs, d_cfst, sizeof cs, cudaMemcpyDeviceToHost));
@@ -1017,9 +1074,10 @@ void diaglib_b200_finalize(void) {
   g.rank = 0;
   g.release_workspace();
   for (DevBuf* b : {&g.partial, &g.smallws, &g.resid_scratch, &g.scal, &g.b_rowptr, &g.b_col, &g.b_val, &g.b_diag,
-                    &g.b_send, &g.b_recv, &g.b_halo})
+                    &g.b_send, &g.b_recv, &g.b_halo, &g.bb_rowptr, &g.bb_col, &g.bb_val})
     b->release();
   g.A = CsrDevice();
+  g.B = CsrDevice();
   g.inited = false;
 }
 
@@ -1033,13 +1091,13 @@ const char* diaglib_b200_last_message(void) { return g.msg.c_str(); }
 void diaglib_b200_lobpcg_driver(const int32_t* verbose, const int32_t* gen_eig, const int32_t* n,
                                 const int32_t* n_targ, const int32_t* n_max, const int32_t* max_iter,
                                 const double* tol, const double* shift, diaglib_matvec_t matvec,
-                                diaglib_precnd_t precnd, diaglib_matvec_t /*bvec*/, double* eig, double* evec,
+                                diaglib_precnd_t precnd, diaglib_matvec_t bvec, double* eig, double* evec,
                                 int32_t* ok) {
   *ok = 0;
   if (!require_init()) return;
-  if (*gen_eig) {
+  if (*gen_eig && !bvec) {
     g.status = 0;
-    g.fail(DIAGLIB_B200_EARG, "lobpcg_driver: gen_eig=.true. (generalized problem) is out of scope of this library");
+    g.fail(DIAGLIB_B200_EARG, "lobpcg_driver: gen_eig=.true. needs a bvec callback");
     return;
   }
   if (*n_targ > *n_max || *n_max < 1 || *n < 0) {
@@ -1047,7 +1105,7 @@ void diaglib_b200_lobpcg_driver(const int32_t* verbose, const int32_t* gen_eig, 
     g.fail(DIAGLIB_B200_EARG, "lobpcg_driver: need 1 <= n_targ <= n_max");
     return;
   }
-  g.lobpcg(*verbose != 0, *n, *n_targ, *n_max, *max_iter, *tol, *shift, matvec, precnd, eig, evec, ok);
+  g.lobpcg(*verbose != 0, *gen_eig != 0, *n, *n_targ, *n_max, *max_iter, *tol, *shift, matvec, precnd, bvec, eig, evec, ok);
 }
 
 void diaglib_b200_davidson_driver(const int32_t* verbose, const int32_t* n, const int32_t* n_targ,
@@ -1092,6 +1150,33 @@ void diaglib_b200_ortho_vs_x(const int32_t* n, const int32_t* m, const int32_t* 
   g.end_call();
 }
 
+void diaglib_b200_b_ortho(const int32_t* n, const int32_t* m, double* u, double* bu) {
+  if (!require_init()) return;
+  g.begin_call(*m);
+  g.ensure_small(*m, *m);
+  Staged su(u, sizeof(double) * (size_t)*n * *m);
+  Staged sb(bu, sizeof(double) * (size_t)*n * *m);
+  g.b_ortho(*n, *m, su.dev, *n, sb.dev, *n);
+  su.back();
+  sb.back();
+  g.sync();
+  g.end_call();
+}
+
+void diaglib_b200_b_ortho_vs_x(const int32_t* n, const int32_t* m, const int32_t* k, const double* x,
+                               const double* bx, double* u) {
+  if (!require_init()) return;
+  g.begin_call(*k);
+  g.ensure_small(*k, *m);
+  Staged sx(x, sizeof(double) * (size_t)*n * *m);
+  Staged sbx(bx, sizeof(double) * (size_t)*n * *m);
+  Staged su(u, sizeof(double) * (size_t)*n * *k);
+  g.ortho_vs_x(*n, *m, *k, sx.dev, *n, su.dev, *n, sbx.dev);
+  su.back();
+  g.sync();
+  g.end_call();
+}
+
 void diaglib_b200_ortho(const int32_t* n, const int32_t* m, double* u, double* /*w*/) {
   if (!require_init()) return;
   g.begin_call(*m);
@@ -1117,6 +1202,44 @@ void diaglib_b200_diag_precnd(const int32_t* n, const int32_t* m, const double* 
     return;
   }
   diag_precnd(g.st, *n, *m, *shift, g.A.diag, x, *n, px, *n);
+}
+
+void diaglib_b200_csr_bvec(const int32_t* n, const int32_t* m, const double* x, double* bx) {
+  if (!g.inited || g.B.n != *n) {
+    g.fail(DIAGLIB_B200_EARG, "csr_bvec: no metric installed for n = %d (diaglib_b200_set_csr_b)", *n);
+    return;
+  }
+  if (g.B.n_halo > 0) g.halo_exchange(*m, x, *n);   // same halo plan and numbering as the matrix
+  spmm_csr(g.st, g.B, *m, x, *n, g.b_halo.as<double>(), bx, *n, 0.0);
+}
+
+int32_t diaglib_b200_set_csr_b(int64_t n_loc, int64_t n_halo, const int64_t* rowptr, const int32_t* col,
+                               const double* val) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  if (n_halo > 0 && (g.A.n != n_loc || g.A.n_halo != n_halo)) {
+    g.status = 0;
+    g.fail(DIAGLIB_B200_EARG, "set_csr_b: a metric with halo columns must share the matrix's halo (set_csr first)");
+    return DIAGLIB_B200_EARG;
+  }
+  const int64_t nnz = rowptr[n_loc];
+  if (!g.bb_rowptr.ensure((n_loc + 1) * sizeof(int64_t)) || !g.bb_col.ensure(std::max<int64_t>(nnz, 1) * sizeof(int32_t)) ||
+      !g.bb_val.ensure(std::max<int64_t>(nnz, 1) * sizeof(double)))
+    return DIAGLIB_B200_EALLOC;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.bb_rowptr.p, rowptr, (n_loc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.bb_col.p, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.bb_val.p, val, nnz * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
+  g.B = CsrDevice();
+  g.B.n = n_loc;
+  g.B.nnz = nnz;
+  g.B.n_halo = n_halo;
+  int64_t longest = 0;
+  for (int64_t i = 0; i < n_loc; ++i) longest = std::max(longest, rowptr[i + 1] - rowptr[i]);
+  g.B.max_row_nnz = (int)std::min<int64_t>(longest, INT32_MAX);
+  g.B.rowptr = g.bb_rowptr.as<int64_t>();
+  g.B.col = g.bb_col.as<int32_t>();
+  g.B.val = g.bb_val.as<double>();
+  return DIAGLIB_B200_OK;
 }
 
 int32_t diaglib_b200_set_csr(int64_t n_loc, int64_t n_halo, const int64_t* rowptr, const int32_t* col,

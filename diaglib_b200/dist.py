@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 from . import partition
-from .api import _check, lib, set_csr
+from .api import _check, lib, set_csr, set_csr_b
 
 
 def env_rank():
@@ -32,13 +32,17 @@ def init_comm(dist=None):
     return rank, world
 
 
-def install_partitioned(gen_rows, n: int, rank: int, world: int, dist=None):
+def install_partitioned(gen_rows, n: int, rank: int, world: int, dist=None, metric_rows=None):
     """gen_rows(r0, r1) -> (rowptr, col_global, val, diag) for the owned rows.  Localises the
-    columns, exchanges the needed ranges and installs matrix + halo plan.  Returns (r0, r1)."""
+    columns, exchanges the needed ranges and installs matrix + halo plan.  Returns (r0, r1).
+    metric_rows(r0, r1) -> (rowptr, col_global, val) optionally installs the metric B of the
+    generalized problem; its remote columns must lie inside the matrix's halo."""
     r0, r1 = partition.row_range(n, rank, world)
     rowptr, col, val, diag = gen_rows(r0, r1)
     if world == 1:
         set_csr(rowptr, col, val, diag)
+        if metric_rows is not None:
+            set_csr_b(*metric_rows(r0, r1))
         return r0, r1
     needed = partition.needed_ranges(col, n, rank, world)
     all_needed = [None] * world
@@ -46,4 +50,8 @@ def install_partitioned(gen_rows, n: int, rank: int, world: int, dist=None):
     col_loc, n_halo, recv = partition.localize(col, n, rank, world, needed)
     plan = partition.halo_plan(recv, all_needed, n, rank, world)
     set_csr(rowptr, col_loc, val, diag, n_halo=n_halo, halo_plan=plan)
+    if metric_rows is not None:
+        b_rowptr, b_col, b_val = metric_rows(r0, r1)
+        b_loc, _, _ = partition.localize(b_col, n, rank, world, needed)
+        set_csr_b(b_rowptr, b_loc, b_val, n_halo=n_halo)
     return r0, r1

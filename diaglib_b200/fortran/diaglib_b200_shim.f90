@@ -1,8 +1,9 @@
 !
 ! diaglib_b200_shim.f90 -- drop-in `module diaglib` for Fortran hosts.
 !
-! Provides lobpcg_driver / davidson_driver / ortho / ortho_cd / ortho_vs_x with exactly the
-! argument lists of Molecolab-Pisa/diaglib (diaglib.f90:171-172, 1483-1484, 3052, 3185, 3481)
+! Provides lobpcg_driver / davidson_driver / ortho / b_ortho / ortho_cd / ortho_vs_x /
+! b_ortho_vs_x with exactly the argument lists of Molecolab-Pisa/diaglib (diaglib.f90:171-172,
+! 1483-1484, 3052, 3094, 3185, 3481, 3576)
 ! and forwards them to the C-ABI of libdiaglib_b200.so (include/diaglib_b200.h) through
 ! iso_c_binding.  A program that does `use diaglib` and links this module plus
 ! -ldiaglib_b200 instead of the reference diaglib.o runs the B200 path unchanged.
@@ -24,8 +25,9 @@ module diaglib
   use iso_c_binding
   implicit none
   private
-  public :: lobpcg_driver, davidson_driver, ortho, ortho_cd, ortho_vs_x
-  public :: diaglib_b200_init, diaglib_b200_set_csr, diaglib_b200_csr_matvec, diaglib_b200_diag_precnd
+  public :: lobpcg_driver, davidson_driver, ortho, b_ortho, ortho_cd, ortho_vs_x, b_ortho_vs_x
+  public :: diaglib_b200_init, diaglib_b200_set_csr, diaglib_b200_set_csr_b
+  public :: diaglib_b200_csr_matvec, diaglib_b200_csr_bvec, diaglib_b200_diag_precnd
 !
   interface
     subroutine c_lobpcg(verbose, gen_eig, n, n_targ, n_max, max_iter, tol, shift, matvec, precnd, bvec, &
@@ -58,6 +60,17 @@ module diaglib
       real(c_double),     intent(in)    :: x(*), ax(*)
       real(c_double),     intent(inout) :: u(*), au(*)
     end subroutine c_ortho_vs_x
+    subroutine c_b_ortho(n, m, u, bu) bind(C, name='diaglib_b200_b_ortho')
+      import :: c_int32_t, c_double
+      integer(c_int32_t), intent(in)    :: n, m
+      real(c_double),     intent(inout) :: u(*), bu(*)
+    end subroutine c_b_ortho
+    subroutine c_b_ortho_vs_x(n, m, k, x, bx, u) bind(C, name='diaglib_b200_b_ortho_vs_x')
+      import :: c_int32_t, c_double
+      integer(c_int32_t), intent(in)    :: n, m, k
+      real(c_double),     intent(in)    :: x(*), bx(*)
+      real(c_double),     intent(inout) :: u(*)
+    end subroutine c_b_ortho_vs_x
     subroutine c_ortho(n, m, u, w) bind(C, name='diaglib_b200_ortho')
       import :: c_int32_t, c_double
       integer(c_int32_t), intent(in)    :: n, m
@@ -81,7 +94,22 @@ module diaglib
       real(c_double),     intent(in) :: val(*), diag(*)
       integer(c_int32_t)             :: st
     end function diaglib_b200_set_csr
-    ! built-in conforming callbacks (device pointers); pass them as matvec / precnd
+    function diaglib_b200_set_csr_b(n_loc, n_halo, rowptr, col, val) &
+             bind(C, name='diaglib_b200_set_csr_b') result(st)
+      import :: c_int32_t, c_int64_t, c_double
+      integer(c_int64_t), value      :: n_loc, n_halo
+      integer(c_int64_t), intent(in) :: rowptr(*)
+      integer(c_int32_t), intent(in) :: col(*)
+      real(c_double),     intent(in) :: val(*)
+      integer(c_int32_t)             :: st
+    end function diaglib_b200_set_csr_b
+    ! built-in conforming callbacks (device pointers); pass them as matvec / precnd / bvec
+    subroutine diaglib_b200_csr_bvec(n, m, x, bx) bind(C, name='diaglib_b200_csr_bvec')
+      import :: c_int32_t, c_double
+      integer(c_int32_t), intent(in)    :: n, m
+      real(c_double),     intent(in)    :: x(*)
+      real(c_double),     intent(inout) :: bx(*)
+    end subroutine diaglib_b200_csr_bvec
     subroutine diaglib_b200_csr_matvec(n, m, x, ax) bind(C, name='diaglib_b200_csr_matvec')
       import :: c_int32_t, c_double
       integer(c_int32_t), intent(in)    :: n, m
@@ -160,6 +188,23 @@ contains
     call c_ortho_vs_x(n, m, k, x, u, ax, au)
     call check_stop('ortho_vs_x')
   end subroutine ortho_vs_x
+!
+! diaglib.f90:3094
+  subroutine b_ortho(n,m,u,bu)
+    integer,  intent(in)    :: n, m
+    real(8),  intent(inout) :: u(n,m), bu(n,m)
+    call c_b_ortho(n, m, u, bu)
+    call check_stop('b_ortho')
+  end subroutine b_ortho
+!
+! diaglib.f90:3576
+  subroutine b_ortho_vs_x(n,m,k,x,bx,u)
+    integer,  intent(in)    :: n, m, k
+    real(8),  intent(in)    :: x(n,m), bx(n,m)
+    real(8),  intent(inout) :: u(n,k)
+    call c_b_ortho_vs_x(n, m, k, x, bx, u)
+    call check_stop('b_ortho_vs_x')
+  end subroutine b_ortho_vs_x
 !
 ! diaglib.f90:3052
   subroutine ortho(n,m,u,w)

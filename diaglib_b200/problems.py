@@ -187,3 +187,23 @@ def guess_lowest_diag(diag_glob, n_max: int, r0: int = 0, r1: int | None = None)
         if r0 <= ipos < r1:
             out[ipos - r0, j] = 1.0
     return out
+
+
+def metric_like(csr, eps: float = 0.02, seed: int = 7, r0: int = 0):
+    """SPD metric B for the generalized problem A x = lambda B x (gen_eig branch,
+    diaglib.f90:299-302): same sparsity pattern as the matrix, unit-ish diagonal
+    b_ii = 1 + 0.3 u(i) and symmetric off-diagonals eps * u(min(i,j), max(i,j)) / row-length scale,
+    diagonally dominant by construction.  csr holds rows [r0, r0 + n_loc) with GLOBAL column
+    indices.  Returns (rowptr, col, val)."""
+    rowptr, col, _, _ = csr
+    n = len(rowptr) - 1
+    rows = r0 + np.repeat(np.arange(n, dtype=np.int64), np.diff(rowptr))
+    c = col.astype(np.int64)
+    lo, hi = np.minimum(rows, c), np.maximum(rows, c)
+    h = splitmix64((lo * np.int64(2654435761) + hi + np.int64(seed) * np.int64(1000003)).astype(np.uint64))
+    u = (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    maxlen = max(1, int(np.diff(rowptr).max()))
+    val = eps * (u - 0.5) * (2.0 / maxlen)
+    dg = rows == c
+    val[dg] = 1.0 + 0.3 * u[dg]
+    return rowptr.copy(), col.copy(), val

@@ -45,15 +45,17 @@ enum {
   DIAGLIB_B200_ECHOL = 3,       /* Cholesky level-shift loop exhausted    (diaglib.f90:3276-3284) */
   DIAGLIB_B200_EORTHO = 4,      /* ortho_vs_x did not converge            (diaglib.f90:3568) */
   DIAGLIB_B200_ENODEVICE = 5,   /* no CUDA device / library not initialised */
-  DIAGLIB_B200_EARG = 6,        /* unsupported argument (e.g. gen_eig=.true., out of scope) */
+  DIAGLIB_B200_EARG = 6,        /* invalid argument (n_targ > n_max, gen_eig without bvec, no matrix installed) */
   DIAGLIB_B200_ECOMM = 7        /* NCCL failure */
 };
 
 /* ---- drivers ----------------------------------------------------------------------- */
 
 /* replaces lobpcg_driver, diaglib.f90:171-172 (argument list 221-228).  logicals are
- * 4-byte integers (gfortran logical(4)).  gen_eig must be .false. (the generalized branch
- * is out of scope); bvec is never called. */
+ * 4-byte integers (gfortran logical(4)).  With gen_eig = .true. the generalized problem
+ * A x = lambda B x is solved (diaglib.f90:299-302, 329-346, 357-364, 422-436, 500-526 with
+ * b_ortho 3094-3183 and b_ortho_vs_x 3576-3663): bvec(n,m,x,bx) applies the metric, same
+ * contract as matvec; with gen_eig = .false. bvec is never called and may be NULL. */
 void diaglib_b200_lobpcg_driver(const int32_t* verbose, const int32_t* gen_eig, const int32_t* n,
                                 const int32_t* n_targ, const int32_t* n_max, const int32_t* max_iter,
                                 const double* tol, const double* shift, diaglib_matvec_t matvec,
@@ -74,6 +76,11 @@ void diaglib_b200_ortho_cd(const int32_t* n, const int32_t* m, double* u, double
  * signature compatibility and, as in the reference, never referenced */
 void diaglib_b200_ortho_vs_x(const int32_t* n, const int32_t* m, const int32_t* k, const double* x, double* u,
                              const double* ax, double* au);
+/* replaces b_ortho, diaglib.f90:3094 : u(n,m), bu(n,m) = B u, both in/out */
+void diaglib_b200_b_ortho(const int32_t* n, const int32_t* m, double* u, double* bu);
+/* replaces b_ortho_vs_x, diaglib.f90:3576 : x(n,m), bx(n,m) = B x in, u(n,k) in/out */
+void diaglib_b200_b_ortho_vs_x(const int32_t* n, const int32_t* m, const int32_t* k, const double* x,
+                               const double* bx, double* u);
 /* replaces ortho (QR fallback), diaglib.f90:3052 : second argument untouched, as in the reference */
 void diaglib_b200_ortho(const int32_t* n, const int32_t* m, double* u, double* w);
 
@@ -81,6 +88,9 @@ void diaglib_b200_ortho(const int32_t* n, const int32_t* m, double* u, double* w
 
 /* CSR block matvec on the installed matrix; replaces the role of mmult, main.f90:72-90 */
 void diaglib_b200_csr_matvec(const int32_t* n, const int32_t* m, const double* x, double* ax);
+/* CSR block product with the metric installed by diaglib_b200_set_csr_b; a conforming bvec
+ * (the reference's tests use bmult, main.f90, in the same role) */
+void diaglib_b200_csr_bvec(const int32_t* n, const int32_t* m, const double* x, double* bx);
 /* diagonal shift-and-invert preconditioner; replaces the role of mprec, main.f90:146-171 */
 void diaglib_b200_diag_precnd(const int32_t* n, const int32_t* m, const double* shift, const double* x,
                               double* px);
@@ -103,6 +113,10 @@ const char* diaglib_b200_last_message(void);
  * by the exchange plan below.  diag = the matrix diagonal of the owned rows (preconditioner). */
 int32_t diaglib_b200_set_csr(int64_t n_loc, int64_t n_halo, const int64_t* rowptr, const int32_t* col,
                              const double* val, const double* diag);
+/* metric B of the generalized problem for the built-in bvec.  Same conventions as set_csr; if
+ * it has halo columns (n_halo > 0) they use the matrix's halo numbering and exchange plan. */
+int32_t diaglib_b200_set_csr_b(int64_t n_loc, int64_t n_halo, const int64_t* rowptr, const int32_t* col,
+                               const double* val);
 /* halo exchange plan: for neighbour i, send owned rows [send_row0[i], +send_cnt[i]) and
  * receive recv_cnt[i] rows into halo rows [recv_off[i], ...). */
 int32_t diaglib_b200_set_halo(int32_t n_nbr, const int32_t* peer, const int64_t* send_row0,

@@ -230,6 +230,48 @@ void ortho_vs_x(int n, int m, int k, const double* x, double* u) {
   }
 }
 
+// diaglib.f90:3094-3183 (use_svd = .false.): B-orthonormalise u given bu = B u with the
+// Cholesky factor of u^T B u.  As in the reference the dpotrf status is not examined.
+void b_ortho(int n, int m, double* u, double* bu) {
+  std::vector<double> metric((size_t)m * m);
+  char lo = 'l', r = 'r', t = 't', nd = 'n';
+  dgemm('t', 'n', m, m, n, one, u, n, bu, n, zero, metric.data(), m);            // 3124
+  scipy_dpotrf_(&lo, &m, metric.data(), &m, &info, 1);                           // 3172
+  scipy_dtrsm_(&r, &lo, &t, &nd, &n, &m, &one, metric.data(), &m, u, &n, 1, 1, 1, 1);   // 3176
+  scipy_dtrsm_(&r, &lo, &t, &nd, &n, &m, &one, metric.data(), &m, bu, &n, 1, 1, 1, 1);  // 3177
+}
+
+// diaglib.f90:3576-3663 (useqr = .false.): u <- u - x (bx^T u), then ortho_cd(u), iterated
+void b_ortho_vs_x(int n, int m, int k, const double* x, const double* bx, double* u) {
+  const int maxit = 10;
+  bool ok = false, done = false;
+  int it = 0;
+  double growth = one, xu_norm;
+  std::vector<double> xu((size_t)m * k);
+  ortho_cd(n, k, u, growth, ok);  // 3622
+  if (!ok) ortho(n, k, u);        // 3623
+  while (!done) {
+    it = it + 1;
+    ++stat_ortho_vs_x_sweeps;
+    dgemm('t', 'n', m, k, n, one, bx, n, u, n, zero, xu.data(), m);   // 3632
+    dgemm('n', 'n', n, k, m, -one, x, n, xu.data(), m, one, u, n);    // 3633
+    ortho_cd(n, k, u, growth, ok);                                    // 3637
+    if (!ok) ortho(n, k, u);                                          // 3638
+    if (!ok) {                                                        // 3647-3649
+      dgemm('t', 'n', m, k, n, one, bx, n, u, n, zero, xu.data(), m);
+      xu_norm = dnrm2(m * k, xu.data());
+    } else {
+      xu_norm = growth * eps;                                         // 3651
+    }
+    done = xu_norm < tol_ortho;
+    if (it > maxit) {  // 3657: `stop ' catastrophic failure of b_ortho_vs_x'`
+      std::printf(" catastrophic failure of b_ortho_vs_x\n");
+      last_status = 4;
+      return;
+    }
+  }
+}
+
 // diaglib.f90:3686-3732
 void get_coeffs(int len_a, int len_u, int n_max, int n_act, const double* a_red, double* u_x, double* u_p) {
   int off_x = n_max - n_act;
@@ -284,22 +326,19 @@ void record(int it, int n_act, int n_max, const double* eig, const double* r_nor
 extern "C" {
 
 // ------------------------------------------------------------------------------------
-// lobpcg_driver, standard (gen_eig=.false.) branch — diaglib.f90:171-556.
-// The reference also allocates bspace/bx_new (n x 3n_max, n x n_max; 258-271) which the
-// standard branch never reads; they are skipped here to halve host memory.
+// lobpcg_driver — diaglib.f90:171-556, standard and generalized (gen_eig) branches.
+// The reference always allocates bspace/bx_new (n x 3n_max, n x n_max; 258-271); the
+// standard branch never reads them, so they are only allocated here when gen_eig is set.
 // ------------------------------------------------------------------------------------
 void oracle_lobpcg_driver(const int32_t* verbose_, const int32_t* gen_eig_, const int32_t* n_,
                           const int32_t* n_targ_, const int32_t* n_max_, const int32_t* max_iter_,
                           const double* tol_, const double* shift_, matvec_t matvec, precnd_t precnd,
-                          void* /*bvec*/, double* eig, double* evec, int32_t* ok_) {
+                          matvec_t bvec, double* eig, double* evec, int32_t* ok_) {
   const bool verbose = *verbose_ != 0;
   const int n = *n_, n_targ = *n_targ_, n_max = *n_max_, max_iter = *max_iter_;
   const double tol = *tol_, shift = *shift_;
   last_status = 0;
-  if (*gen_eig_) {
-    std::printf("oracle: gen_eig=.true. is out of scope (SURVEY section 8f)\n");
-    *ok_ = 0; last_status = 9; return;
-  }
+  const bool gen_eig = *gen_eig_ != 0;
   lwork = get_mem_lapack(n, n_max);
   work.assign(lwork, 0.0);
   tau.assign(2 * n_max, 0.0);
@@ -308,6 +347,7 @@ void oracle_lobpcg_driver(const int32_t* verbose_, const int32_t* gen_eig_, cons
   std::vector<double> space(nn * len_a, 0.0), aspace(nn * len_a, 0.0), r(nn * n_max);
   std::vector<double> a_red((size_t)len_a * len_a, 0.0), e_red(len_a);
   std::vector<double> x_new(nn * n_max), ax_new(nn * n_max);
+  std::vector<double> bspace(gen_eig ? nn * len_a : 0, 0.0), bx_new(gen_eig ? nn * n_max : 0);
   std::vector<char> done(n_max, 0);
   std::vector<double> r_norm(2 * n_max, 0.0);
   hist.clear(n_max);
@@ -316,7 +356,12 @@ void oracle_lobpcg_driver(const int32_t* verbose_, const int32_t* gen_eig_, cons
   char v = 'v', lo = 'l';
 
   check_guess(n, n_max, evec);                                                 // 295
+  if (gen_eig) {                                                               // 299-302
+    bvec(&n, &n_max, evec, bx_new.data());
+    b_ortho(n, n_max, evec, bx_new.data());
+  }
   dcopy(n * n_max, evec, space.data());                                        // 306
+  if (gen_eig) dcopy(n * n_max, bx_new.data(), bspace.data());                 // 307
   t1 = now();
   matvec(&n, &n_max, space.data(), aspace.data());                             // 309
   t_mv += now() - t1;
@@ -330,8 +375,13 @@ void oracle_lobpcg_driver(const int32_t* verbose_, const int32_t* gen_eig_, cons
   dcopy(n * n_max, evec, space.data());
   dgemm('n', 'n', n, n_max, n_max, one, aspace.data(), n, a_red.data(), len_a, zero, evec, n);  // 324
   dcopy(n * n_max, evec, aspace.data());
+  if (gen_eig) {                                                               // 329-332
+    dgemm('n', 'n', n, n_max, n_max, one, bspace.data(), n, a_red.data(), len_a, zero, evec, n);
+    dcopy(n * n_max, evec, bspace.data());
+  }
   dcopy(n * n_max, aspace.data(), r.data());                                   // 337
-  for (int i = 0; i < n_max; ++i) daxpy(n, -eig[i], &space[nn * i], &r[nn * i]);  // 343-345
+  for (int i = 0; i < n_max; ++i)                                              // 338-346
+    daxpy(n, -eig[i], gen_eig ? &bspace[nn * i] : &space[nn * i], &r[nn * i]);
   int ind_x = 1;
   int ind_w = ind_x + n_max;
   int ind_p = 0;
@@ -340,7 +390,13 @@ void oracle_lobpcg_driver(const int32_t* verbose_, const int32_t* gen_eig_, cons
     precnd(&n, &n_max, &fac, &r[nn * (ind_x - 1)], &space[nn * (ind_w - 1)]);  // 352
   }
   t1 = now();
-  ortho_vs_x(n, n_max, n_max, space.data(), &space[nn * (ind_w - 1)]);         // 366
+  if (gen_eig) {                                                               // 357-364
+    b_ortho_vs_x(n, n_max, n_max, space.data(), bspace.data(), &space[nn * (ind_w - 1)]);
+    bvec(&n, &n_max, &space[nn * (ind_w - 1)], &bspace[nn * (ind_w - 1)]);
+    b_ortho(n, n_max, &space[nn * (ind_w - 1)], &bspace[nn * (ind_w - 1)]);
+  } else {
+    ortho_vs_x(n, n_max, n_max, space.data(), &space[nn * (ind_w - 1)]);       // 366
+  }
   t_ortho += now() - t1;
 
   const double tol_rms = tol, tol_max = 10.0 * tol;
@@ -372,10 +428,12 @@ void oracle_lobpcg_driver(const int32_t* verbose_, const int32_t* gen_eig_, cons
     for (int i = 0; i < n_max; ++i) eig[i] = e_red[i];                          // 416
     dgemm('n', 'n', n, n_max, len_u, one, space.data(), n, a_red.data(), len_a, zero, x_new.data(), n);    // 420
     dgemm('n', 'n', n, n_max, len_u, one, aspace.data(), n, a_red.data(), len_a, zero, ax_new.data(), n);  // 421
+    if (gen_eig)                                                                // 422-424
+      dgemm('n', 'n', n, n_max, len_u, one, bspace.data(), n, a_red.data(), len_a, zero, bx_new.data(), n);
     dcopy(n * n_max, ax_new.data(), r.data());                                  // 428
     for (int i = 0; i < n_max; ++i) {                                            // 429-442
       if (done[i]) continue;
-      daxpy(n, -eig[i], &x_new[nn * i], &r[nn * i]);
+      daxpy(n, -eig[i], gen_eig ? &bx_new[nn * i] : &x_new[nn * i], &r[nn * i]);
       r_norm[2 * i] = dnrm2(n, &r[nn * i]) / sqrtn;
       double mx = 0.0;
       const double* ri = &r[nn * i];
@@ -416,14 +474,25 @@ void oracle_lobpcg_driver(const int32_t* verbose_, const int32_t* gen_eig_, cons
     dcopy(n_act * n, evec, &space[nn * (ind_p - 1)]);
     dgemm('n', 'n', n, n_act, len_u, one, aspace.data(), n, u_p.data(), len_u, zero, evec, n);  // 497
     dcopy(n_act * n, evec, &aspace[nn * (ind_p - 1)]);
+    if (gen_eig) {                                                               // 500-503
+      dgemm('n', 'n', n, n_act, len_u, one, bspace.data(), n, u_p.data(), len_u, zero, evec, n);
+      dcopy(n_act * n, evec, &bspace[nn * (ind_p - 1)]);
+    }
     dcopy(n * n_max, x_new.data(), space.data());                                // 510
     dcopy(n * n_max, ax_new.data(), aspace.data());                              // 511
+    if (gen_eig) dcopy(n * n_max, bx_new.data(), bspace.data());                 // 512-514
     {
       double fac = shift - eig[0];
       precnd(&n, &n_act, &fac, &r[nn * (ind_x - 1)], &space[nn * (ind_w - 1)]);  // 518
     }
     t1 = now();
-    ortho_vs_x(n, n_max + n_act, n_act, space.data(), &space[nn * (ind_w - 1)]);  // 528
+    if (gen_eig) {                                                               // 523-526
+      b_ortho_vs_x(n, n_max + n_act, n_act, space.data(), bspace.data(), &space[nn * (ind_w - 1)]);
+      bvec(&n, &n_act, &space[nn * (ind_w - 1)], &bspace[nn * (ind_w - 1)]);
+      b_ortho(n, n_act, &space[nn * (ind_w - 1)], &bspace[nn * (ind_w - 1)]);
+    } else {
+      ortho_vs_x(n, n_max + n_act, n_act, space.data(), &space[nn * (ind_w - 1)]);  // 528
+    }
     t_ortho += now() - t1;
   }
   t2 = now();
@@ -584,6 +653,11 @@ void oracle_ortho_vs_x(const int32_t* n, const int32_t* m, const int32_t* k, con
   ortho_vs_x(*n, *m, *k, x, u);
 }
 void oracle_ortho(const int32_t* n, const int32_t* m, double* u) { ortho(*n, *m, u); }
+void oracle_b_ortho(const int32_t* n, const int32_t* m, double* u, double* bu) { b_ortho(*n, *m, u, bu); }
+void oracle_b_ortho_vs_x(const int32_t* n, const int32_t* m, const int32_t* k, const double* x, const double* bx,
+                         double* u) {
+  b_ortho_vs_x(*n, *m, *k, x, bx, u);
+}
 double oracle_norm_est(const int32_t* m, const double* a) { return norm_est(*m, a); }
 void oracle_get_coeffs(const int32_t* len_a, const int32_t* len_u, const int32_t* n_max,
                        const int32_t* n_act, const double* a_red, double* u_x, double* u_p) {
@@ -639,6 +713,28 @@ void oracle_set_csr(int64_t n, const int64_t* rowptr, const int32_t* col, const 
   g_n = n; g_rowptr = rowptr; g_col = col; g_val = val; g_diag = diag;
 }
 void oracle_set_dense(int64_t n, const double* a, const double* diag) { g_n = n; g_dense = a; g_diag = diag; }
+
+// metric B of the generalized problem (role of the reference's bvec callback, diaglib.f90:206)
+static const int64_t* gb_rowptr = nullptr;
+static const int32_t* gb_col = nullptr;
+static const double* gb_val = nullptr;
+void oracle_set_csr_b(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val) {
+  (void)n; gb_rowptr = rowptr; gb_col = col; gb_val = val;
+}
+void oracle_csr_bvec(const int32_t* n_, const int32_t* m_, const double* x, double* bx) {
+  const int64_t n = *n_;
+  const int m = *m_;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t b = gb_rowptr[i], e = gb_rowptr[i + 1];
+    for (int j = 0; j < m; ++j) {
+      const double* xj = x + (size_t)j * n;
+      double s = 0.0;
+      for (int64_t k = b; k < e; ++k) s = std::fma(gb_val[k], xj[gb_col[k]], s);
+      bx[i + (size_t)j * n] = s;
+    }
+  }
+}
 
 // CSR block matvec, contract of diaglib.f90:66 / main.f90:72-90.  Each row is summed in
 // CSR order with fused multiply-adds, the same order the CUDA SpMM uses.

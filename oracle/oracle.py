@@ -47,6 +47,7 @@ def _p(a):
 
 class _Keep:
     refs: list = []
+    refs_b: list = []
 
 
 def set_csr(rowptr, col, val, diag):
@@ -56,6 +57,15 @@ def set_csr(rowptr, col, val, diag):
     diag = np.ascontiguousarray(diag, dtype=np.float64)
     _Keep.refs = [rowptr, col, val, diag]
     lib().oracle_set_csr(C.c_int64(len(rowptr) - 1), _p(rowptr), _p(col), _p(val), _p(diag))
+
+
+def set_csr_b(rowptr, col, val):
+    """metric of the generalized problem, applied by oracle_csr_bvec"""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    _Keep.refs_b = [rowptr, col, val]
+    lib().oracle_set_csr_b(C.c_int64(len(rowptr) - 1), _p(rowptr), _p(col), _p(val))
 
 
 def set_dense(a, diag=None):
@@ -96,15 +106,16 @@ def _collect(n_max):
 
 
 def lobpcg(evec, n_targ, max_iter, tol, shift=0.0, matvec="oracle_csr_matvec", precnd="oracle_diag_precnd",
-           verbose=False):
+           verbose=False, gen_eig=False, bvec="oracle_csr_bvec"):
     """Runs the oracle's lobpcg_driver.  evec: (n, n_max) Fortran-ordered guess, overwritten."""
     assert evec.flags.f_contiguous and evec.dtype == np.float64
     n, n_max = evec.shape
     eig = np.zeros(n_max)
     ok = C.c_int32(0)
     lib().oracle_stats_reset()
-    lib().oracle_lobpcg_driver(_i(verbose), _i(0), _i(n), _i(n_targ), _i(n_max), _i(max_iter), _d(tol), _d(shift),
-                               _cb(matvec), _cb(precnd), None, _p(eig), _p(evec), C.byref(ok))
+    lib().oracle_lobpcg_driver(_i(verbose), _i(1 if gen_eig else 0), _i(n), _i(n_targ), _i(n_max), _i(max_iter),
+                               _d(tol), _d(shift), _cb(matvec), _cb(precnd), _cb(bvec) if gen_eig else None, _p(eig),
+                               _p(evec), C.byref(ok))
     out = _collect(n_max)
     out.update(eig=eig, ok=bool(ok.value), hist_eig=out["eig"])
     return out
@@ -138,6 +149,25 @@ def ortho_vs_x(x, u):
     n, m = x.shape
     k = u.shape[1]
     lib().oracle_ortho_vs_x(_i(n), _i(m), _i(k), _p(x), _p(u))
+
+
+def b_ortho(u, bu):
+    assert u.flags.f_contiguous and bu.flags.f_contiguous
+    n, m = u.shape
+    lib().oracle_b_ortho(_i(n), _i(m), _p(u), _p(bu))
+
+
+def b_ortho_vs_x(x, bx, u):
+    assert x.flags.f_contiguous and bx.flags.f_contiguous and u.flags.f_contiguous
+    n, m = x.shape
+    lib().oracle_b_ortho_vs_x(_i(n), _i(m), _i(u.shape[1]), _p(x), _p(bx), _p(u))
+
+
+def csr_bvec(x):
+    n, m = x.shape
+    bx = np.zeros_like(x, order="F")
+    lib().oracle_csr_bvec(_i(n), _i(m), _p(x), _p(bx))
+    return bx
 
 
 def ortho(u):

@@ -68,6 +68,14 @@ def _worker(rank, world, port, gen, out_q):
         ax = a_loc @ xe
         a_full = sp.csr_matrix((full[2], full[1], full[0]), shape=(n, n))
         err_spmm = float(np.abs(ax - (a_full @ x_glob)[r0:r1]).max())
+        # metric of the generalized problem: localised with the matrix's halo numbering
+        # (dist.install_partitioned(metric_rows=...)), applied to the same extended block
+        b_rowptr, b_col, b_val = P.metric_like((rowptr, col, val, diag), r0=r0)
+        b_loc, b_halo, _ = partition.localize(b_col, n, rank, world, needed)
+        b_full = P.metric_like(full)
+        bx = sp.csr_matrix((b_val, b_loc, b_rowptr), shape=(r1 - r0, r1 - r0 + n_halo)) @ xe
+        bx_ref = (sp.csr_matrix((b_full[2], b_full[1], b_full[0]), shape=(n, n)) @ x_glob)[r0:r1]
+        err_metric = float(np.abs(bx - bx_ref).max()) + (0.0 if b_halo == n_halo else 1.0)
         # Gram all-reduce: sum of the per-rank partial X^T (A X) equals the global one
         g = torch.from_numpy(x.T @ ax)
         dist.all_reduce(g)
@@ -81,7 +89,7 @@ def _worker(rank, world, port, gen, out_q):
         ref = a_full @ x_glob
         err_norm = float(max((np.abs(ss.numpy() - (ref * ref).sum(axis=0)) / (ref * ref).sum(axis=0)).max(),
                              np.abs(mx.numpy() - np.abs(ref).max(axis=0)).max()))
-        out_q.put((rank, err_spmm, err_gram, err_norm, int(n_halo), len(peer)))
+        out_q.put((rank, err_spmm, err_gram, err_norm, int(n_halo), len(peer), err_metric))
     finally:
         dist.destroy_process_group()
 
@@ -99,8 +107,8 @@ def test_partitioned_spmm_and_reductions_world2(gen):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, e1, e2, e3, n_halo, n_peer in res:
-        assert e1 < 1e-12 and e2 < 1e-13 and e3 < 1e-13
+    for rank, e1, e2, e3, n_halo, n_peer, e4 in res:
+        assert e1 < 1e-12 and e2 < 1e-13 and e3 < 1e-13 and e4 < 1e-13
         assert n_halo > 0 and n_peer == 1
     if gen == "lap3d":  # z-slabs: the halo is exactly one 16x16 plane
         assert all(r[4] == 256 for r in res)

@@ -231,10 +231,139 @@ def test_device_resident_evec(gpu_lib, oracle):
     assert np.array_equal(dev.numpy(), ev_h)
 
 
-def test_gen_eig_is_rejected(gpu_lib):
+def test_gen_eig_without_metric_fails_loudly(gpu_lib):
+    """gen_eig=.true. with the built-in bvec but no metric installed for this n"""
+    gpu_lib.set_csr(*P.toy_sparse(100))
     ev = P.guess(100, 4)
     with pytest.raises(gpu_lib.DiaglibError):
         gpu_lib.lobpcg_driver(False, True, 100, 2, 4, 10, 1e-8, 0.0, None, None, None, np.zeros(4), ev)
+
+
+# ---- generalized problem (gen_eig branch, diaglib.f90:299-302, 357-364, 422-436, 500-526) ------
+def check_gen_solution(csr, bcsr, eig, evec, n_targ, tol):
+    import scipy.sparse as sp
+    n = len(csr[0]) - 1
+    a = sp.csr_matrix((csr[2], csr[1], csr[0]), shape=(n, n))
+    b = sp.csr_matrix((bcsr[2], bcsr[1], bcsr[0]), shape=(n, n))
+    x = evec[:, :n_targ]
+    res = a @ x - (b @ x) * eig[:n_targ]
+    assert (np.linalg.norm(res, axis=0) / np.sqrt(n)).max() < 2 * tol
+    assert np.abs(x.T @ (b @ x) - np.eye(n_targ)).max() < 1e-10   # B-orthonormal Ritz vectors
+
+
+@pytest.mark.parametrize("gen", ["toy_sparse", "lap3d"])
+def test_gen_eig_lobpcg_vs_oracle(gpu_lib, oracle, gen):
+    if gen == "toy_sparse":
+        csr = P.toy_sparse(4096)
+        n_targ, n_max, guess = 5, 10, None
+    else:
+        csr = P.lap3d(32, 16, 16, delta=1.0)
+        n_targ, n_max = 6, 11
+        guess = noisy_unit_guess(csr, n_max, eps=0.03)
+    n = len(csr[0]) - 1
+    bcsr = P.metric_like(csr)
+    install(gpu_lib, oracle, csr)
+    oracle.set_csr_b(*bcsr)
+    gpu_lib.set_csr_b(*bcsr)
+    ev_o = P.guess(n, n_max) if guess is None else guess.copy(order="F")
+    ev_g = ev_o.copy(order="F")
+    eig_g = np.zeros(n_max)
+    ro = oracle.lobpcg(ev_o, n_targ, 300, 1e-8, gen_eig=True)
+    ok = gpu_lib.lobpcg_driver(False, True, n, n_targ, n_max, 300, 1e-8, 0.0, None, None, None, eig_g, ev_g)
+    hg = gpu_lib.last_history(n_max)
+    assert ok and ro["ok"]
+    assert_parity(ro, ok, eig_g, hg, n_targ)
+    assert_history(ro, hg, n_targ, upto=min(3, len(hg["it"])))
+    check_gen_solution(csr, bcsr, eig_g, ev_g, n_targ, 1e-8)
+    # against dense LAPACK on the pencil (A, B)
+    if n <= 5000:
+        import scipy.linalg as sl
+        import scipy.sparse as sp
+        a = sp.csr_matrix((csr[2], csr[1], csr[0]), shape=(n, n)).toarray()
+        b = sp.csr_matrix((bcsr[2], bcsr[1], bcsr[0]), shape=(n, n)).toarray()
+        w = sl.eigh(a, b, eigvals_only=True, subset_by_index=[0, n_targ - 1])
+        assert np.abs(eig_g[:n_targ] - w).max() / np.abs(w).max() < REL
+
+
+def test_gen_eig_identity_metric_matches_standard(gpu_lib, oracle):
+    """B = I: the generalized branch must reproduce the standard one"""
+    csr = P.toy_sparse(3000)
+    n, n_targ, n_max = 3000, 4, 9
+    ident = (np.arange(n + 1, dtype=np.int64), np.arange(n, dtype=np.int32), np.ones(n))
+    gpu_lib.set_csr(*csr)
+    gpu_lib.set_csr_b(*ident)
+    ev_s, ev_g = P.guess(n, n_max), P.guess(n, n_max)
+    eig_s, eig_g = np.zeros(n_max), np.zeros(n_max)
+    ok_s = gpu_lib.lobpcg_driver(False, False, n, n_targ, n_max, 300, 1e-8, 0.0, None, None, None, eig_s, ev_s)
+    its_s = len(gpu_lib.last_history(n_max)["it"])
+    ok_g = gpu_lib.lobpcg_driver(False, True, n, n_targ, n_max, 300, 1e-8, 0.0, None, None, None, eig_g, ev_g)
+    its_g = len(gpu_lib.last_history(n_max)["it"])
+    assert ok_s and ok_g
+    assert np.abs(eig_s[:n_targ] - eig_g[:n_targ]).max() / np.abs(eig_s[:n_targ]).max() < REL
+    assert abs(its_s - its_g) <= 1
+
+
+def test_gen_eig_user_bvec_callback(gpu_lib, oracle):
+    """caller-written bvec(n,m,x,bx) on the library stream (contract diaglib.f90:206)"""
+    import torch
+    csr = P.toy_sparse(2048)
+    n, n_targ, n_max = 2048, 4, 9
+    bcsr = P.metric_like(csr)
+    gpu_lib.set_csr(*csr)
+    gpu_lib.set_csr_b(*bcsr)
+    ev_b, eig_b = P.guess(n, n_max), np.zeros(n_max)
+    assert gpu_lib.lobpcg_driver(False, True, n, n_targ, n_max, 300, 1e-8, 0.0, None, None, None, eig_b, ev_b)
+    import scipy.sparse as sp
+    b_t = torch.as_tensor(sp.csr_matrix((bcsr[2], bcsr[1], bcsr[0]), shape=(n, n)).toarray(), device="cuda:0")
+    stream = torch.cuda.ExternalStream(gpu_lib.lib().diaglib_b200_stream(), device="cuda:0")
+    calls = [0]
+
+    def bvec(nn, m, x, bx):
+        calls[0] += 1
+        with torch.cuda.stream(stream):
+            xt = torch.as_tensor(_DevView(x, nn, m), device="cuda:0")
+            torch.as_tensor(_DevView(bx, nn, m), device="cuda:0").copy_(xt @ b_t)   # B symmetric
+
+    ev, eig = P.guess(n, n_max), np.zeros(n_max)
+    assert gpu_lib.lobpcg_driver(False, True, n, n_targ, n_max, 300, 1e-8, 0.0, None, None, bvec, eig, ev)
+    assert calls[0] >= 2
+    assert np.abs(eig[:n_targ] - eig_b[:n_targ]).max() / np.abs(eig_b[:n_targ]).max() < REL
+    check_gen_solution(csr, bcsr, eig, ev, n_targ, 1e-8)
+
+
+@pytest.mark.parametrize("n,m", [(3000, 12), (20000, 37)])
+def test_b_ortho_vs_oracle(gpu_lib, oracle, n, m):
+    csr = P.toy_sparse(n)
+    bcsr = P.metric_like(csr)
+    oracle.set_csr_b(*bcsr)
+    rng = np.random.default_rng(m)
+    u, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    u = np.asfortranarray(u)
+    bu = oracle.csr_bvec(u)
+    uo, buo = u.copy(order="F"), bu.copy(order="F")
+    oracle.b_ortho(uo, buo)
+    gpu_lib.b_ortho(n, m, u, bu)
+    assert np.abs(u.T @ bu - np.eye(m)).max() < 1e-13 * m
+    assert np.abs(u - uo).max() < 1e-12 and np.abs(bu - buo).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,m,k", [(3000, 12, 12), (20000, 74, 37)])
+def test_b_ortho_vs_x_vs_oracle(gpu_lib, oracle, n, m, k):
+    csr = P.toy_sparse(n)
+    bcsr = P.metric_like(csr)
+    oracle.set_csr_b(*bcsr)
+    rng = np.random.default_rng(k)
+    x, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    x = np.asfortranarray(x)
+    bx = oracle.csr_bvec(x)
+    oracle.b_ortho(x, bx)                          # x B-orthonormal, bx = B x
+    u = np.asfortranarray(rng.standard_normal((n, k)) + 30.0 * x[:, :k])
+    uo = u.copy(order="F")
+    oracle.b_ortho_vs_x(x, bx, uo)
+    gpu_lib.b_ortho_vs_x(n, m, k, x, bx, u)
+    assert np.linalg.norm(bx.T @ u) < 1e-13 * np.sqrt(m * k)
+    assert np.linalg.norm(u.T @ u - np.eye(k)) < 1e-13 * k
+    assert np.abs(u - uo).max() < 1e-9
 
 
 class _DevView:

@@ -55,10 +55,14 @@ def _worker(rank, world, port, case, q):
             n_max = P.n_eig_rule(n_targ)
             r0, r1 = partition.row_range(n, rank, world)
             guess = P.guess(n, n_max, r0, r1)
-        DD.install_partitioned(gen, n, rank, world, dist)
+        gen_eig = case.endswith("gen_eig")
+        metric = (lambda a, b: P.metric_like(gen(a, b), r0=a)) if gen_eig else None  # noqa: E731
+        DD.install_partitioned(gen, n, rank, world, dist, metric_rows=metric)
         ev = np.asfortranarray(guess)
         eig = np.zeros(n_max)
-        if case.endswith("davidson"):
+        if gen_eig:
+            ok = D.lobpcg_driver(False, True, r1 - r0, n_targ, n_max, 300, 1e-8, 0.0, None, None, None, eig, ev)
+        elif case.endswith("davidson"):
             ok = D.davidson_driver(False, r1 - r0, n_targ, n_max, 300, 1e-8, 12, 0.0, None, None, eig, ev)
         else:
             ok = D.lobpcg_driver(False, False, r1 - r0, n_targ, n_max, 300, 1e-8, 0.0, None, None, None, eig, ev)
@@ -69,7 +73,7 @@ def _worker(rank, world, port, case, q):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("case", ["lap3d", "toy_sparse", "toy_sparse_davidson"])
+@pytest.mark.parametrize("case", ["lap3d", "toy_sparse", "toy_sparse_davidson", "toy_sparse_gen_eig"])
 def test_two_rank_parity(oracle, case):
     import torch.multiprocessing as mp
     world = 2
@@ -95,7 +99,13 @@ def test_two_rank_parity(oracle, case):
         n_max = P.n_eig_rule(n_targ)
         g = P.guess(n, n_max)
     oracle.set_csr(*csr)
-    ro = oracle.davidson(g, n_targ, 300, 1e-8, 12) if case.endswith("davidson") else oracle.lobpcg(g, n_targ, 300, 1e-8)
+    gen_eig = case.endswith("gen_eig")
+    if gen_eig:
+        bcsr = P.metric_like(csr)
+        oracle.set_csr_b(*bcsr)
+        ro = oracle.lobpcg(g, n_targ, 300, 1e-8, gen_eig=True)
+    else:
+        ro = oracle.davidson(g, n_targ, 300, 1e-8, 12) if case.endswith("davidson") else oracle.lobpcg(g, n_targ, 300, 1e-8)
     evec = np.vstack([r[6] for r in res])
     for rank, ok, its, eig, r0, r1, _ in res:
         assert ok and ro["ok"]
@@ -105,6 +115,7 @@ def test_two_rank_parity(oracle, case):
     import scipy.sparse as sp
     a = sp.csr_matrix((csr[2], csr[1], csr[0]), shape=(n, n))
     x = evec[:, :n_targ]
-    resid = a @ x - x * res[0][3][:n_targ]
+    bx = sp.csr_matrix((bcsr[2], bcsr[1], bcsr[0]), shape=(n, n)) @ x if gen_eig else x
+    resid = a @ x - bx * res[0][3][:n_targ]
     assert (np.linalg.norm(resid, axis=0) / np.sqrt(n)).max() < 2e-8
-    assert np.abs(x.T @ x - np.eye(n_targ)).max() < 1e-11
+    assert np.abs(x.T @ bx - np.eye(n_targ)).max() < (1e-10 if gen_eig else 1e-11)
