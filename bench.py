@@ -197,8 +197,15 @@ def main():
     nx = args.nx
     n = nx ** 3
     n_max = P.n_eig_rule(N_TARG)
-    r0, r1 = DD.install_partitioned(lambda a, b: P.lap3d(nx, nx, nx, a, b, delta=DELTA), n, rank, world,
-                                    dist if world > 1 else None)
+    csr_nnz = [0]
+
+    def rows(a, b):
+        out = P.lap3d(nx, nx, nx, a, b, delta=DELTA)
+        csr_nnz[0] = len(out[1])
+        return out
+
+    r0, r1 = DD.install_partitioned(rows, n, rank, world, dist if world > 1 else None)
+    csr_nnz = csr_nnz[0]
     n_loc = r1 - r0
     guess = make_guess(global_diag(nx, nx, nx), n, n_max, r0, r1)
     blk_bytes = guess.nbytes
@@ -352,6 +359,22 @@ def main():
         roof["gram"] = {"kernel": f"gram_tma_kernel sym {p}x{p}, n={n_loc}", "ms_per_launch": gr_ms,
                         "achieved_tflops": gflops / (gr_ms * 1e-3) / 1e12, "achieved_gbs": gbytes / (gr_ms * 1e-3) / 1e9,
                         "frac_tensor": gflops / (gr_ms * 1e-3) / 1e12 / f64_peak, "frac_hbm": gbytes / (gr_ms * 1e-3) / 1e9 / hbm_peak}
+        # third family: the built-in CSR block matvec at m = n_max (includes the halo exchange for N > 1)
+        import ctypes as C
+        i32 = lambda v_: C.byref(C.c_int32(int(v_)))  # noqa: E731
+        nnz_loc = int(csr_nnz)
+        for _ in range(2):
+            lib.diaglib_b200_csr_matvec(i32(n_loc), i32(q), C.c_void_p(v.ptr), C.c_void_p(y.ptr))
+        lib.diaglib_b200_sync()
+        K.timer_start()
+        for _ in range(reps):
+            lib.diaglib_b200_csr_matvec(i32(n_loc), i32(q), C.c_void_p(v.ptr), C.c_void_p(y.ptr))
+        sp_ms = K.timer_stop_ms() / reps
+        sbytes = 12.0 * nnz_loc + 8.0 * (n_loc + 1) + 16.0 * n_loc * q
+        roof["spmm"] = {"kernel": f"spmm_csr_short_kernel m={q}, n={n_loc}, nnz={nnz_loc}", "bound": "hbm", "ms_per_launch": sp_ms,
+                        "achieved_gbs": sbytes / (sp_ms * 1e-3) / 1e9, "frac_hbm": sbytes / (sp_ms * 1e-3) / 1e9 / hbm_peak,
+                        "algorithmic_bytes": sbytes,
+                        "note": "L2->SM fill path (~10 TB/s, 52 B per row and column) saturates first: profiles/ncu_spmm_r01.json"}
         for a in (v, y, cd, w, cg):
             a.free()
 
