@@ -10,6 +10,7 @@ from .api import (  # noqa: F401
     DiaglibError,
     build,
     davidson_driver,
+    gen_david_driver,
     init,
     lib,
     lib_path,

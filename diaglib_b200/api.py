@@ -176,6 +176,17 @@ def davidson_driver(verbose, n, n_targ, n_max, max_iter, tol, max_dav, shift, ma
     return bool(ok.value)
 
 
+def gen_david_driver(verbose, n, n_targ, n_max, max_iter, tol, max_dav, shift, matvec, precnd, bvec, eig, evec) -> bool:
+    """diaglib.f90:1855-1856.  bvec=None selects the built-in product with the metric installed
+    by set_csr_b."""
+    ok = C.c_int32(0)
+    lib().diaglib_b200_gen_david_driver(_i(verbose), _i(n), _i(n_targ), _i(n_max), _i(max_iter), _d(tol), _i(max_dav),
+                                        _d(shift), _callback(matvec, "matvec"), _callback(precnd, "precnd"),
+                                        _callback(bvec, "bvec"), _ptr(eig), _ptr(evec), C.byref(ok))
+    _check(lib().diaglib_b200_last_status(), "gen_david_driver")
+    return bool(ok.value)
+
+
 def ortho_cd(n, m, u):
     """diaglib.f90:3185.  Returns (growth, ok)."""
     g = C.c_double(0)

@@ -406,8 +406,9 @@ struct Engine {
   void lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, int max_iter, double tol, double shift,
               diaglib_matvec_t matvec, diaglib_precnd_t precnd, diaglib_matvec_t bvec, double* eig, double* evec,
               int32_t* ok);
-  void davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, double tol, int max_dav, double shift,
-                diaglib_matvec_t matvec, diaglib_precnd_t precnd, double* eig, double* evec, int32_t* ok);
+  void davidson(bool verbose, bool gen, int n, int n_targ, int n_max, int max_iter, double tol, int max_dav, double shift,
+                diaglib_matvec_t matvec, diaglib_precnd_t precnd, diaglib_matvec_t bvec, double* eig, double* evec,
+                int32_t* ok);
   void begin_call(int n_max) {
     status = 0;
     msg.clear();
@@ -767,11 +768,17 @@ void Engine::lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, in
 }
 
 // =======================================================================================
-// davidson_driver — diaglib.f90:1483-1853
+// davidson_driver — diaglib.f90:1483-1853; with gen = true gen_david_driver, 1855-2250, which
+// adds bspace = B*space, b_evec = B*evec and the B-orthogonalisation calls (cited at each use).
+// Deviation: the reference's restart executes `bspace = zero` (2200) right after filling
+// bspace(:,1:n_max) with B times the restart vectors (2197-2198), which makes every later
+// residual and b_ortho_vs_x wrong (the run then "converges" to wrong eigenvalues: pinned in
+// tests/test_oracle.py).  Here, as in the oracle's default, only the columns beyond n_max are
+// cleared.
 // =======================================================================================
-void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, double tol, int max_dav,
-                      double shift, diaglib_matvec_t matvec, diaglib_precnd_t precnd, double* eig, double* evec,
-                      int32_t* ok_out) {
+void Engine::davidson(bool verbose, bool gen, int n, int n_targ, int n_max, int max_iter, double tol, int max_dav,
+                      double shift, diaglib_matvec_t matvec, diaglib_precnd_t precnd, diaglib_matvec_t bvec,
+                      double* eig, double* evec, int32_t* ok_out) {
   begin_call(n_max);
   *ok_out = 0;
   const int64_t nn = n;
@@ -790,6 +797,7 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
   if (b_space.cap < big || b_r.cap < blk) release_workspace();  // regrow from scratch
   bool okm = b_space.ensure(big) && b_aspace.ensure(big) && b_r.ensure(blk);
   if (!evec_on_dev) okm = okm && b_evec.ensure(blk);
+  if (gen) okm = okm && ws_bspace.ensure(big) && ws_bspace2.ensure(blk);   // bspace, b_evec (1984-1985)
   const size_t eigw = eig_work_doubles(lda);
   const size_t red_doubles = 2 * (size_t)lda * lda + lda + eigw + 4 * n_max + 64;
   okm = okm && b_red.ensure(red_doubles * sizeof(double));
@@ -809,6 +817,8 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
   double* space = b_space.as<double>();
   double* aspace = b_aspace.as<double>();
   double* r = b_r.as<double>();
+  double* bspace = gen ? ws_bspace.as<double>() : nullptr;
+  double* bevec = gen ? ws_bspace2.as<double>() : nullptr;
   double* d_evec = evec_on_dev ? evec : b_evec.as<double>();
   double* a_red = b_red.as<double>();
   double* a_copy = a_red + (size_t)lda * lda;
@@ -820,6 +830,7 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
 
   DLB_CUDA_CHECK(cudaMemsetAsync(space, 0, big, st));                                   // 1632-1634
   DLB_CUDA_CHECK(cudaMemsetAsync(aspace, 0, big, st));
+  if (gen) DLB_CUDA_CHECK(cudaMemsetAsync(bspace, 0, big, st));                         // 2013
   DLB_CUDA_CHECK(cudaMemsetAsync(a_red, 0, (size_t)lda * lda * sizeof(double), st));
   if (!evec_on_dev) {
     PhaseHandle h = ph_open(PH_STAGE);
@@ -837,9 +848,17 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
 
   check_guess(nn, n_max, d_evec, nn);                                                   // 1644
   kcopy(nn, n_max, d_evec, nn, space, nn);                                     // 1648
+  if (gen) {                                                                            // 2033-2034
+    h = ph_open(PH_MV);
+    { int32_t m32 = n_max; bvec(&n32, &m32, space, bspace); }
+    ph_close(h);
+    h = ph_open(PH_ORTHO);
+    b_ortho(nn, n_max, space, nn, bspace, nn);
+    ph_close(h);
+  }
   int n_act = n_max, ind = 1, i_beg = 1, m_dim = 1, ldu = 0, n_rst = 0, n_frozen = 0;
   bool restart = false;
-  if (verbose && rank == 0) print_header("Davidson-Liu", tol);
+  if (verbose && rank == 0) print_header(gen ? "Generalized Davidson-Liu" : "Davidson-Liu", tol);
 
   for (int it = 1; it <= max_iter && status == 0; ++it) {
     ldu = ldu + n_act;                                                                  // 1680
@@ -866,11 +885,12 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
     h = ph_open(PH_RITZ);
     kbmul(nn, space, nn, ldu, a_copy, lda, n_max, 1.0, 0.0, d_evec, nn);        // 1717
     kbmul(nn, aspace, nn, ldu, a_copy, lda, n_max, 1.0, 0.0, r, nn);            // 1721
+    if (gen) kbmul(nn, bspace, nn, ldu, a_copy, lda, n_max, 1.0, 0.0, bevec, nn);        // 2112
     ph_close(h);
     h = ph_open(PH_RESID);
     for (int i = 0; i < n_max; ++i) h_active[i] = (i < n_targ && !done[i]) ? 1 : 0;     // 1723-1727
     DLB_CUDA_CHECK(cudaMemcpyAsync(d_active, h_active.data(), n_max * sizeof(int), cudaMemcpyHostToDevice, st));
-    residual_norms(st, num_sms, nn, n_max, r, nn, d_evec, nn, e_red, d_active, r, nn, d_norms,
+    residual_norms(st, num_sms, nn, n_max, r, nn, gen ? bevec : d_evec, nn, e_red, d_active, r, nn, d_norms,
                    resid_scratch.as<double>());                                         // 1729-1731
     ph_close(h);
     allreduce(d_norms, n_max, ncclSum);
@@ -925,13 +945,28 @@ void Engine::davidson(bool verbose, int n, int n_targ, int n_max, int max_iter, 
       }
       ph_close(h);
       h = ph_open(PH_ORTHO);
-      ortho_vs_x(nn, ldu, n_act, space, nn, COL(space, i_beg), nn);                      // 1792
+      ortho_vs_x(nn, ldu, n_act, space, nn, COL(space, i_beg), nn, bspace);              // 1792 / 2183
       ph_close(h);
+      if (gen && status == 0) {                                                          // 2184-2185
+        h = ph_open(PH_MV);
+        { int32_t m32 = n_act; bvec(&n32, &m32, COL(space, i_beg), COL(bspace, i_beg)); }
+        ph_close(h);
+        h = ph_open(PH_ORTHO);
+        b_ortho(nn, n_act, COL(space, i_beg), nn, COL(bspace, i_beg), nn);
+        ph_close(h);
+      }
     } else {                                                                             // 1795-1825
       if (verbose && rank == 0) std::printf("      Restarting davidson.\n");
       n_act = n_max;
       DLB_CUDA_CHECK(cudaMemsetAsync(space, 0, big, st));
       kcopy(nn, n_max, d_evec, nn, space, nn);
+      if (gen) {                                                                         // 2197-2200, see the note above
+        DLB_CUDA_CHECK(cudaMemsetAsync(bspace, 0, big, st));
+        kcopy(nn, n_max, bevec, nn, bspace, nn);
+        h = ph_open(PH_ORTHO);
+        b_ortho(nn, n_max, space, nn, bspace, nn);
+        ph_close(h);
+      }
       DLB_CUDA_CHECK(cudaMemsetAsync(aspace, 0, big, st));
       DLB_CUDA_CHECK(cudaMemsetAsync(a_red, 0, (size_t)lda * lda * sizeof(double), st));
       ldu = 0; i_beg = 1; m_dim = 1; n_rst = 0;
@@ -1119,7 +1154,22 @@ void diaglib_b200_davidson_driver(const int32_t* verbose, const int32_t* n, cons
     g.fail(DIAGLIB_B200_EARG, "davidson_driver: need 1 <= n_targ <= n_max");
     return;
   }
-  g.davidson(*verbose != 0, *n, *n_targ, *n_max, *max_iter, *tol, *max_dav, *shift, matvec, precnd, eig, evec, ok);
+  g.davidson(*verbose != 0, false, *n, *n_targ, *n_max, *max_iter, *tol, *max_dav, *shift, matvec, precnd, nullptr, eig, evec, ok);
+}
+
+void diaglib_b200_gen_david_driver(const int32_t* verbose, const int32_t* n, const int32_t* n_targ,
+                                   const int32_t* n_max, const int32_t* max_iter, const double* tol,
+                                   const int32_t* max_dav, const double* shift, diaglib_matvec_t matvec,
+                                   diaglib_precnd_t precnd, diaglib_matvec_t bvec, double* eig, double* evec,
+                                   int32_t* ok) {
+  *ok = 0;
+  if (!require_init()) return;
+  if (*n_targ > *n_max || *n_max < 1 || *n < 0 || !bvec) {
+    g.status = 0;
+    g.fail(DIAGLIB_B200_EARG, "gen_david_driver: need 1 <= n_targ <= n_max and a bvec callback");
+    return;
+  }
+  g.davidson(*verbose != 0, true, *n, *n_targ, *n_max, *max_iter, *tol, *max_dav, *shift, matvec, precnd, bvec, eig, evec, ok);
 }
 
 void diaglib_b200_ortho_cd(const int32_t* n, const int32_t* m, double* u, double* growth, int32_t* ok) {

@@ -25,7 +25,7 @@ module diaglib
   use iso_c_binding
   implicit none
   private
-  public :: lobpcg_driver, davidson_driver, ortho, b_ortho, ortho_cd, ortho_vs_x, b_ortho_vs_x
+  public :: lobpcg_driver, davidson_driver, gen_david_driver, ortho, b_ortho, ortho_cd, ortho_vs_x, b_ortho_vs_x
   public :: diaglib_b200_init, diaglib_b200_set_csr, diaglib_b200_set_csr_b
   public :: diaglib_b200_csr_matvec, diaglib_b200_csr_bvec, diaglib_b200_diag_precnd
 !
@@ -48,6 +48,15 @@ module diaglib
       real(c_double),     intent(inout) :: eig(*), evec(*)
       integer(c_int32_t), intent(inout) :: ok
     end subroutine c_davidson
+    subroutine c_gen_david(verbose, n, n_targ, n_max, max_iter, tol, max_dav, shift, matvec, precnd, bvec, &
+                           eig, evec, ok) bind(C, name='diaglib_b200_gen_david_driver')
+      import :: c_int32_t, c_double, c_funptr
+      integer(c_int32_t), intent(in)    :: verbose, n, n_targ, n_max, max_iter, max_dav
+      real(c_double),     intent(in)    :: tol, shift
+      type(c_funptr),     value         :: matvec, precnd, bvec
+      real(c_double),     intent(inout) :: eig(*), evec(*)
+      integer(c_int32_t), intent(inout) :: ok
+    end subroutine c_gen_david
     subroutine c_ortho_cd(n, m, u, growth, ok) bind(C, name='diaglib_b200_ortho_cd')
       import :: c_int32_t, c_double
       integer(c_int32_t), intent(in)    :: n, m
@@ -167,6 +176,22 @@ contains
     call check_stop('davidson_driver')
     ok = iok .ne. 0
   end subroutine davidson_driver
+!
+! diaglib.f90:1855-1856
+  subroutine gen_david_driver(verbose,n,n_targ,n_max,max_iter,tol,max_dav,shift,matvec,precnd,bvec,eig,evec,ok)
+    logical,  intent(in)    :: verbose
+    integer,  intent(in)    :: n, n_targ, n_max, max_iter, max_dav
+    real(8),  intent(in)    :: tol, shift
+    real(8),  intent(inout) :: eig(n_max), evec(n,n_max)
+    logical,  intent(inout) :: ok
+    external                :: matvec, precnd, bvec
+    integer(c_int32_t)      :: iok
+    iok = 0
+    call c_gen_david(merge(1,0,verbose), n, n_targ, n_max, max_iter, tol, max_dav, shift, &
+                     c_funloc(matvec), c_funloc(precnd), c_funloc(bvec), eig, evec, iok)
+    call check_stop('gen_david_driver')
+    ok = iok .ne. 0
+  end subroutine gen_david_driver
 !
 ! diaglib.f90:3185
   subroutine ortho_cd(n,m,u,growth,ok)

@@ -68,6 +68,16 @@ void diaglib_b200_davidson_driver(const int32_t* verbose, const int32_t* n, cons
                                   const int32_t* max_dav, const double* shift, diaglib_matvec_t matvec,
                                   diaglib_precnd_t precnd, double* eig, double* evec, int32_t* ok);
 
+/* replaces gen_david_driver, diaglib.f90:1855-1856 (argument list 1907-1913): Davidson-Liu for
+ * A x = lambda B x.  One deliberate deviation: after a restart the reference clears all of
+ * bspace (2200), losing B times the restart vectors, and from then on converges to wrong
+ * eigenvalues; this library keeps those columns. */
+void diaglib_b200_gen_david_driver(const int32_t* verbose, const int32_t* n, const int32_t* n_targ,
+                                   const int32_t* n_max, const int32_t* max_iter, const double* tol,
+                                   const int32_t* max_dav, const double* shift, diaglib_matvec_t matvec,
+                                   diaglib_precnd_t precnd, diaglib_matvec_t bvec, double* eig, double* evec,
+                                   int32_t* ok);
+
 /* ---- public block kernels of the reference (public list diaglib.f90:166-167) --------- */
 
 /* replaces ortho_cd, diaglib.f90:3185 : u(n,m) in/out (host or device) */

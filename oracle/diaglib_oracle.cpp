@@ -511,10 +511,20 @@ void oracle_lobpcg_driver(const int32_t* verbose_, const int32_t* gen_eig_, cons
 // ------------------------------------------------------------------------------------
 // davidson_driver — diaglib.f90:1483-1853
 // ------------------------------------------------------------------------------------
-void oracle_davidson_driver(const int32_t* verbose_, const int32_t* n_, const int32_t* n_targ_,
-                            const int32_t* n_max_, const int32_t* max_iter_, const double* tol_,
-                            const int32_t* max_dav_, const double* shift_, matvec_t matvec,
-                            precnd_t precnd, double* eig, double* evec, int32_t* ok_) {
+// gen_david_driver's restart (diaglib.f90:2197-2200) copies B*evec into bspace, B-orthonormalises,
+// and then executes `bspace = zero`, which discards B times the restart vectors: every later
+// residual r - eig*b_evec and every b_ortho_vs_x misses their contribution and the run cannot
+// converge any more.  0 (default): keep bspace(:,1:n_max), the evident intent.  1: reproduce the
+// reference statement literally (used by one test that documents the behaviour).
+static int g_gen_david_zero_bspace = 0;
+void oracle_set_gen_david_reference_restart(int on) { g_gen_david_zero_bspace = on; }
+
+// davidson_driver (1483-1853) and gen_david_driver (1855-2250) share this body; the generalized
+// one adds bspace / b_evec and the B-orthogonalisation calls (cited at each use).
+static void davidson_impl(bool gen, matvec_t bvec, const int32_t* verbose_, const int32_t* n_, const int32_t* n_targ_,
+                          const int32_t* n_max_, const int32_t* max_iter_, const double* tol_,
+                          const int32_t* max_dav_, const double* shift_, matvec_t matvec,
+                          precnd_t precnd, double* eig, double* evec, int32_t* ok_) {
   const bool verbose = *verbose_ != 0;
   const int n = *n_, n_targ = *n_targ_, n_max = *n_max_, max_iter = *max_iter_, max_dav = *max_dav_;
   const double tol = *tol_, shift = *shift_;
@@ -530,6 +540,7 @@ void oracle_davidson_driver(const int32_t* verbose_, const int32_t* n_, const in
   tau.assign(n_max, 0.0);
   const size_t nn = (size_t)n;
   std::vector<double> space(nn * lda, 0.0), aspace(nn * lda, 0.0), r(nn * n_max);
+  std::vector<double> bspace(gen ? nn * lda : 0, 0.0), b_evec(gen ? nn * n_max : 0);   // 1984-1985
   std::vector<char> done(n_max, 0);
   std::vector<double> r_norm(2 * n_max, 0.0);
   std::vector<double> a_red((size_t)lda * lda, 0.0), a_copy((size_t)lda * lda), e_red(lda);
@@ -543,10 +554,14 @@ void oracle_davidson_driver(const int32_t* verbose_, const int32_t* n_, const in
 
   check_guess(n, n_max, evec);                    // 1644
   dcopy(n * n_max, evec, space.data());           // 1648
+  if (gen) {                                      // 2033-2034
+    bvec(&n, &n_max, space.data(), bspace.data());
+    b_ortho(n, n_max, space.data(), bspace.data());
+  }
   int n_act = n_max, ind = 1, i_beg = 1, m_dim = 1, ldu = 0, n_rst = 0, n_frozen = 0;
   bool restart = false;
   if (verbose) {
-    std::printf("    Davidson-Liu iterations (tol=%10.2E):\n", tol);
+    std::printf("    %sDavidson-Liu iterations (tol=%10.2E):\n", gen ? "Generalized " : "", tol);
     std::printf("    ------------------------------------------------------------------\n");
     std::printf("        iter  root              eigenvalue         rms         max ok\n");
     std::printf("    ------------------------------------------------------------------\n");
@@ -570,9 +585,10 @@ void oracle_davidson_driver(const int32_t* verbose_, const int32_t* n_, const in
     for (int i = 0; i < n_max; ++i) eig[i] = e_red[i];                                     // 1715
     dgemm('n', 'n', n, n_max, ldu, one, space.data(), n, a_copy.data(), lda, zero, evec, n);      // 1717
     dgemm('n', 'n', n, n_max, ldu, one, aspace.data(), n, a_copy.data(), lda, zero, r.data(), n); // 1721
+    if (gen) dgemm('n', 'n', n, n_max, ldu, one, bspace.data(), n, a_copy.data(), lda, zero, b_evec.data(), n);  // 2112
     for (int i = 0; i < n_targ; ++i) {                                                     // 1723-1732
       if (done[i]) continue;
-      daxpy(n, -eig[i], &evec[nn * i], &r[nn * i]);
+      daxpy(n, -eig[i], gen ? &b_evec[nn * i] : &evec[nn * i], &r[nn * i]);                  // 1729 / 2120
       r_norm[2 * i] = dnrm2(n, &r[nn * i]) / sqrtn;
       double mx = 0.0;
       const double* ri = &r[nn * i];
@@ -609,13 +625,24 @@ void oracle_davidson_driver(const int32_t* verbose_, const int32_t* n_, const in
       double fac = -eig[ind - 1];
       precnd(&n, &n_act, &fac, &r[nn * (ind - 1)], &space[nn * (i_beg - 1)]);               // 1786
       t1 = now();
-      ortho_vs_x(n, ldu, n_act, space.data(), &space[nn * (i_beg - 1)]);                   // 1792
+      if (gen) {                                                                           // 2183-2185
+        b_ortho_vs_x(n, ldu, n_act, space.data(), bspace.data(), &space[nn * (i_beg - 1)]);
+        bvec(&n, &n_act, &space[nn * (i_beg - 1)], &bspace[nn * (i_beg - 1)]);
+        b_ortho(n, n_act, &space[nn * (i_beg - 1)], &bspace[nn * (i_beg - 1)]);
+      } else {
+        ortho_vs_x(n, ldu, n_act, space.data(), &space[nn * (i_beg - 1)]);                 // 1792
+      }
       t_ortho += now() - t1;
     } else {                                                                               // 1795-1825
       if (verbose) std::printf("      Restarting davidson.\n");
       n_act = n_max;
       std::fill(space.begin(), space.end(), 0.0);
       dcopy(n_max * n, evec, space.data());
+      if (gen) {                                                                           // 2197-2200
+        dcopy(n_max * n, b_evec.data(), bspace.data());
+        b_ortho(n, n_max, space.data(), bspace.data());
+        std::fill(bspace.begin() + (g_gen_david_zero_bspace ? 0 : nn * n_max), bspace.end(), 0.0);
+      }
       std::fill(aspace.begin(), aspace.end(), 0.0);
       std::fill(a_red.begin(), a_red.end(), 0.0);
       ldu = 0; i_beg = 1; m_dim = 1; n_rst = 0;
@@ -639,6 +666,22 @@ void oracle_davidson_driver(const int32_t* verbose_, const int32_t* n_, const in
     std::printf("    total:                         %12.4f\n", t_tot);
   }
   *ok_ = ok ? 1 : 0;
+}
+
+void oracle_davidson_driver(const int32_t* verbose_, const int32_t* n_, const int32_t* n_targ_,
+                            const int32_t* n_max_, const int32_t* max_iter_, const double* tol_,
+                            const int32_t* max_dav_, const double* shift_, matvec_t matvec,
+                            precnd_t precnd, double* eig, double* evec, int32_t* ok_) {
+  davidson_impl(false, nullptr, verbose_, n_, n_targ_, n_max_, max_iter_, tol_, max_dav_, shift_, matvec, precnd, eig,
+                evec, ok_);
+}
+// gen_david_driver, diaglib.f90:1855-1856 (argument list 1907-1913)
+void oracle_gen_david_driver(const int32_t* verbose_, const int32_t* n_, const int32_t* n_targ_,
+                             const int32_t* n_max_, const int32_t* max_iter_, const double* tol_,
+                             const int32_t* max_dav_, const double* shift_, matvec_t matvec,
+                             precnd_t precnd, matvec_t bvec, double* eig, double* evec, int32_t* ok_) {
+  davidson_impl(true, bvec, verbose_, n_, n_targ_, n_max_, max_iter_, tol_, max_dav_, shift_, matvec, precnd, eig, evec,
+                ok_);
 }
 
 // standalone block kernels (reference public list, diaglib.f90:166-167)

@@ -135,6 +135,24 @@ def davidson(evec, n_targ, max_iter, tol, max_dav, shift=0.0, matvec="oracle_csr
     return out
 
 
+def gen_david(evec, n_targ, max_iter, tol, max_dav, shift=0.0, matvec="oracle_csr_matvec",
+              precnd="oracle_diag_precnd", bvec="oracle_csr_bvec", verbose=False, reference_restart=False):
+    """gen_david_driver (diaglib.f90:1855).  reference_restart=True reproduces the reference's
+    `bspace = zero` after a restart (see diaglib_oracle.cpp)."""
+    assert evec.flags.f_contiguous and evec.dtype == np.float64
+    n, n_max = evec.shape
+    eig = np.zeros(n_max)
+    ok = C.c_int32(0)
+    lib().oracle_stats_reset()
+    lib().oracle_set_gen_david_reference_restart(1 if reference_restart else 0)
+    lib().oracle_gen_david_driver(_i(verbose), _i(n), _i(n_targ), _i(n_max), _i(max_iter), _d(tol), _i(max_dav),
+                                  _d(shift), _cb(matvec), _cb(precnd), _cb(bvec), _p(eig), _p(evec), C.byref(ok))
+    lib().oracle_set_gen_david_reference_restart(0)
+    out = _collect(n_max)
+    out.update(eig=eig, ok=bool(ok.value), hist_eig=out["eig"])
+    return out
+
+
 def ortho_cd(u):
     assert u.flags.f_contiguous
     n, m = u.shape

@@ -331,6 +331,58 @@ def test_gen_eig_user_bvec_callback(gpu_lib, oracle):
     check_gen_solution(csr, bcsr, eig, ev, n_targ, 1e-8)
 
 
+@pytest.mark.parametrize("case", ["no_restart", "restart"])
+def test_gen_david_vs_oracle(gpu_lib, oracle, case):
+    """gen_david_driver (diaglib.f90:1855-2250) against the oracle's restatement; the restart case
+    runs past dim_dav = 10 expansions (2188-2222)"""
+    if case == "no_restart":
+        csr = P.lap3d(32, 16, 16, delta=1.0)
+        n_targ, n_max, tol = 6, 11, 1e-8
+        guess = noisy_unit_guess(csr, n_max, eps=0.03)
+    else:
+        csr = P.toy_sparse(4096)
+        n_targ, n_max, tol = 10, 15, 1e-10
+        guess = None
+    n = len(csr[0]) - 1
+    bcsr = P.metric_like(csr)
+    install(gpu_lib, oracle, csr)
+    oracle.set_csr_b(*bcsr)
+    gpu_lib.set_csr_b(*bcsr)
+    ev_o = P.guess(n, n_max) if guess is None else guess.copy(order="F")
+    ev_g = ev_o.copy(order="F")
+    eig_g = np.zeros(n_max)
+    ro = oracle.gen_david(ev_o, n_targ, 100, tol, 10)
+    ok = gpu_lib.gen_david_driver(False, n, n_targ, n_max, 100, tol, 10, 0.0, None, None, None, eig_g, ev_g)
+    hg = gpu_lib.last_history(n_max)
+    assert ok and ro["ok"]
+    assert (len(hg["it"]) > 10) == (case == "restart")
+    assert_parity(ro, ok, eig_g, hg, n_targ)
+    assert np.array_equal(hg["n_act"], ro["n_act"][:len(hg["n_act"])])
+    check_gen_solution(csr, bcsr, eig_g, ev_g, n_targ, tol)
+    import scipy.linalg as sl
+    import scipy.sparse as sp
+    a = sp.csr_matrix((csr[2], csr[1], csr[0]), shape=(n, n)).toarray()
+    b = sp.csr_matrix((bcsr[2], bcsr[1], bcsr[0]), shape=(n, n)).toarray()
+    w = sl.eigh(a, b, eigvals_only=True, subset_by_index=[0, n_targ - 1])
+    assert np.abs(eig_g[:n_targ] - w).max() / np.abs(w).max() < REL
+
+
+def test_gen_david_identity_metric_matches_davidson(gpu_lib):
+    csr = P.toy_sparse(3000)
+    n, n_targ, n_max = 3000, 4, 9
+    ident = (np.arange(n + 1, dtype=np.int64), np.arange(n, dtype=np.int32), np.ones(n))
+    gpu_lib.set_csr(*csr)
+    gpu_lib.set_csr_b(*ident)
+    ev_s, ev_g = P.guess(n, n_max), P.guess(n, n_max)
+    eig_s, eig_g = np.zeros(n_max), np.zeros(n_max)
+    assert gpu_lib.davidson_driver(False, n, n_targ, n_max, 100, 1e-8, 10, 0.0, None, None, eig_s, ev_s)
+    its_s = len(gpu_lib.last_history(n_max)["it"])
+    assert gpu_lib.gen_david_driver(False, n, n_targ, n_max, 100, 1e-8, 10, 0.0, None, None, None, eig_g, ev_g)
+    its_g = len(gpu_lib.last_history(n_max)["it"])
+    assert np.abs(eig_s[:n_targ] - eig_g[:n_targ]).max() / np.abs(eig_s[:n_targ]).max() < REL
+    assert abs(its_s - its_g) <= 1
+
+
 @pytest.mark.parametrize("n,m", [(3000, 12), (20000, 37)])
 def test_b_ortho_vs_oracle(gpu_lib, oracle, n, m):
     csr = P.toy_sparse(n)

@@ -186,3 +186,29 @@ def test_oracle_b_ortho(oracle):
     assert np.abs(u.T @ bu - np.eye(m)).max() < 1e-12
     assert np.abs(bu - oracle.csr_bvec(u)).max() < 1e-12          # bu stays B u
     assert np.linalg.matrix_rank(np.hstack([span, u]), tol=1e-8) == m   # same span
+
+
+def test_oracle_gen_david_and_the_reference_restart(oracle):
+    """gen_david_driver restated (diaglib.f90:1855-2250).  With the evident intent at the restart
+    (keep B times the restart vectors) it agrees with LAPACK's generalized eigensolver; with the
+    reference's literal `bspace = zero` (2200) a run that restarts returns wrong eigenvalues while
+    reporting ok -- the reason the product keeps the intended behaviour."""
+    import scipy.linalg as sl
+    import scipy.sparse as sp
+    from diaglib_b200 import problems as P
+    n, n_targ, n_max = 600, 4, 9
+    csr = P.toy_sparse(n)
+    bcsr = P.metric_like(csr)
+    oracle.set_csr(*csr)
+    oracle.set_csr_b(*bcsr)
+    a = sp.csr_matrix((csr[2], csr[1], csr[0]), shape=(n, n)).toarray()
+    b = sp.csr_matrix((bcsr[2], bcsr[1], bcsr[0]), shape=(n, n)).toarray()
+    w = sl.eigh(a, b, eigvals_only=True, subset_by_index=[0, n_targ - 1])
+    r = oracle.gen_david(P.guess(n, n_max), n_targ, 100, 1e-8, 10)
+    assert r["ok"] and len(r["it"]) > 10                      # went through a restart
+    assert np.abs(r["eig"][:n_targ] - w).max() / np.abs(w).max() < 1e-10
+    lit = oracle.gen_david(P.guess(n, n_max), n_targ, 100, 1e-8, 10, reference_restart=True)
+    assert np.abs(lit["eig"][:n_targ] - w).max() > 1e-3       # the literal reference statement is wrong
+    # identical up to the restart
+    k = 10
+    assert np.allclose(lit["hist_eig"][:k, :n_targ], r["hist_eig"][:k, :n_targ], rtol=0, atol=1e-12)
