@@ -11,6 +11,8 @@ from .api import (  # noqa: F401
     build,
     davidson_driver,
     gen_david_driver,
+    caslr_eff_driver,
+    set_lr,
     init,
     lib,
     lib_path,

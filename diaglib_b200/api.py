@@ -15,6 +15,8 @@ _LIB = None
 
 MATVEC_T = C.CFUNCTYPE(None, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p)
 PRECND_T = C.CFUNCTYPE(None, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p, C.c_void_p)
+LRPREC_T = C.CFUNCTYPE(None, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p, C.c_void_p,
+                       C.c_void_p, C.c_void_p)
 
 STATUS = {0: "ok", 1: "reduced eigensolver failed", 2: "device allocation failed", 3: "Cholesky shift loop exhausted",
           4: "ortho_vs_x failed", 5: "no CUDA device", 6: "bad argument", 7: "NCCL failure"}
@@ -58,6 +60,8 @@ def lib():
         L.diaglib_b200_timer_stop_ms.restype = C.c_double
         L.diaglib_b200_set_csr.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.diaglib_b200_set_csr_b.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.diaglib_b200_set_csr_lr.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.diaglib_b200_set_lr_diag.argtypes = [C.c_int64, C.c_void_p, C.c_void_p]
         L.diaglib_b200_set_halo.argtypes = [C.c_int32] + [C.c_void_p] * 5
         L.diaglib_b200_k_gram.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                           C.c_void_p, C.c_int32, C.c_int32]
@@ -116,12 +120,16 @@ def _callback(cb, kind):
     wrapped."""
     L = lib()
     if cb is None or isinstance(cb, str):
-        builtin = dict(matvec=L.diaglib_b200_csr_matvec, precnd=L.diaglib_b200_diag_precnd, bvec=L.diaglib_b200_csr_bvec)
+        builtin = dict(matvec=L.diaglib_b200_csr_matvec, precnd=L.diaglib_b200_diag_precnd, bvec=L.diaglib_b200_csr_bvec,
+                       apbmul=L.diaglib_b200_csr_apbmul, ambmul=L.diaglib_b200_csr_ambmul,
+                       spdmul=L.diaglib_b200_csr_spdmul, smdmul=L.diaglib_b200_csr_smdmul, lrprec=L.diaglib_b200_lrprec)
         return C.cast(builtin[kind], C.c_void_p)
     if isinstance(cb, C._CFuncPtr):
         return C.cast(cb, C.c_void_p)
-    if kind in ("matvec", "bvec"):
+    if kind in ("matvec", "bvec", "apbmul", "ambmul", "spdmul", "smdmul"):
         f = MATVEC_T(lambda n, m, x, ax: cb(n[0], m[0], x, ax))
+    elif kind == "lrprec":
+        f = LRPREC_T(lambda n, m, fac, xp, xm, yp, ym: cb(n[0], m[0], fac[0], xp, xm, yp, ym))
     else:
         f = PRECND_T(lambda n, m, s, x, px: cb(n[0], m[0], s[0], x, px))
     _keep.append(f)
@@ -184,6 +192,33 @@ def gen_david_driver(verbose, n, n_targ, n_max, max_iter, tol, max_dav, shift, m
                                         _d(shift), _callback(matvec, "matvec"), _callback(precnd, "precnd"),
                                         _callback(bvec, "bvec"), _ptr(eig), _ptr(evec), C.byref(ok))
     _check(lib().diaglib_b200_last_status(), "gen_david_driver")
+    return bool(ok.value)
+
+
+def set_lr(apb, amb, spd, smd, aa_diag, sigma_diag, n_halo: int = 0) -> None:
+    """Install the four CSR matrices (rowptr, col, val) A+B, A-B, S+D, S-D and the diagonals of A
+    and S used by the built-in linear-response callbacks."""
+    for which, (rowptr, col, val) in enumerate((apb, amb, spd, smd)):
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        _check(lib().diaglib_b200_set_csr_lr(which, len(rowptr) - 1, int(n_halo), _ptr(rowptr), _ptr(col), _ptr(val)),
+               "set_csr_lr")
+    aa = np.ascontiguousarray(aa_diag, dtype=np.float64)
+    sg = np.ascontiguousarray(sigma_diag, dtype=np.float64)
+    _check(lib().diaglib_b200_set_lr_diag(len(aa), _ptr(aa), _ptr(sg)), "set_lr_diag")
+
+
+def caslr_eff_driver(verbose, n, n2, n_targ, n_max, max_iter, tol, max_dav, apbmul, ambmul, spdmul, smdmul, lrprec,
+                     eig, evec) -> bool:
+    """diaglib.f90:1024-1025.  evec is (2n, n_max): rows [0,n) = Y, [n,2n) = Z.  None selects the
+    built-in callbacks on the matrices installed by set_lr."""
+    ok = C.c_int32(0)
+    lib().diaglib_b200_caslr_eff_driver(_i(verbose), _i(n), _i(n2), _i(n_targ), _i(n_max), _i(max_iter), _d(tol),
+                                        _i(max_dav), _callback(apbmul, "apbmul"), _callback(ambmul, "ambmul"),
+                                        _callback(spdmul, "spdmul"), _callback(smdmul, "smdmul"),
+                                        _callback(lrprec, "lrprec"), _ptr(eig), _ptr(evec), C.byref(ok))
+    _check(lib().diaglib_b200_last_status(), "caslr_eff_driver")
     return bool(ok.value)
 
 

@@ -112,6 +112,7 @@ struct Engine {
   DevBuf ws_space, ws_aspace, ws_r, ws_xnew, ws_axnew, ws_evec, ws_red, ws_bspace, ws_bspace2;
   void release_workspace() {
     for (DevBuf* b : {&ws_space, &ws_aspace, &ws_r, &ws_xnew, &ws_axnew, &ws_evec, &ws_red, &ws_bspace, &ws_bspace2}) b->release();
+    for (DevBuf& b : ws_lr) b.release();
   }
   void* h_pin = nullptr;  // pinned staging for small read-backs
   size_t h_pin_bytes = 0;
@@ -121,6 +122,9 @@ struct Engine {
   DevBuf b_rowptr, b_col, b_val, b_diag, b_send, b_recv, b_halo;
   DevBuf bb_rowptr, bb_col, bb_val;   // metric B of the generalized problem (built-in bvec)
   CsrDevice B;
+  DevBuf lr_rowptr[4], lr_col[4], lr_val[4], lr_aa, lr_sg;   // linear-response matrices (A+B, A-B, S+D, S-D) and diagonals
+  CsrDevice LR[4];
+  DevBuf ws_lr[12];
   std::vector<int> peer;
   std::vector<int64_t> send_row0, send_cnt, recv_off, recv_cnt;
 
@@ -402,6 +406,9 @@ struct Engine {
   }
 
   void halo_exchange(int m, const double* x, int64_t ldx);
+  void caslr_eff(bool verbose, int n, int n2, int n_targ, int n_max, int max_iter, double tol, int max_dav,
+                 diaglib_matvec_t apbmul, diaglib_matvec_t ambmul, diaglib_matvec_t spdmul, diaglib_matvec_t smdmul,
+                 diaglib_lrprec_t lrprec, double* eig, double* evec, int32_t* ok);
   void check_guess(int64_t n, int m, double* evec, int64_t ld);
   void lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, int max_iter, double tol, double shift,
               diaglib_matvec_t matvec, diaglib_precnd_t precnd, diaglib_matvec_t bvec, double* eig, double* evec,
@@ -995,6 +1002,233 @@ void Engine::davidson(bool verbose, bool gen, int n, int n_targ, int n_max, int 
   *ok_out = (ok && status == 0) ? 1 : 0;
 }
 
+// =======================================================================================
+// caslr_eff_driver — diaglib.f90:1024-1481.  [A B; B A][Y;Z] = w [S D; -D -S][Y;Z] in the paired
+// spaces v+ = Y+Z, v- = Y-Z with the (A+B) / (A-B) metrics; reduced problem s^T s u+ = w^-2 u+.
+// evec is (n2 = 2n, n_max): rows [0,n) hold Y, rows [n,2n) hold Z (of the local row block).
+// =======================================================================================
+void Engine::caslr_eff(bool verbose, int n, int n2, int n_targ, int n_max, int max_iter, double tol, int max_dav,
+                       diaglib_matvec_t apbmul, diaglib_matvec_t ambmul, diaglib_matvec_t spdmul,
+                       diaglib_matvec_t smdmul, diaglib_lrprec_t lrprec, double* eig, double* evec, int32_t* ok_out) {
+  begin_call(n_max);
+  *ok_out = 0;
+  const int64_t nn = n;
+  const int min_dav = 10;
+  const int dim_dav = std::max(min_dav, max_dav);  // 1130
+  const int lda = dim_dav * n_max;                 // 1131
+  int64_t n_glob, row0;
+  global_rows(nn, n_glob, row0);
+  PhaseHandle ph_tot = ph_open(PH_TOTAL);
+  const size_t blk = (size_t)nn * n_max * sizeof(double);
+  const size_t big = (size_t)nn * lda * sizeof(double);
+  const bool evec_on_dev = is_device_ptr(evec);
+  const bool eig_on_dev = is_device_ptr(eig);
+  bool okm = true;
+  for (int i = 0; i < 6; ++i) okm = okm && ws_lr[i].ensure(big);        // vp vm lvp lvm bvp bvm (1144)
+  for (int i = 6; i < 12; ++i) okm = okm && ws_lr[i].ensure(blk);       // rp rm eigp eigm bp bm
+  if (!evec_on_dev) okm = okm && ws_evec.ensure(2 * blk);
+  const size_t eigw = eig_work_doubles(lda);
+  const size_t red_doubles = 2 * (size_t)lda * lda + 2 * lda + 2 * (size_t)lda * n_max + eigw + 8 * n_max + 64;
+  okm = okm && ws_red.ensure(red_doubles * sizeof(double));
+  if (okm) ensure_small(n_max, lda);
+  okm = okm && resid_scratch.ensure(residual_scratch_bytes(n_max, num_sms));
+  if (!okm || status) {
+    fail(DIAGLIB_B200_EALLOC, "memory allocation failed. (caslr_eff workspaces)");
+    release_workspace();
+    ph_close(ph_tot);
+    sync();
+    end_call();
+    return;
+  }
+  double *vp = ws_lr[0].as<double>(), *vm = ws_lr[1].as<double>(), *lvp = ws_lr[2].as<double>(),
+         *lvm = ws_lr[3].as<double>(), *bvp = ws_lr[4].as<double>(), *bvm = ws_lr[5].as<double>();
+  double *rp = ws_lr[6].as<double>(), *rm = ws_lr[7].as<double>(), *eigp = ws_lr[8].as<double>(),
+         *eigm = ws_lr[9].as<double>(), *bp = ws_lr[10].as<double>(), *bm = ws_lr[11].as<double>();
+  double* d_evec = evec_on_dev ? evec : ws_evec.as<double>();
+  double* smat = ws_red.as<double>();                    // compact: leading dimension = current ldu
+  double* s_copy = smat + (size_t)lda * lda;
+  double* e_red = s_copy + (size_t)lda * lda;            // 2*lda
+  double* up = e_red + 2 * lda;                          // lda x n_max, ld = lda
+  double* um = up + (size_t)lda * n_max;
+  double* eig_work = um + (size_t)lda * n_max;
+  double* d_eigv = eig_work + eigw;                      // n_max: sqrt of the reduced eigenvalues = 1/w
+  double* d_norms_p = d_eigv + n_max;                    // 2*n_max
+  double* d_norms_m = d_norms_p + 2 * n_max;             // 2*n_max
+  int* d_active = reinterpret_cast<int*>(d_norms_m + 2 * n_max);
+  EigStatus* d_eigst = reinterpret_cast<EigStatus*>(d_norms_m + 3 * n_max + 8);
+
+  for (double* b : {vp, vm, lvp, lvm, bvp, bvm}) DLB_CUDA_CHECK(cudaMemsetAsync(b, 0, big, st));   // 1177-1182
+  if (!evec_on_dev) {
+    PhaseHandle h = ph_open(PH_STAGE);
+    DLB_CUDA_CHECK(cudaMemcpyAsync(d_evec, evec, 2 * blk, cudaMemcpyHostToDevice, st));
+    ph_close(h);
+  }
+  std::vector<double> h_eig(n_max), h_np(2 * n_max), h_nm(2 * n_max), r_norm(2 * n_max, 0.0), h_w(n_max);
+  std::vector<int> done(n_max, 0), h_active(n_max, 0);
+  const int32_t n32 = n;
+  const double sqrtn = std::sqrt((double)n_glob), sqrt2 = std::sqrt(2.0);
+  const double tol_rms = tol, tol_max = 10.0 * tol;
+  bool ok = false;
+  PhaseHandle h;
+  auto COL = [&](double* base, int col1) { return base + (size_t)nn * (col1 - 1); };
+  auto start_space = [&]() {   // 1190-1249 and the restart 1424-1437
+    lr_split(st, nn, n_max, d_evec, n2, vp, vm, nn);
+    int32_t m32 = n_max;
+    h = ph_open(PH_MV);
+    apbmul(&n32, &m32, vp, lvp);
+    ph_close(h);
+    h = ph_open(PH_ORTHO);
+    b_ortho(nn, n_max, vp, nn, lvp, nn);
+    ph_close(h);
+    h = ph_open(PH_MV);
+    ambmul(&n32, &m32, vm, lvm);
+    ph_close(h);
+    h = ph_open(PH_ORTHO);
+    b_ortho(nn, n_max, vm, nn, lvm, nn);
+    ph_close(h);
+  };
+  start_space();
+  int n_act = n_max, ind = 1, i_beg = 1, m_dim = 1, ldu = 0, n_frozen = 0;
+  if (verbose && rank == 0) print_header("Davidson-Liu", tol);
+
+  for (int it = 1; it <= max_iter && status == 0; ++it) {
+    ldu = ldu + n_act;                                                                  // 1279
+    h = ph_open(PH_MV);
+    { int32_t m32 = n_act; spdmul(&n32, &m32, COL(vp, i_beg), COL(bvm, i_beg)); }         // 1284
+    { int32_t m32 = n_act; smdmul(&n32, &m32, COL(vm, i_beg), COL(bvp, i_beg)); }         // 1285
+    ph_close(h);
+    h = ph_open(PH_GRAM);
+    kgram(nn, vm, nn, ldu, bvm, nn, ldu, smat, ldu, false);                              // 1293
+    allreduce(smat, (size_t)ldu * ldu);
+    ph_close(h);
+    h = ph_open(PH_DIAG);
+    small_ata(st, ldu, smat, ldu, s_copy, ldu);                                          // 1303
+    sym_eig(st, ldu, s_copy, ldu, true, e_red, eig_work, d_eigst);                       // 1308
+    lr_reduced_vectors(st, ldu, n_max, s_copy, ldu, e_red, smat, ldu, up, lda, um, lda, d_eigv);  // 1314-1324
+    ph_close(h);
+    h = ph_open(PH_RITZ);
+    kbmul(nn, vp, nn, ldu, up, lda, n_max, 1.0, 0.0, eigp, nn);                          // 1330
+    kbmul(nn, vm, nn, ldu, um, lda, n_max, 1.0, 0.0, eigm, nn);                          // 1331
+    lr_merge(st, nn, n_max, eigp, eigm, nn, d_evec, n2);                                 // 1333-1336
+    kbmul(nn, bvp, nn, ldu, um, lda, n_max, 1.0, 0.0, rp, nn);                           // 1340
+    kbmul(nn, bvm, nn, ldu, up, lda, n_max, 1.0, 0.0, rm, nn);                           // 1341
+    kbmul(nn, lvp, nn, ldu, up, lda, n_max, 1.0, 0.0, bp, nn);                           // 1342
+    kbmul(nn, lvm, nn, ldu, um, lda, n_max, 1.0, 0.0, bm, nn);                           // 1343
+    ph_close(h);
+    h = ph_open(PH_RESID);
+    for (int i = 0; i < n_max; ++i) h_active[i] = (i < n_targ && !done[i]) ? 1 : 0;      // 1345-1346
+    DLB_CUDA_CHECK(cudaMemcpyAsync(d_active, h_active.data(), n_max * sizeof(int), cudaMemcpyHostToDevice, st));
+    residual_norms(st, num_sms, nn, n_max, rp, nn, bp, nn, d_eigv, d_active, rp, nn, d_norms_p,
+                   resid_scratch.as<double>());                                          // 1347, 1349-1350
+    residual_norms(st, num_sms, nn, n_max, rm, nn, bm, nn, d_eigv, d_active, rm, nn, d_norms_m,
+                   resid_scratch.as<double>());                                          // 1348
+    ph_close(h);
+    allreduce(d_norms_p, n_max, ncclSum);
+    allreduce(d_norms_p + n_max, n_max, ncclMax);
+    allreduce(d_norms_m, n_max, ncclSum);
+    allreduce(d_norms_m + n_max, n_max, ncclMax);
+    {
+      DLB_CUDA_CHECK(cudaMemcpyAsync(h_np.data(), d_norms_p, 2 * n_max * sizeof(double), cudaMemcpyDeviceToHost, st));
+      DLB_CUDA_CHECK(cudaMemcpyAsync(h_nm.data(), d_norms_m, 2 * n_max * sizeof(double), cudaMemcpyDeviceToHost, st));
+      EigStatus es;
+      DLB_CUDA_CHECK(cudaMemcpyAsync(&es, d_eigst, sizeof es, cudaMemcpyDeviceToHost, st));
+      read_back(h_eig.data(), d_eigv, n_max * sizeof(double));
+      if (!es.converged) {
+        fail(DIAGLIB_B200_EDSYEV, "dsyev failed. info = %6d", es.sweeps);
+        break;
+      }
+    }
+    for (int i = 0; i < n_targ; ++i) {                                                   // 1349-1350
+      if (done[i]) continue;
+      r_norm[2 * i] = (std::sqrt(h_np[i]) + std::sqrt(h_nm[i])) / (h_eig[i] * sqrt2 * sqrtn);
+      r_norm[2 * i + 1] = (h_np[n_max + i] + h_nm[n_max + i]) / (sqrt2 * h_eig[i]);
+    }
+    for (int i = 0; i < n_targ; ++i) {                                                   // 1356-1365
+      if (done[i]) continue;
+      done[i] = (r_norm[2 * i] < tol_rms && r_norm[2 * i + 1] < tol_max && it > 1) ? 1 : 0;
+      if (!done[i]) {
+        for (int j = i + 1; j < n_max; ++j) done[j] = 0;
+        break;
+      }
+    }
+    for (int i = 0; i < n_max; ++i) h_w[i] = 1.0 / h_eig[i];
+    record(it, n_act, n_max, h_w.data(), r_norm.data(), done.data());
+    if (verbose && rank == 0) {                                                          // 1369-1374
+      for (int i = 0; i < n_targ; ++i)
+        std::printf("        %4d  %4d%24.12f%12.4E%12.4E%3s\n", it, i + 1, h_w[i], r_norm[2 * i], r_norm[2 * i + 1],
+                    done[i] ? "T" : "F");
+      std::printf("\n");
+    }
+    bool all_done = true;
+    for (int i = 0; i < n_targ; ++i) all_done = all_done && done[i];
+    if (all_done) {                                                                      // 1376-1382
+      ok = true;
+      for (int i = 0; i < n_targ; ++i) h_eig[i] = 1.0 / h_eig[i];
+      break;
+    }
+    if (m_dim < dim_dav) {                                                               // 1387
+      m_dim = m_dim + 1;
+      i_beg = i_beg + n_act;
+      n_act = n_max;
+      n_frozen = 0;
+      for (int i = 0; i < n_targ; ++i) {
+        if (done[i]) { n_act--; n_frozen++; } else break;
+      }
+      ind = n_max - n_act + 1;
+      h = ph_open(PH_RESID);
+      {
+        int32_t m32 = n_act;
+        double fac = h_eig[ind - 1];
+        lrprec(&n32, &m32, &fac, COL(rp, ind), COL(rm, ind), COL(vp, i_beg), COL(vm, i_beg));   // 1408
+      }
+      ph_close(h);
+      int32_t m32 = n_act;
+      h = ph_open(PH_ORTHO);
+      ortho_vs_x(nn, ldu, n_act, vp, nn, COL(vp, i_beg), nn, lvp);                       // 1413
+      ph_close(h);
+      if (status) break;
+      h = ph_open(PH_MV);
+      apbmul(&n32, &m32, COL(vp, i_beg), COL(lvp, i_beg));                               // 1414
+      ph_close(h);
+      h = ph_open(PH_ORTHO);
+      b_ortho(nn, n_act, COL(vp, i_beg), nn, COL(lvp, i_beg), nn);                       // 1415
+      ortho_vs_x(nn, ldu, n_act, vm, nn, COL(vm, i_beg), nn, lvm);                       // 1416
+      ph_close(h);
+      if (status) break;
+      h = ph_open(PH_MV);
+      ambmul(&n32, &m32, COL(vm, i_beg), COL(lvm, i_beg));                               // 1417
+      ph_close(h);
+      h = ph_open(PH_ORTHO);
+      b_ortho(nn, n_act, COL(vm, i_beg), nn, COL(lvm, i_beg), nn);                       // 1418
+      ph_close(h);
+    } else {                                                                             // 1422-1457
+      if (verbose && rank == 0) std::printf("      Restarting davidson.\n");
+      ldu = 0; i_beg = 1; m_dim = 1;
+      n_act = n_max;
+      for (double* b : {vp, vm, lvp, lvm, bvp, bvm}) DLB_CUDA_CHECK(cudaMemsetAsync(b, 0, big, st));
+      start_space();
+    }
+    if (verbose && rank == 0) {
+      std::printf("    ----------------------------------------\n");
+      std::printf("      # target vectors:    %4d\n      # new vectors added: %4d\n      # converged vectors: %4d\n",
+                  n_targ, n_act, n_frozen);
+      std::printf("    ----------------------------------------\n");
+    }
+  }
+  if (eig_on_dev) DLB_CUDA_CHECK(cudaMemcpyAsync(eig, h_eig.data(), n_max * sizeof(double), cudaMemcpyHostToDevice, st));
+  else std::memcpy(eig, h_eig.data(), n_max * sizeof(double));
+  if (!evec_on_dev) {
+    h = ph_open(PH_STAGE);
+    DLB_CUDA_CHECK(cudaMemcpyAsync(evec, d_evec, 2 * blk, cudaMemcpyDeviceToHost, st));
+    ph_close(h);
+  }
+  ph_close(ph_tot);
+  sync();
+  if (verbose && rank == 0) print_timings("caslr_eff", t_acc);
+  end_call();
+  *ok_out = (ok && status == 0) ? 1 : 0;
+}
+
 // ---- halo exchange for the built-in CSR matvec ------------------------------------------
 void Engine::halo_exchange(int m, const double* x, int64_t ldx) {
   if (nranks == 1 || A.n_halo == 0 || peer.empty()) return;
@@ -1109,8 +1343,9 @@ void diaglib_b200_finalize(void) {
   g.rank = 0;
   g.release_workspace();
   for (DevBuf* b : {&g.partial, &g.smallws, &g.resid_scratch, &g.scal, &g.b_rowptr, &g.b_col, &g.b_val, &g.b_diag,
-                    &g.b_send, &g.b_recv, &g.b_halo, &g.bb_rowptr, &g.bb_col, &g.bb_val})
+                    &g.b_send, &g.b_recv, &g.b_halo, &g.bb_rowptr, &g.bb_col, &g.bb_val, &g.lr_aa, &g.lr_sg})
     b->release();
+  for (int i = 0; i < 4; ++i) { g.lr_rowptr[i].release(); g.lr_col[i].release(); g.lr_val[i].release(); g.LR[i] = CsrDevice(); }
   g.A = CsrDevice();
   g.B = CsrDevice();
   g.inited = false;
@@ -1170,6 +1405,83 @@ void diaglib_b200_gen_david_driver(const int32_t* verbose, const int32_t* n, con
     return;
   }
   g.davidson(*verbose != 0, true, *n, *n_targ, *n_max, *max_iter, *tol, *max_dav, *shift, matvec, precnd, bvec, eig, evec, ok);
+}
+
+void diaglib_b200_caslr_eff_driver(const int32_t* verbose, const int32_t* n, const int32_t* n2, const int32_t* n_targ,
+                                   const int32_t* n_max, const int32_t* max_iter, const double* tol,
+                                   const int32_t* max_dav, diaglib_matvec_t apbmul, diaglib_matvec_t ambmul,
+                                   diaglib_matvec_t spdmul, diaglib_matvec_t smdmul, diaglib_lrprec_t lrprec,
+                                   double* eig, double* evec, int32_t* ok) {
+  *ok = 0;
+  if (!require_init()) return;
+  if (*n_targ > *n_max || *n_max < 1 || *n < 0 || *n2 != 2 * *n || !apbmul || !ambmul || !spdmul || !smdmul || !lrprec) {
+    g.status = 0;
+    g.fail(DIAGLIB_B200_EARG, "caslr_eff_driver: need 1 <= n_targ <= n_max, n2 = 2 n and all five callbacks");
+    return;
+  }
+  g.caslr_eff(*verbose != 0, *n, *n2, *n_targ, *n_max, *max_iter, *tol, *max_dav, apbmul, ambmul, spdmul, smdmul, lrprec,
+              eig, evec, ok);
+}
+
+static void lr_matvec(int which, const int32_t* n, const int32_t* m, const double* x, double* y) {
+  if (!g.inited || g.LR[which].n != *n) {
+    g.fail(DIAGLIB_B200_EARG, "linear-response product %d: no matrix installed for n = %d (diaglib_b200_set_csr_lr)", which, *n);
+    return;
+  }
+  if (g.LR[which].n_halo > 0) g.halo_exchange(*m, x, *n);   // same halo plan and numbering as set_csr's matrix
+  spmm_csr(g.st, g.LR[which], *m, x, *n, g.b_halo.as<double>(), y, *n, 0.0);
+}
+void diaglib_b200_csr_apbmul(const int32_t* n, const int32_t* m, const double* x, double* y) { lr_matvec(0, n, m, x, y); }
+void diaglib_b200_csr_ambmul(const int32_t* n, const int32_t* m, const double* x, double* y) { lr_matvec(1, n, m, x, y); }
+void diaglib_b200_csr_spdmul(const int32_t* n, const int32_t* m, const double* x, double* y) { lr_matvec(2, n, m, x, y); }
+void diaglib_b200_csr_smdmul(const int32_t* n, const int32_t* m, const double* x, double* y) { lr_matvec(3, n, m, x, y); }
+void diaglib_b200_lrprec(const int32_t* n, const int32_t* m, const double* fac, const double* xp, const double* xm,
+                         double* yp, double* ym) {
+  if (!g.inited || !g.lr_aa.p || g.lr_aa.cap < (size_t)*n * sizeof(double)) {
+    g.fail(DIAGLIB_B200_EARG, "lrprec: no diagonals installed for n = %d (diaglib_b200_set_lr_diag)", *n);
+    return;
+  }
+  lr_precnd(g.st, *n, *m, *fac, g.lr_aa.as<double>(), g.lr_sg.as<double>(), xp, xm, yp, ym);
+}
+
+int32_t diaglib_b200_set_csr_lr(int32_t which, int64_t n_loc, int64_t n_halo, const int64_t* rowptr, const int32_t* col,
+                                const double* val) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  if (which < 0 || which > 3 || (n_halo > 0 && (g.A.n != n_loc || g.A.n_halo != n_halo))) {
+    g.status = 0;
+    g.fail(DIAGLIB_B200_EARG, "set_csr_lr: which must be 0..3; a matrix with halo columns must share set_csr's halo");
+    return DIAGLIB_B200_EARG;
+  }
+  const int64_t nnz = rowptr[n_loc];
+  if (!g.lr_rowptr[which].ensure((n_loc + 1) * sizeof(int64_t)) ||
+      !g.lr_col[which].ensure(std::max<int64_t>(nnz, 1) * sizeof(int32_t)) ||
+      !g.lr_val[which].ensure(std::max<int64_t>(nnz, 1) * sizeof(double)))
+    return DIAGLIB_B200_EALLOC;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.lr_rowptr[which].p, rowptr, (n_loc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.lr_col[which].p, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.lr_val[which].p, val, nnz * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
+  CsrDevice& M = g.LR[which];
+  M = CsrDevice();
+  M.n = n_loc;
+  M.nnz = nnz;
+  M.n_halo = n_halo;
+  int64_t longest = 0;
+  for (int64_t i = 0; i < n_loc; ++i) longest = std::max(longest, rowptr[i + 1] - rowptr[i]);
+  M.max_row_nnz = (int)std::min<int64_t>(longest, INT32_MAX);
+  M.rowptr = g.lr_rowptr[which].as<int64_t>();
+  M.col = g.lr_col[which].as<int32_t>();
+  M.val = g.lr_val[which].as<double>();
+  return DIAGLIB_B200_OK;
+}
+int32_t diaglib_b200_set_lr_diag(int64_t n_loc, const double* aa_diag, const double* sigma_diag) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  if (!g.lr_aa.ensure(std::max<int64_t>(n_loc, 1) * sizeof(double)) || !g.lr_sg.ensure(std::max<int64_t>(n_loc, 1) * sizeof(double)))
+    return DIAGLIB_B200_EALLOC;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.lr_aa.p, aa_diag, n_loc * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.lr_sg.p, sigma_diag, n_loc * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
+  return DIAGLIB_B200_OK;
 }
 
 void diaglib_b200_ortho_cd(const int32_t* n, const int32_t* m, double* u, double* growth, int32_t* ok) {

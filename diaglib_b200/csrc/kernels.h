@@ -76,6 +76,12 @@ void block_copy(cudaStream_t st, int64_t n, int m, const double* x, int64_t ldx,
 // gathers rows [row0,row0+cnt) of an n x m block into a dense cnt x m buffer (halo packing)
 void pack_rows(cudaStream_t st, int64_t row0, int64_t cnt, int m, const double* x, int64_t ldx, double* out);
 
+// linear-response helpers (caslr_eff_driver 1190-1193, 1333-1336; lrprec_2 of main.f90:257-281)
+void lr_split(cudaStream_t st, int64_t n, int m, const double* evec, int64_t ld2, double* vp, double* vm, int64_t ldv);
+void lr_merge(cudaStream_t st, int64_t n, int m, const double* ep, const double* em, int64_t lde, double* evec, int64_t ld2);
+void lr_precnd(cudaStream_t st, int64_t n, int m, double fac, const double* aa, const double* sg, const double* xp,
+               const double* xm, double* yp, double* ym);
+
 // ---- small.cu (single-CTA dense kernels, replicated per rank) --------------------------
 struct CholStatus {      // written by chol_inv, read back by the host control loop
   double l_norm, linv_norm, shift_used, unorm;
@@ -103,5 +109,11 @@ struct CoeffStatus { int sweeps; int cd_passes; int fail; int qr; };
 size_t coeffs_work_doubles(int len_u, int n_max, int n_act);
 void get_coeffs(cudaStream_t st, int len_a, int len_u, int n_max, int n_act, const double* a_red, double* u_p,
                 double* work, CoeffStatus* status_dev);
+
+// reduced problem of caslr_eff_driver: c = a^T a (1303); eig(i) = sqrt(e(k-1-i)), up(:,i) = z(:,k-1-i),
+// um(:,i) = sred up(:,i) / eig(i) (1314-1324)
+void small_ata(cudaStream_t st, int k, const double* a, int lda, double* c, int ldc);
+void lr_reduced_vectors(cudaStream_t st, int k, int n_max, const double* z, int ldz, const double* e, const double* sred,
+                        int lds, double* up, int ldup, double* um, int ldum, double* eig);
 
 }  // namespace dlb

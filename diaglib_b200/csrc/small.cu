@@ -725,4 +725,47 @@ void get_coeffs(cudaStream_t st, int len_a, int len_u, int n_max, int n_act, con
   DLB_CUDA_CHECK(cudaGetLastError());
 }
 
+
+// ---- reduced problem of caslr_eff_driver (diaglib.f90:1293-1324) ---------------------------
+namespace {
+// c(i,j) = sum_k a(k,i) a(k,j), i,j < k_  (dgemm('t','n') 1303); one thread per element
+__global__ void small_ata_kernel(int k_, const double* __restrict__ a, int lda, double* __restrict__ c, int ldc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= k_ || j >= k_) return;
+  double s = 0.0;
+  for (int k = 0; k < k_; ++k) s = fma(a[k + (size_t)i * lda], a[k + (size_t)j * lda], s);
+  c[i + (size_t)j * ldc] = s;
+}
+// eig(i) = sqrt(e(k-1-i)), up(:,i) = z(:,k-1-i)  (1314-1317)
+__global__ void lr_pick_kernel(int k_, int n_max, const double* __restrict__ z, int ldz, const double* __restrict__ e,
+                               double* __restrict__ up, int ldup, double* __restrict__ eig) {
+  const int i = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_max) return;
+  if (r == 0) eig[i] = sqrt(e[k_ - 1 - i]);
+  if (r < k_) up[r + (size_t)i * ldup] = z[r + (size_t)(k_ - 1 - i) * ldz];
+}
+// um(:,i) = (s_red * up(:,i)) / eig(i)  (1321-1324)
+__global__ void lr_um_kernel(int k_, int n_max, const double* __restrict__ sred, int lds, const double* __restrict__ up,
+                             int ldup, const double* __restrict__ e, double* __restrict__ um, int ldum) {
+  const int i = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_max || r >= k_) return;
+  double s = 0.0;
+  for (int k = 0; k < k_; ++k) s = fma(sred[r + (size_t)k * lds], up[k + (size_t)i * ldup], s);
+  um[r + (size_t)i * ldum] = s / sqrt(e[k_ - 1 - i]);
+}
+}  // namespace
+
+void small_ata(cudaStream_t st, int k, const double* a, int lda, double* c, int ldc) {
+  if (k <= 0) return;
+  small_ata_kernel<<<dim3((k + 127) / 128, k), 128, 0, st>>>(k, a, lda, c, ldc);
+  ++g_launches;
+}
+void lr_reduced_vectors(cudaStream_t st, int k, int n_max, const double* z, int ldz, const double* e, const double* sred,
+                        int lds, double* up, int ldup, double* um, int ldum, double* eig) {
+  if (k <= 0) return;
+  lr_pick_kernel<<<dim3((k + 127) / 128, n_max), 128, 0, st>>>(k, n_max, z, ldz, e, up, ldup, eig);
+  lr_um_kernel<<<dim3((k + 127) / 128, n_max), 128, 0, st>>>(k, n_max, sred, lds, up, ldup, e, um, ldum);
+  g_launches += 2;
+}
+
 }  // namespace dlb

@@ -221,7 +221,68 @@ axpy_kernel(int64_t n, int m, double a, const double* __restrict__ x, int64_t ld
   for (int j = 0; j < m; ++j) y[row + (int64_t)j * ldy] = fma(a, x[row + (int64_t)j * ldx], y[row + (int64_t)j * ldy]);
 }
 
+// linear-response helpers (caslr_eff_driver): split evec = [Y; Z] into Y+Z / Y-Z, merge back,
+// and the diagonal preconditioner of main.f90:257-281
+__global__ void __launch_bounds__(256)
+lr_split_kernel(int64_t n, int m, const double* __restrict__ evec, int64_t ld2, double* __restrict__ vp,
+                double* __restrict__ vm, int64_t ldv) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  for (int j = 0; j < m; ++j) {
+    const double y = evec[row + (int64_t)j * ld2], z = evec[n + row + (int64_t)j * ld2];
+    vp[row + (int64_t)j * ldv] = y + z;
+    vm[row + (int64_t)j * ldv] = y - z;
+  }
+}
+__global__ void __launch_bounds__(256)
+lr_merge_kernel(int64_t n, int m, const double* __restrict__ ep, const double* __restrict__ em, int64_t lde,
+                double* __restrict__ evec, int64_t ld2) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  for (int j = 0; j < m; ++j) {
+    const double a = ep[row + (int64_t)j * lde], b = em[row + (int64_t)j * lde];
+    evec[row + (int64_t)j * ld2] = a + b;
+    evec[n + row + (int64_t)j * ld2] = a - b;
+  }
+}
+__global__ void __launch_bounds__(256)
+lr_precnd_kernel(int64_t n, int m, double fac, const double* __restrict__ aa, const double* __restrict__ sg,
+                 const double* __restrict__ xp, const double* __restrict__ xm, double* __restrict__ yp,
+                 double* __restrict__ ym) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const double a = aa[row], s = sg[row];
+  double denom = fac * fac * a * a - s * s;
+  denom = 1.0 / denom;
+  for (int j = 0; j < m; ++j) {
+    const int64_t o = row + (int64_t)j * n;
+    const double p = xp[o], q = xm[o];
+    yp[o] = denom * (fac * a * p + s * q);
+    ym[o] = denom * (fac * a * q + s * p);
+  }
+}
+
 }  // namespace
+
+void lr_split(cudaStream_t st, int64_t n, int m, const double* evec, int64_t ld2, double* vp, double* vm, int64_t ldv) {
+  if (n <= 0 || m <= 0) return;
+  lr_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, m, evec, ld2, vp, vm, ldv);
+  ++g_launches;
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+void lr_merge(cudaStream_t st, int64_t n, int m, const double* ep, const double* em, int64_t lde, double* evec, int64_t ld2) {
+  if (n <= 0 || m <= 0) return;
+  lr_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, m, ep, em, lde, evec, ld2);
+  ++g_launches;
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+void lr_precnd(cudaStream_t st, int64_t n, int m, double fac, const double* aa, const double* sg, const double* xp,
+               const double* xm, double* yp, double* ym) {
+  if (n <= 0 || m <= 0) return;
+  lr_precnd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, m, fac, aa, sg, xp, xm, yp, ym);
+  ++g_launches;
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
 
 void spmm_csr(cudaStream_t st, const CsrDevice& A, int m, const double* x, int64_t ldx, const double* x_halo,
               double* ax, int64_t ldax, double shift) {

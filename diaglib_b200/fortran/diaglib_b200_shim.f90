@@ -25,7 +25,7 @@ module diaglib
   use iso_c_binding
   implicit none
   private
-  public :: lobpcg_driver, davidson_driver, gen_david_driver, ortho, b_ortho, ortho_cd, ortho_vs_x, b_ortho_vs_x
+  public :: lobpcg_driver, davidson_driver, gen_david_driver, caslr_eff_driver, ortho, b_ortho, ortho_cd, ortho_vs_x, b_ortho_vs_x
   public :: diaglib_b200_init, diaglib_b200_set_csr, diaglib_b200_set_csr_b
   public :: diaglib_b200_csr_matvec, diaglib_b200_csr_bvec, diaglib_b200_diag_precnd
 !
@@ -57,6 +57,15 @@ module diaglib
       real(c_double),     intent(inout) :: eig(*), evec(*)
       integer(c_int32_t), intent(inout) :: ok
     end subroutine c_gen_david
+    subroutine c_caslr_eff(verbose, n, n2, n_targ, n_max, max_iter, tol, max_dav, apbmul, ambmul, spdmul, smdmul, &
+                           lrprec, eig, evec, ok) bind(C, name='diaglib_b200_caslr_eff_driver')
+      import :: c_int32_t, c_double, c_funptr
+      integer(c_int32_t), intent(in)    :: verbose, n, n2, n_targ, n_max, max_iter, max_dav
+      real(c_double),     intent(in)    :: tol
+      type(c_funptr),     value         :: apbmul, ambmul, spdmul, smdmul, lrprec
+      real(c_double),     intent(inout) :: eig(*), evec(*)
+      integer(c_int32_t), intent(inout) :: ok
+    end subroutine c_caslr_eff
     subroutine c_ortho_cd(n, m, u, growth, ok) bind(C, name='diaglib_b200_ortho_cd')
       import :: c_int32_t, c_double
       integer(c_int32_t), intent(in)    :: n, m
@@ -192,6 +201,22 @@ contains
     call check_stop('gen_david_driver')
     ok = iok .ne. 0
   end subroutine gen_david_driver
+!
+! diaglib.f90:1024-1025
+  subroutine caslr_eff_driver(verbose,n,n2,n_targ,n_max,max_iter,tol,max_dav,apbmul,ambmul,spdmul,smdmul,lrprec,eig,evec,ok)
+    logical,  intent(in)    :: verbose
+    integer,  intent(in)    :: n, n2, n_targ, n_max, max_iter, max_dav
+    real(8),  intent(in)    :: tol
+    real(8),  intent(inout) :: eig(n_max), evec(n2,n_max)
+    logical,  intent(inout) :: ok
+    external                :: apbmul, ambmul, spdmul, smdmul, lrprec
+    integer(c_int32_t)      :: iok
+    iok = 0
+    call c_caslr_eff(merge(1,0,verbose), n, n2, n_targ, n_max, max_iter, tol, max_dav, c_funloc(apbmul), &
+                     c_funloc(ambmul), c_funloc(spdmul), c_funloc(smdmul), c_funloc(lrprec), eig, evec, iok)
+    call check_stop('caslr_eff_driver')
+    ok = iok .ne. 0
+  end subroutine caslr_eff_driver
 !
 ! diaglib.f90:3185
   subroutine ortho_cd(n,m,u,growth,ok)

@@ -207,3 +207,30 @@ def metric_like(csr, eps: float = 0.02, seed: int = 7, r0: int = 0):
     dg = rows == c
     val[dg] = 1.0 + 0.3 * u[dg]
     return rowptr.copy(), col.copy(), val
+
+
+def caslr_like(n: int, r0: int = 0, r1: int | None = None, seed: int = 11):
+    """Linear-response test problem in the spirit of main.f90:528-600 on the toy_sparse pattern
+    (|i-j| in {1,2,4,...}): apb = A+B (diag 5+i, off-diag 1/(i+j)), amb = A-B (diag 2+i, off-diag
+    0.2/(i+j)), sigma SPD (diag 1+u, small symmetric off-diagonals), delta antisymmetric (small).
+    Returns dict(apb, amb, spd, smd = (rowptr, col_global, val) for rows [r0, r1), aa_diag,
+    sigma_diag)."""
+    rowptr, col, val, _ = toy_sparse(n, r0, r1)
+    r1 = n if r1 is None else r1
+    rows = r0 + np.repeat(np.arange(r1 - r0, dtype=np.int64), np.diff(rowptr))
+    c = col.astype(np.int64)
+    dg = rows == c
+    i1, j1 = rows + 1, c + 1
+    apb = np.where(dg, 5.0 + i1, 1.0 / (i1 + j1))
+    amb = np.where(dg, 2.0 + i1, 0.2 / (i1 + j1))
+    lo, hi = np.minimum(rows, c), np.maximum(rows, c)
+    h = splitmix64((lo * np.int64(2654435761) + hi + np.int64(seed) * np.int64(1000003)).astype(np.uint64))
+    u = (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    h2 = splitmix64(h)
+    u2 = (h2 >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    maxlen = max(1, int(np.diff(rowptr).max()))
+    sigma = np.where(dg, 1.0 + u, 0.2 * (u - 0.5) / maxlen)
+    delta = np.where(dg, 0.0, np.sign(c - rows) * 0.2 * u2 / maxlen)       # delta(j,i) = -delta(i,j)
+    mk = lambda v_: (rowptr.copy(), col.copy(), np.ascontiguousarray(v_, dtype=np.float64))  # noqa: E731
+    return dict(apb=mk(apb), amb=mk(amb), spd=mk(sigma + delta), smd=mk(sigma - delta),
+                aa_diag=0.5 * (apb[dg] + amb[dg]), sigma_diag=sigma[dg])

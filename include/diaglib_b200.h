@@ -78,6 +78,19 @@ void diaglib_b200_gen_david_driver(const int32_t* verbose, const int32_t* n, con
                                    diaglib_precnd_t precnd, diaglib_matvec_t bvec, double* eig, double* evec,
                                    int32_t* ok);
 
+/* lrprec(n, m, fac, xp, xm, yp, ym): preconditioner of the linear-response solver (contract of
+ * lrprec_1/lrprec_2, main.f90:234-281); device pointers, work enqueued on diaglib_b200_stream() */
+typedef void (*diaglib_lrprec_t)(const int32_t* n, const int32_t* m, const double* fac, const double* xp,
+                                 const double* xm, double* yp, double* ym);
+/* replaces caslr_eff_driver, diaglib.f90:1024-1025 (argument list 1101-1110): the linear-response
+ * problem [A B; B A][Y;Z] = w [S D; -D -S][Y;Z] through the four products (A+B)x, (A-B)x, (S+D)x,
+ * (S-D)x (same contract as matvec).  evec is (n2 = 2n, n_max): rows [0,n) = Y, [n,2n) = Z. */
+void diaglib_b200_caslr_eff_driver(const int32_t* verbose, const int32_t* n, const int32_t* n2, const int32_t* n_targ,
+                                   const int32_t* n_max, const int32_t* max_iter, const double* tol,
+                                   const int32_t* max_dav, diaglib_matvec_t apbmul, diaglib_matvec_t ambmul,
+                                   diaglib_matvec_t spdmul, diaglib_matvec_t smdmul, diaglib_lrprec_t lrprec,
+                                   double* eig, double* evec, int32_t* ok);
+
 /* ---- public block kernels of the reference (public list diaglib.f90:166-167) --------- */
 
 /* replaces ortho_cd, diaglib.f90:3185 : u(n,m) in/out (host or device) */
@@ -101,6 +114,15 @@ void diaglib_b200_csr_matvec(const int32_t* n, const int32_t* m, const double* x
 /* CSR block product with the metric installed by diaglib_b200_set_csr_b; a conforming bvec
  * (the reference's tests use bmult, main.f90, in the same role) */
 void diaglib_b200_csr_bvec(const int32_t* n, const int32_t* m, const double* x, double* bx);
+/* the four products and the preconditioner of the linear-response problem on the matrices installed
+ * by diaglib_b200_set_csr_lr / set_lr_diag; roles of apbvec, ambvec, spdvec, smdvec and lrprec_2,
+ * main.f90:173-232, 257-281 */
+void diaglib_b200_csr_apbmul(const int32_t* n, const int32_t* m, const double* x, double* y);
+void diaglib_b200_csr_ambmul(const int32_t* n, const int32_t* m, const double* x, double* y);
+void diaglib_b200_csr_spdmul(const int32_t* n, const int32_t* m, const double* x, double* y);
+void diaglib_b200_csr_smdmul(const int32_t* n, const int32_t* m, const double* x, double* y);
+void diaglib_b200_lrprec(const int32_t* n, const int32_t* m, const double* fac, const double* xp, const double* xm,
+                         double* yp, double* ym);
 /* diagonal shift-and-invert preconditioner; replaces the role of mprec, main.f90:146-171 */
 void diaglib_b200_diag_precnd(const int32_t* n, const int32_t* m, const double* shift, const double* x,
                               double* px);
@@ -127,6 +149,11 @@ int32_t diaglib_b200_set_csr(int64_t n_loc, int64_t n_halo, const int64_t* rowpt
  * it has halo columns (n_halo > 0) they use the matrix's halo numbering and exchange plan. */
 int32_t diaglib_b200_set_csr_b(int64_t n_loc, int64_t n_halo, const int64_t* rowptr, const int32_t* col,
                                const double* val);
+/* linear-response matrices for the built-in products: which = 0 (A+B), 1 (A-B), 2 (S+D), 3 (S-D);
+ * same conventions as set_csr_b.  set_lr_diag installs diag(A) and diag(S) for the built-in lrprec. */
+int32_t diaglib_b200_set_csr_lr(int32_t which, int64_t n_loc, int64_t n_halo, const int64_t* rowptr, const int32_t* col,
+                                const double* val);
+int32_t diaglib_b200_set_lr_diag(int64_t n_loc, const double* aa_diag, const double* sigma_diag);
 /* halo exchange plan: for neighbour i, send owned rows [send_row0[i], +send_cnt[i]) and
  * receive recv_cnt[i] rows into halo rows [recv_off[i], ...). */
 int32_t diaglib_b200_set_halo(int32_t n_nbr, const int32_t* peer, const int64_t* send_row0,

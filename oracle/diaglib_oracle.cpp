@@ -684,6 +684,221 @@ void oracle_gen_david_driver(const int32_t* verbose_, const int32_t* n_, const i
                 ok_);
 }
 
+typedef void (*lrprec_t)(const int32_t* n, const int32_t* m, const double* fac, const double* xp, const double* xm,
+                         double* yp, double* ym);
+
+// ------------------------------------------------------------------------------------
+// caslr_eff_driver — diaglib.f90:1024-1481.  Linear-response problem
+//   [A B; B A][Y;Z] = w [S D; -D -S][Y;Z]  solved as  s^T s u+ = (1/w)^2 u+  in the paired
+// spaces (b+, b+) / (b-, -b-), with the (A+B) / (A-B) metrics.
+// ------------------------------------------------------------------------------------
+void oracle_caslr_eff_driver(const int32_t* verbose_, const int32_t* n_, const int32_t* n2_, const int32_t* n_targ_,
+                             const int32_t* n_max_, const int32_t* max_iter_, const double* tol_,
+                             const int32_t* max_dav_, matvec_t apbmul, matvec_t ambmul, matvec_t spdmul,
+                             matvec_t smdmul, lrprec_t lrprec, double* eig, double* evec, int32_t* ok_) {
+  const bool verbose = *verbose_ != 0;
+  const int n = *n_, n2 = *n2_, n_targ = *n_targ_, n_max = *n_max_, max_iter = *max_iter_, max_dav = *max_dav_;
+  const double tol = *tol_;
+  const int min_dav = 10;
+  last_status = 0;
+  const int dim_dav = std::max(min_dav, max_dav);  // 1130
+  const int lda = dim_dav * n_max;                 // 1131
+  lwork = std::max(get_mem_lapack(n, n_max), 3 * lda);
+  work.assign(lwork, 0.0);
+  const size_t nn = (size_t)n;
+  std::vector<double> vp(nn * lda, 0.0), vm(nn * lda, 0.0), lvp(nn * lda, 0.0), lvm(nn * lda, 0.0),
+      bvp(nn * lda, 0.0), bvm(nn * lda, 0.0);                                           // 1144
+  std::vector<double> rp(nn * n_max), rm(nn * n_max), eigp(nn * n_max), eigm(nn * n_max), bp(nn * n_max), bm(nn * n_max);
+  std::vector<double> s_red((size_t)lda * lda, 0.0), s_copy((size_t)lda * lda, 0.0), smat((size_t)lda * lda, 0.0),
+      e_red(2 * lda), up((size_t)lda * n_max, 0.0), um((size_t)lda * n_max, 0.0);
+  std::vector<char> done(n_max, 0);
+  std::vector<double> r_norm(2 * n_max, 0.0);
+  hist.clear(n_max);
+  const double sqrtn = std::sqrt((double)n), sqrt2 = std::sqrt(2.0);
+  const double tol_rms = tol, tol_max = 10.0 * tol;
+  t_diag = t_ortho = t_mv = t_tot = 0;
+  bool ok = false;
+  double t_start = now(), t1;
+  char v = 'v', upc = 'u';
+  auto split = [&]() {                                                                   // 1190-1193, 1424-1427
+    for (int i = 0; i < n_max; ++i)
+      for (int j = 0; j < n; ++j) {
+        const double y = evec[(size_t)i * n2 + j], z = evec[(size_t)i * n2 + n + j];
+        vp[nn * i + j] = y + z;
+        vm[nn * i + j] = y - z;
+      }
+  };
+  split();
+  apbmul(&n, &n_max, vp.data(), lvp.data());        // 1246
+  b_ortho(n, n_max, vp.data(), lvp.data());
+  ambmul(&n, &n_max, vm.data(), lvm.data());
+  b_ortho(n, n_max, vm.data(), lvm.data());
+  int n_act = n_max, ind = 1, i_beg = 1, m_dim = 1, ldu = 0, n_frozen = 0;
+  if (verbose) {
+    std::printf("    Davidson-Liu iterations (tol=%10.2E):\n", tol);
+    std::printf("    ------------------------------------------------------------------\n");
+    std::printf("        iter  root              eigenvalue         rms         max ok\n");
+    std::printf("    ------------------------------------------------------------------\n");
+  }
+  for (int it = 1; it <= max_iter && last_status == 0; ++it) {
+    ldu = ldu + n_act;                                                                    // 1279
+    t1 = now();
+    spdmul(&n, &n_act, &vp[nn * (i_beg - 1)], &bvm[nn * (i_beg - 1)]);                    // 1284
+    smdmul(&n, &n_act, &vm[nn * (i_beg - 1)], &bvp[nn * (i_beg - 1)]);                    // 1285
+    t_mv += now() - t1;
+    dgemm('t', 'n', ldu, ldu, n, one, vm.data(), n, bvm.data(), n, zero, smat.data(), lda);  // 1293
+    s_red = smat;
+    std::fill(s_copy.begin(), s_copy.end(), 0.0);
+    dgemm('t', 'n', ldu, ldu, ldu, one, s_red.data(), lda, s_red.data(), lda, zero, s_copy.data(), lda);  // 1303
+    t1 = now();
+    scipy_dsyev_(&v, &upc, &ldu, s_copy.data(), &lda, e_red.data(), work.data(), &lwork, &info, 1, 1);   // 1308
+    t_diag += now() - t1;
+    for (int i = 0; i < n_max; ++i) {                                                      // 1314-1317
+      eig[i] = std::sqrt(e_red[ldu - i - 1]);
+      for (int j = 0; j < ldu; ++j) up[j + (size_t)i * lda] = s_copy[j + (size_t)(ldu - i - 1) * lda];
+    }
+    dgemm('n', 'n', ldu, n_max, ldu, one, s_red.data(), lda, up.data(), lda, zero, um.data(), lda);       // 1321
+    for (int i = 0; i < n_max; ++i)
+      for (int j = 0; j < ldu; ++j) um[j + (size_t)i * lda] = um[j + (size_t)i * lda] / eig[i];           // 1322-1324
+    dgemm('n', 'n', n, n_max, ldu, one, vp.data(), n, up.data(), lda, zero, eigp.data(), n);              // 1330
+    dgemm('n', 'n', n, n_max, ldu, one, vm.data(), n, um.data(), lda, zero, eigm.data(), n);
+    for (int i = 0; i < n_max; ++i)                                                        // 1333-1336
+      for (int j = 0; j < n; ++j) {
+        evec[(size_t)i * n2 + j] = eigp[nn * i + j] + eigm[nn * i + j];
+        evec[(size_t)i * n2 + n + j] = eigp[nn * i + j] - eigm[nn * i + j];
+      }
+    dgemm('n', 'n', n, n_max, ldu, one, bvp.data(), n, um.data(), lda, zero, rp.data(), n);               // 1340-1343
+    dgemm('n', 'n', n, n_max, ldu, one, bvm.data(), n, up.data(), lda, zero, rm.data(), n);
+    dgemm('n', 'n', n, n_max, ldu, one, lvp.data(), n, up.data(), lda, zero, bp.data(), n);
+    dgemm('n', 'n', n, n_max, ldu, one, lvm.data(), n, um.data(), lda, zero, bm.data(), n);
+    for (int i = 0; i < n_targ; ++i) {                                                     // 1345-1351
+      if (done[i]) continue;
+      daxpy(n, -eig[i], &bp[nn * i], &rp[nn * i]);
+      daxpy(n, -eig[i], &bm[nn * i], &rm[nn * i]);
+      double mp = 0.0, mm = 0.0;
+      for (int j = 0; j < n; ++j) { mp = std::max(mp, std::fabs(rp[nn * i + j])); mm = std::max(mm, std::fabs(rm[nn * i + j])); }
+      r_norm[2 * i] = (dnrm2(n, &rp[nn * i]) + dnrm2(n, &rm[nn * i])) / (eig[i] * sqrt2 * sqrtn);
+      r_norm[2 * i + 1] = (mp + mm) / (sqrt2 * eig[i]);
+    }
+    for (int i = 0; i < n_targ; ++i) {                                                     // 1356-1365
+      if (done[i]) continue;
+      done[i] = r_norm[2 * i] < tol_rms && r_norm[2 * i + 1] < tol_max && it > 1;
+      if (!done[i]) {
+        for (int j = i + 1; j < n_max; ++j) done[j] = 0;
+        break;
+      }
+    }
+    {
+      std::vector<double> w(n_max);
+      for (int i = 0; i < n_max; ++i) w[i] = one / eig[i];   // the printed quantity (1371)
+      record(it, n_act, n_max, w.data(), r_norm.data(), done);
+    }
+    if (verbose) {
+      for (int i = 0; i < n_targ; ++i)
+        std::printf("        %4d  %4d%24.12f%12.4E%12.4E%3s\n", it, i + 1, one / eig[i], r_norm[2 * i], r_norm[2 * i + 1],
+                    done[i] ? "T" : "F");
+      std::printf("\n");
+    }
+    bool all_done = true;
+    for (int i = 0; i < n_targ; ++i) all_done = all_done && done[i];
+    if (all_done) {                                                                        // 1376-1382
+      ok = true;
+      for (int i = 0; i < n_targ; ++i) eig[i] = one / eig[i];
+      break;
+    }
+    if (m_dim < dim_dav) {                                                                 // 1387
+      m_dim = m_dim + 1;
+      i_beg = i_beg + n_act;
+      n_act = n_max;
+      n_frozen = 0;
+      for (int i = 0; i < n_targ; ++i) {
+        if (done[i]) { n_act--; n_frozen++; } else break;
+      }
+      ind = n_max - n_act + 1;
+      lrprec(&n, &n_act, &eig[ind - 1], &rp[nn * (ind - 1)], &rm[nn * (ind - 1)], &vp[nn * (i_beg - 1)],
+             &vm[nn * (i_beg - 1)]);                                                       // 1408
+      t1 = now();
+      b_ortho_vs_x(n, ldu, n_act, vp.data(), lvp.data(), &vp[nn * (i_beg - 1)]);           // 1413-1418
+      apbmul(&n, &n_act, &vp[nn * (i_beg - 1)], &lvp[nn * (i_beg - 1)]);
+      b_ortho(n, n_act, &vp[nn * (i_beg - 1)], &lvp[nn * (i_beg - 1)]);
+      b_ortho_vs_x(n, ldu, n_act, vm.data(), lvm.data(), &vm[nn * (i_beg - 1)]);
+      ambmul(&n, &n_act, &vm[nn * (i_beg - 1)], &lvm[nn * (i_beg - 1)]);
+      b_ortho(n, n_act, &vm[nn * (i_beg - 1)], &lvm[nn * (i_beg - 1)]);
+      t_ortho += now() - t1;
+    } else {                                                                               // 1422-1457
+      if (verbose) std::printf("      Restarting davidson.\n");
+      ldu = 0; i_beg = 1; m_dim = 1;
+      n_act = n_max;
+      std::fill(vp.begin(), vp.end(), 0.0);
+      std::fill(vm.begin(), vm.end(), 0.0);
+      split();
+      std::fill(lvp.begin(), lvp.end(), 0.0);
+      std::fill(lvm.begin(), lvm.end(), 0.0);
+      apbmul(&n, &n_max, vp.data(), lvp.data());
+      b_ortho(n, n_max, vp.data(), lvp.data());
+      ambmul(&n, &n_max, vm.data(), lvm.data());
+      b_ortho(n, n_max, vm.data(), lvm.data());
+      std::fill(bvp.begin(), bvp.end(), 0.0);
+      std::fill(bvm.begin(), bvm.end(), 0.0);
+      std::fill(s_red.begin(), s_red.end(), 0.0);
+      std::fill(smat.begin(), smat.end(), 0.0);
+    }
+    if (verbose) {
+      std::printf("    ----------------------------------------\n");
+      std::printf("      # target vectors:    %4d\n      # new vectors added: %4d\n      # converged vectors: %4d\n",
+                  n_targ, n_act, n_frozen);
+      std::printf("    ----------------------------------------\n");
+    }
+  }
+  t_tot = now() - t_start;
+  *ok_ = ok ? 1 : 0;
+}
+
+// the four products and the preconditioner of the linear-response problem (roles of apbvec,
+// ambvec, spdvec, smdvec, lrprec_2 in main.f90:173-232, 257-281) on CSR matrices
+static const int64_t* lr_rowptr[4] = {nullptr, nullptr, nullptr, nullptr};
+static const int32_t* lr_col[4] = {nullptr, nullptr, nullptr, nullptr};
+static const double* lr_val[4] = {nullptr, nullptr, nullptr, nullptr};
+static const double* lr_aa = nullptr;
+static const double* lr_sig = nullptr;
+void oracle_set_csr_lr(int which, const int64_t* rowptr, const int32_t* col, const double* val) {
+  lr_rowptr[which] = rowptr; lr_col[which] = col; lr_val[which] = val;
+}
+void oracle_set_lr_diag(const double* aa_diag, const double* sigma_diag) { lr_aa = aa_diag; lr_sig = sigma_diag; }
+static void lr_spmm(int which, const int32_t* n_, const int32_t* m_, const double* x, double* y) {
+  const int64_t n = *n_;
+  const int m = *m_;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t b = lr_rowptr[which][i], e = lr_rowptr[which][i + 1];
+    for (int j = 0; j < m; ++j) {
+      const double* xj = x + (size_t)j * n;
+      double s = 0.0;
+      for (int64_t k = b; k < e; ++k) s = std::fma(lr_val[which][k], xj[lr_col[which][k]], s);
+      y[i + (size_t)j * n] = s;
+    }
+  }
+}
+void oracle_csr_apbmul(const int32_t* n, const int32_t* m, const double* x, double* y) { lr_spmm(0, n, m, x, y); }
+void oracle_csr_ambmul(const int32_t* n, const int32_t* m, const double* x, double* y) { lr_spmm(1, n, m, x, y); }
+void oracle_csr_spdmul(const int32_t* n, const int32_t* m, const double* x, double* y) { lr_spmm(2, n, m, x, y); }
+void oracle_csr_smdmul(const int32_t* n, const int32_t* m, const double* x, double* y) { lr_spmm(3, n, m, x, y); }
+// lrprec_2, main.f90:257-281
+void oracle_lrprec(const int32_t* n_, const int32_t* m_, const double* fac_, const double* xp, const double* xm,
+                   double* yp, double* ym) {
+  const int64_t n = *n_;
+  const int m = *m_;
+  const double fac = *fac_;
+  for (int j = 0; j < m; ++j)
+    for (int64_t i = 0; i < n; ++i) {
+      double denom = fac * fac * lr_aa[i] * lr_aa[i] - lr_sig[i] * lr_sig[i];
+      denom = 1.0 / denom;
+      const size_t o = i + (size_t)j * n;
+      yp[o] = denom * (fac * lr_aa[i] * xp[o] + lr_sig[i] * xm[o]);
+      ym[o] = denom * (fac * lr_aa[i] * xm[o] + lr_sig[i] * xp[o]);
+    }
+}
+
 // standalone block kernels (reference public list, diaglib.f90:166-167)
 void oracle_ortho_cd(const int32_t* n, const int32_t* m, double* u, double* growth, int32_t* ok) {
   bool okb = false;

@@ -48,6 +48,7 @@ def _p(a):
 class _Keep:
     refs: list = []
     refs_b: list = []
+    refs_lr: list = []
 
 
 def set_csr(rowptr, col, val, diag):
@@ -148,6 +149,38 @@ def gen_david(evec, n_targ, max_iter, tol, max_dav, shift=0.0, matvec="oracle_cs
     lib().oracle_gen_david_driver(_i(verbose), _i(n), _i(n_targ), _i(n_max), _i(max_iter), _d(tol), _i(max_dav),
                                   _d(shift), _cb(matvec), _cb(precnd), _cb(bvec), _p(eig), _p(evec), C.byref(ok))
     lib().oracle_set_gen_david_reference_restart(0)
+    out = _collect(n_max)
+    out.update(eig=eig, ok=bool(ok.value), hist_eig=out["eig"])
+    return out
+
+
+def set_lr(apb, amb, spd, smd, aa_diag, sigma_diag):
+    """the four CSR matrices (rowptr, col, val) and the two diagonals of the linear-response problem"""
+    keep = []
+    for which, (rowptr, col, val) in enumerate((apb, amb, spd, smd)):
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        keep += [rowptr, col, val]
+        lib().oracle_set_csr_lr(which, _p(rowptr), _p(col), _p(val))
+    aa = np.ascontiguousarray(aa_diag, dtype=np.float64)
+    sg = np.ascontiguousarray(sigma_diag, dtype=np.float64)
+    keep += [aa, sg]
+    lib().oracle_set_lr_diag(_p(aa), _p(sg))
+    _Keep.refs_lr = keep
+
+
+def caslr_eff(evec, n_targ, max_iter, tol, max_dav, verbose=False):
+    """caslr_eff_driver (diaglib.f90:1024).  evec: (2n, n_max) Fortran-ordered guess, overwritten."""
+    assert evec.flags.f_contiguous and evec.dtype == np.float64
+    n2, n_max = evec.shape
+    n = n2 // 2
+    eig = np.zeros(n_max)
+    ok = C.c_int32(0)
+    lib().oracle_stats_reset()
+    lib().oracle_caslr_eff_driver(_i(verbose), _i(n), _i(n2), _i(n_targ), _i(n_max), _i(max_iter), _d(tol), _i(max_dav),
+                                  _cb("oracle_csr_apbmul"), _cb("oracle_csr_ambmul"), _cb("oracle_csr_spdmul"),
+                                  _cb("oracle_csr_smdmul"), _cb("oracle_lrprec"), _p(eig), _p(evec), C.byref(ok))
     out = _collect(n_max)
     out.update(eig=eig, ok=bool(ok.value), hist_eig=out["eig"])
     return out

@@ -383,6 +383,88 @@ def test_gen_david_identity_metric_matches_davidson(gpu_lib):
     assert abs(its_s - its_g) <= 1
 
 
+# ---- linear-response solver (caslr_eff_driver, diaglib.f90:1024-1481) ------------------------------
+def _lr_dense(lr, n):
+    import scipy.sparse as sp
+    m = {k: sp.csr_matrix((lr[k][2], lr[k][1], lr[k][0]), shape=(n, n)).toarray() for k in ("apb", "amb", "spd", "smd")}
+    a, b = 0.5 * (m["apb"] + m["amb"]), 0.5 * (m["apb"] - m["amb"])
+    sg, dl = 0.5 * (m["spd"] + m["smd"]), 0.5 * (m["spd"] - m["smd"])
+    return np.block([[a, b], [b, a]]), np.block([[sg, dl], [-dl, -sg]])
+
+
+def _lr_guess(lr, n, n_max, eps=0.05):
+    """Y = unit vectors on the lowest diag(A)/diag(S) sites, Z = 0, plus eps relative noise"""
+    ev = np.zeros((2 * n, n_max), order="F")
+    ev[:n] = P.guess_lowest_diag(lr["aa_diag"] / lr["sigma_diag"], n_max)
+    return np.asfortranarray(ev + P.guess(2 * n, n_max) * (eps / np.sqrt(2 * n / 12.0)))
+
+
+@pytest.mark.parametrize("n,n_targ,tol,structured", [(1024, 4, 1e-8, False), (4096, 8, 1e-9, True), (20001, 8, 1e-9, True)])
+def test_caslr_eff_vs_oracle(gpu_lib, oracle, n, n_targ, tol, structured):
+    """random guess: runs through restarts (1422-1457); structured guess: converges inside one cycle"""
+    lr = P.caslr_like(n)
+    n_max = P.n_eig_rule(n_targ)
+    args = (lr["apb"], lr["amb"], lr["spd"], lr["smd"], lr["aa_diag"], lr["sigma_diag"])
+    oracle.set_lr(*args)
+    gpu_lib.set_lr(*args)
+    ev_o = _lr_guess(lr, n, n_max) if structured else P.guess(2 * n, n_max)
+    ev_g = ev_o.copy(order="F")
+    eig_g = np.zeros(n_max)
+    ro = oracle.caslr_eff(ev_o, n_targ, 200, tol, 10)
+    ok = gpu_lib.caslr_eff_driver(False, n, 2 * n, n_targ, n_max, 200, tol, 10, None, None, None, None, None, eig_g, ev_g)
+    hg = gpu_lib.last_history(n_max)
+    assert ok and ro["ok"]
+    assert (len(hg["it"]) > 10) == (not structured)
+    assert_parity(ro, ok, eig_g, hg, n_targ, it_slack=1 if structured else 2)
+    assert np.array_equal(hg["n_act"][:8], ro["n_act"][:8])
+    # the returned pairs solve A_full x = w S_full x with x = [Y; Z]
+    af, sf = _lr_dense(lr, n)
+    x = ev_g[:, :n_targ]
+    res = af @ x - (sf @ x) * eig_g[:n_targ]
+    assert (np.linalg.norm(res, axis=0) / np.linalg.norm(af @ x, axis=0)).max() < 50 * tol
+    if n <= 2048:
+        import scipy.linalg as sl
+        w = sl.eigh(sf, af, eigvals_only=True)            # S x = (1/w) A x
+        ref = np.sort(1.0 / w[w > 0])[:n_targ]
+        assert np.abs(eig_g[:n_targ] - ref).max() / ref.max() < REL
+
+
+def test_caslr_eff_user_callbacks(gpu_lib):
+    """caller-written products and lrprec (torch on the library stream) reproduce the built-ins"""
+    import torch
+    n, n_targ = 1024, 4
+    n_max = P.n_eig_rule(n_targ)
+    lr = P.caslr_like(n)
+    gpu_lib.set_lr(lr["apb"], lr["amb"], lr["spd"], lr["smd"], lr["aa_diag"], lr["sigma_diag"])
+    ev_b, eig_b = P.guess(2 * n, n_max), np.zeros(n_max)
+    assert gpu_lib.caslr_eff_driver(False, n, 2 * n, n_targ, n_max, 200, 1e-8, 10, None, None, None, None, None, eig_b, ev_b)
+    import scipy.sparse as sp
+    stream = torch.cuda.ExternalStream(gpu_lib.lib().diaglib_b200_stream(), device="cuda:0")
+    mats = {k: torch.as_tensor(sp.csr_matrix((lr[k][2], lr[k][1], lr[k][0]), shape=(n, n)).toarray(), device="cuda:0")
+            for k in ("apb", "amb", "spd", "smd")}
+    aa, sg = torch.as_tensor(lr["aa_diag"], device="cuda:0"), torch.as_tensor(lr["sigma_diag"], device="cuda:0")
+
+    def product(k):
+        def f(nn, m, x, y):
+            with torch.cuda.stream(stream):
+                xt = torch.as_tensor(_DevView(x, nn, m), device="cuda:0")          # X^T
+                torch.as_tensor(_DevView(y, nn, m), device="cuda:0").copy_(xt @ mats[k].T)
+        return f
+
+    def lrprec(nn, m, fac, xp, xm, yp, ym):
+        with torch.cuda.stream(stream):
+            p = torch.as_tensor(_DevView(xp, nn, m), device="cuda:0")
+            q = torch.as_tensor(_DevView(xm, nn, m), device="cuda:0")
+            den = 1.0 / (fac * fac * aa * aa - sg * sg)
+            torch.as_tensor(_DevView(yp, nn, m), device="cuda:0").copy_(den * (fac * aa * p + sg * q))
+            torch.as_tensor(_DevView(ym, nn, m), device="cuda:0").copy_(den * (fac * aa * q + sg * p))
+
+    ev, eig = P.guess(2 * n, n_max), np.zeros(n_max)
+    assert gpu_lib.caslr_eff_driver(False, n, 2 * n, n_targ, n_max, 200, 1e-8, 10, product("apb"), product("amb"),
+                                    product("spd"), product("smd"), lrprec, eig, ev)
+    assert np.abs(eig[:n_targ] - eig_b[:n_targ]).max() / np.abs(eig_b[:n_targ]).max() < REL
+
+
 @pytest.mark.parametrize("n,m", [(3000, 12), (20000, 37)])
 def test_b_ortho_vs_oracle(gpu_lib, oracle, n, m):
     csr = P.toy_sparse(n)

@@ -212,3 +212,27 @@ def test_oracle_gen_david_and_the_reference_restart(oracle):
     # identical up to the restart
     k = 10
     assert np.allclose(lit["hist_eig"][:k, :n_targ], r["hist_eig"][:k, :n_targ], rtol=0, atol=1e-12)
+
+
+def test_oracle_caslr_eff_matches_dense_pencil(oracle):
+    """caslr_eff_driver restated (diaglib.f90:1024-1481) against LAPACK on the full 2n x 2n pencil,
+    the check the reference's own test_caslr does by hand (main.f90:601-625)"""
+    import scipy.linalg as sl
+    import scipy.sparse as sp
+    from diaglib_b200 import problems as P
+    n, n_targ, n_max = 400, 4, 9
+    lr = P.caslr_like(n)
+    m = {k: sp.csr_matrix((lr[k][2], lr[k][1], lr[k][0]), shape=(n, n)).toarray() for k in ("apb", "amb", "spd", "smd")}
+    a, b = 0.5 * (m["apb"] + m["amb"]), 0.5 * (m["apb"] - m["amb"])
+    sg, dl = 0.5 * (m["spd"] + m["smd"]), 0.5 * (m["spd"] - m["smd"])
+    af, sf = np.block([[a, b], [b, a]]), np.block([[sg, dl], [-dl, -sg]])
+    w = sl.eigh(sf, af, eigvals_only=True)
+    ref = np.sort(1.0 / w[w > 0])[:n_targ]
+    oracle.set_lr(lr["apb"], lr["amb"], lr["spd"], lr["smd"], lr["aa_diag"], lr["sigma_diag"])
+    ev = P.guess(2 * n, n_max)
+    r = oracle.caslr_eff(ev, n_targ, 100, 1e-8, 10)
+    assert r["ok"]
+    assert np.abs(r["eig"][:n_targ] - ref).max() / ref.max() < 1e-10
+    x = ev[:, :n_targ]
+    res = af @ x - (sf @ x) * r["eig"][:n_targ]
+    assert (np.linalg.norm(res, axis=0) / np.linalg.norm(af @ x, axis=0)).max() < 1e-6
