@@ -239,6 +239,58 @@ def test_gen_eig_without_metric_fails_loudly(gpu_lib):
         gpu_lib.lobpcg_driver(False, True, 100, 2, 4, 10, 1e-8, 0.0, None, None, None, np.zeros(4), ev)
 
 
+EDGE = [(64, 1, 1, "lobpcg", 0), (64, 1, 2, "lobpcg", 0), (50, 3, 5, "lobpcg", 0), (33, 2, 4, "davidson", 10),
+        (64, 1, 1, "davidson", 10), (257, 4, 4, "lobpcg", 0), (1000, 20, 25, "davidson", 3), (129, 5, 10, "lobpcg", 0),
+        (1001, 45, 50, "lobpcg", 0), (513, 7, 12, "gen_david", 10), (300, 3, 8, "gen_eig", 0)]
+
+
+@pytest.mark.parametrize("n,n_targ,n_max,driver,max_dav", EDGE)
+def test_small_and_odd_sizes(gpu_lib, oracle, n, n_targ, n_max, driver, max_dav):
+    """n below every tile size, n_max = 1, n_targ = n_max, odd n: same eigenvalues AND the same
+    iteration count as the oracle on the reference's dense toy matrix"""
+    csr = dense_as_csr(P.toy_dense(n))
+    install(gpu_lib, oracle, csr)
+    bcsr = (np.arange(n + 1, dtype=np.int64), np.arange(n, dtype=np.int32), 1.0 + 0.2 * np.cos(np.arange(n)))
+    oracle.set_csr_b(*bcsr)
+    gpu_lib.set_csr_b(*bcsr)
+    ev_g = P.guess(n, n_max)
+    ev_o = ev_g.copy(order="F")
+    eig = np.zeros(n_max)
+    if driver == "lobpcg":
+        ro = oracle.lobpcg(ev_o, n_targ, 200, 1e-8)
+        ok = gpu_lib.lobpcg_driver(False, False, n, n_targ, n_max, 200, 1e-8, 0.0, None, None, None, eig, ev_g)
+    elif driver == "gen_eig":
+        ro = oracle.lobpcg(ev_o, n_targ, 200, 1e-8, gen_eig=True)
+        ok = gpu_lib.lobpcg_driver(False, True, n, n_targ, n_max, 200, 1e-8, 0.0, None, None, None, eig, ev_g)
+    elif driver == "gen_david":
+        ro = oracle.gen_david(ev_o, n_targ, 200, 1e-8, max_dav)
+        ok = gpu_lib.gen_david_driver(False, n, n_targ, n_max, 200, 1e-8, max_dav, 0.0, None, None, None, eig, ev_g)
+    else:
+        ro = oracle.davidson(ev_o, n_targ, 200, 1e-8, max_dav)
+        ok = gpu_lib.davidson_driver(False, n, n_targ, n_max, 200, 1e-8, max_dav, 0.0, None, None, eig, ev_g)
+    hg = gpu_lib.last_history(n_max)
+    assert ok and ro["ok"]
+    assert np.abs(eig[:n_targ] - ro["eig"][:n_targ]).max() / np.abs(ro["eig"][:n_targ]).max() < REL
+    assert abs(len(hg["it"]) - len(ro["it"])) <= 1
+
+
+@pytest.mark.parametrize("n,n_max,driver", [(2, 1, "lobpcg"), (16, 3, "davidson")])
+def test_search_space_larger_than_n_fails_like_the_reference(gpu_lib, oracle, n, n_max, driver):
+    """3*n_max > n (LOBPCG) / dim_dav*n_max > n (Davidson): the expansion block cannot be made
+    orthogonal to the space; the reference stops in ortho_vs_x (diaglib.f90:3568), so do both sides"""
+    csr = dense_as_csr(P.toy_dense(n))
+    install(gpu_lib, oracle, csr)
+    ev_o = P.guess(n, n_max)
+    ev_g = ev_o.copy(order="F")
+    ro = oracle.lobpcg(ev_o, 1, 50, 1e-8) if driver == "lobpcg" else oracle.davidson(ev_o, 1, 50, 1e-8, 10)
+    assert ro["status"] == 4
+    with pytest.raises(gpu_lib.DiaglibError):
+        if driver == "lobpcg":
+            gpu_lib.lobpcg_driver(False, False, n, 1, n_max, 50, 1e-8, 0.0, None, None, None, np.zeros(n_max), ev_g)
+        else:
+            gpu_lib.davidson_driver(False, n, 1, n_max, 50, 1e-8, 10, 0.0, None, None, np.zeros(n_max), ev_g)
+
+
 # ---- generalized problem (gen_eig branch, diaglib.f90:299-302, 357-364, 422-436, 500-526) ------
 def check_gen_solution(csr, bcsr, eig, evec, n_targ, tol):
     import scipy.sparse as sp
