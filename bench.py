@@ -371,10 +371,18 @@ def main():
             lib.diaglib_b200_csr_matvec(i32(n_loc), i32(q), C.c_void_p(v.ptr), C.c_void_p(y.ptr))
         sp_ms = K.timer_stop_ms() / reps
         sbytes = 12.0 * nnz_loc + 8.0 * (n_loc + 1) + 16.0 * n_loc * q
+        spmm_traffic = None
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_spmm_short_r01.json")))
+            spmm_traffic = cap["chunked_m37"]["traffic_bytes"] * (n_loc / 16777216.0) if q == 37 else None
+        except Exception:
+            pass
         roof["spmm"] = {"kernel": f"spmm_csr_short_kernel m={q}, n={n_loc}, nnz={nnz_loc}", "bound": "hbm", "ms_per_launch": sp_ms,
                         "achieved_gbs": sbytes / (sp_ms * 1e-3) / 1e9, "frac_hbm": sbytes / (sp_ms * 1e-3) / 1e9 / hbm_peak,
                         "algorithmic_bytes": sbytes,
-                        "note": "L2->SM fill path (~10 TB/s, 52 B per row and column) saturates first: profiles/ncu_spmm_r01.json"}
+                        "traffic": spmm_traffic,
+                        "note": "two launches (24 + 13 columns) keep x in L2; DRAM 13.3 GB for 11.5 GB algorithmic, L2->SM fill "
+                                "29.6 GB at ~10.6 TB/s: profiles/ncu_spmm_short_r01.json"}
         for a in (v, y, cd, w, cg):
             a.free()
 

@@ -17,6 +17,7 @@ extern bool g_bmul_small_tiles;
 extern bool g_eig_two_sided;
 extern int g_eig_coop_min_k;
 extern int g_spmm_short;
+extern int g_spmm_chunk;
 
 // ---- dense.cu -------------------------------------------------------------------------
 // C(p x q, ldc) = A(n x p, lda)^T * B(n x q, ldb).  Replaces dgemm('t','n',p,q,n,...) at

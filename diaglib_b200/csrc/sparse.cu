@@ -7,6 +7,7 @@
 
 namespace dlb {
 int g_spmm_short = 1;
+int g_spmm_chunk = 24;
 namespace {
 
 // ---------------------------------------------------------------------------------------
@@ -288,9 +289,25 @@ void spmm_csr(cudaStream_t st, const CsrDevice& A, int m, const double* x, int64
               double* ax, int64_t ldax, double shift) {
   if (A.n <= 0 || m <= 0) return;
   const unsigned grid = (unsigned)((A.n + 255) / 256);
-  if (A.max_row_nnz > 0 && A.max_row_nnz <= 7 && g_spmm_short > 0)
-    spmm_csr_short_kernel<8, 7><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, m, x, ldx, x_halo, ax, ldax, shift);
-  else
+  if (A.max_row_nnz > 0 && A.max_row_nnz <= 7 && g_spmm_short > 0) {
+    // column chunks, one launch each: with the gathers pipelined the kernel is DRAM-bound on its
+    // ACTUAL traffic, and beyond ~24 columns the far-neighbour reuse window (2 planes x m columns,
+    // read + written) falls out of L2 and x is fetched from DRAM more than once (ncu at m = 37:
+    // 15.9 GB moved for 11.5 GB algorithmic).  A chunk re-reads the matrix but keeps x in L2.
+    int jc = m;
+    if (g_spmm_chunk > 0 && m > g_spmm_chunk) {
+      const int npass = (m + g_spmm_chunk - 1) / g_spmm_chunk;
+      jc = (((m + npass - 1) / npass) + 7) / 8 * 8;
+    }
+    for (int j0 = 0; j0 < m; j0 += jc) {
+      const int mc = std::min(jc, m - j0);
+      // halo block columns are n_halo apart
+      spmm_csr_short_kernel<8, 7><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, mc, x + (int64_t)j0 * ldx, ldx,
+                                                        x_halo ? x_halo + (int64_t)j0 * A.n_halo : nullptr,
+                                                        ax + (int64_t)j0 * ldax, ldax, shift);
+      if (j0 > 0) ++g_launches;
+    }
+  } else
     spmm_csr_kernel<8><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, m, x, ldx, x_halo, ax, ldax, shift);
   ++g_launches;
   DLB_CUDA_CHECK(cudaGetLastError());
