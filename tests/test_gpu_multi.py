@@ -119,3 +119,55 @@ def test_two_rank_parity(oracle, case):
     resid = a @ x - bx * res[0][3][:n_targ]
     assert (np.linalg.norm(resid, axis=0) / np.sqrt(n)).max() < 2e-8
     assert np.abs(x.T @ bx - np.eye(n_targ)).max() < (1e-10 if gen_eig else 1e-11)
+
+
+def _spmm_worker(rank, world, port, m, q):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import diaglib_b200 as D
+    from diaglib_b200 import dist as DD, kernels as K, partition
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        D.init(rank)
+        DD.init_comm(dist)
+        n = 32 * 32 * 16
+        DD.install_partitioned(lambda a, b: P.lap3d(32, 32, 16, a, b, delta=1.0), n, rank, world, dist)
+        r0, r1 = partition.row_range(n, rank, world)
+        x = np.asfortranarray(P.guess(n, m, r0, r1))
+        dx, dax = K.DeviceArray.from_numpy(x), K.DeviceArray((r1 - r0, m))
+        i32 = lambda v_: C.byref(C.c_int32(v_))  # noqa: E731
+        D.lib().diaglib_b200_csr_matvec(i32(r1 - r0), i32(m), C.c_void_p(dx.ptr), C.c_void_p(dax.ptr))
+        D.lib().diaglib_b200_sync()
+        q.put((rank, r0, r1, dax.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("m", [37, 8])
+def test_two_rank_spmm_bit_exact(oracle, m):
+    """halo exchange + the column-chunked short-row SpMM (m > 24: two launches, halo block offset per
+    chunk) reproduce the single-rank oracle product bit for bit"""
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_spmm_worker, args=(r, world, port, m, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 32 * 32 * 16
+    oracle.set_csr(*P.lap3d(32, 32, 16, delta=1.0))
+    ref = oracle.csr_matvec(P.guess(n, m))
+    got = np.vstack([r[3] for r in res])
+    assert np.array_equal(got, ref)
