@@ -82,6 +82,27 @@ def main():
             ax.free()
         print(json.dumps(dict(n=n, **out)))
         return
+    if only == "spmm_toy":
+        # long rows (~2 log2 n entries): the generic / pipelined kernels
+        import ctypes as C
+        from diaglib_b200 import problems as P
+        csr = P.toy_sparse(n)
+        D.set_csr(*csr)
+        nnz = len(csr[1])
+        for m in (37, 13, 8):
+            ax = K.DeviceArray((n, m))
+            i32 = lambda v_: C.byref(C.c_int32(v_))
+            lib.diaglib_b200_csr_matvec(i32(n), i32(m), C.c_void_p(v.ptr), C.c_void_p(ax.ptr))
+            lib.diaglib_b200_sync()
+            K.timer_start()
+            for _ in range(reps):
+                lib.diaglib_b200_csr_matvec(i32(n), i32(m), C.c_void_p(v.ptr), C.c_void_p(ax.ptr))
+            ms = K.timer_stop_ms() / reps
+            by = 12.0 * nnz + 8.0 * (n + 1) + 16.0 * n * m
+            out["spmm_toy_m%d" % m] = dict(ms=round(ms, 4), gbs=round(by / ms / 1e6, 1), bytes=by, nnz=nnz)
+            ax.free()
+        print(json.dumps(dict(n=n, **out)))
+        return
     if only == "gram":
         t_gram(111, 111, 1, v, w, "gram_sym_111")
         t_gram(74, 37, 0, v, w, "gram_74x37")
