@@ -2,8 +2,9 @@
 // diaglib_oracle.cpp — CPU ORACLE.  TEST INFRASTRUCTURE ONLY, NOT PRODUCT CODE.
 //
 // A C++ restatement of the hot path of Molecolab-Pisa/diaglib (reference tree
-// /root/reference, Fortran 95): lobpcg_driver (standard branch), davidson_driver,
-// ortho, ortho_cd, ortho_vs_x, norm_est, diag_shift, get_coeffs, check_guess.
+// /root/reference, Fortran 95): lobpcg_driver (standard and gen_eig branches),
+// davidson_driver, gen_david_driver, caslr_eff_driver, ortho, b_ortho, ortho_cd, ortho_vs_x,
+// b_ortho_vs_x, norm_est, diag_shift, get_coeffs, check_guess.
 // It calls the SAME BLAS/LAPACK routines with the SAME flags in the SAME order as the
 // reference (dgemm dsyev dpotrf dtrtri dtrmm dgeqrf dtrsm dnrm2 daxpy dcopy ilaenv),
 // through the Fortran ABI of the OpenBLAS that ships inside the scipy wheel (symbols
@@ -16,8 +17,11 @@
 // a manual 6-decimal comparison of the toy-matrix eigenvalues against dense LAPACK
 // (main.f90:302,321-342,371-378).  This oracle is pinned against exactly that:
 // dense-LAPACK eigenvalues of the reference's toy matrix (tests/golden/), plus
-// orthonormality / residual invariants.  Iteration histories are NOT pinned by the
-// reference: beyond the eigenvalue check, parity is "unpinned" (see DESIGN.md).
+// orthonormality / residual invariants; the generalized and linear-response drivers are
+// pinned the same way the reference's test_geneig / test_caslr check them by hand
+// (main.f90:403-526, 601-625): against LAPACK on the dense pencil (tests/test_oracle.py).
+// Iteration histories are NOT pinned by the reference: beyond the eigenvalue check, parity
+// is "unpinned" (see DESIGN.md).
 //
 // Every function cites the reference lines it follows (file:line into /root/reference).
 // =====================================================================================
