@@ -203,7 +203,8 @@ contains
   end subroutine gen_david_driver
 !
 ! diaglib.f90:1024-1025
-  subroutine caslr_eff_driver(verbose,n,n2,n_targ,n_max,max_iter,tol,max_dav,apbmul,ambmul,spdmul,smdmul,lrprec,eig,evec,ok)
+  subroutine caslr_eff_driver(verbose,n,n2,n_targ,n_max,max_iter,tol,max_dav, &
+                              apbmul,ambmul,spdmul,smdmul,lrprec,eig,evec,ok)
     logical,  intent(in)    :: verbose
     integer,  intent(in)    :: n, n2, n_targ, n_max, max_iter, max_dav
     real(8),  intent(in)    :: tol
