@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 from . import partition
-from .api import _check, lib, set_csr, set_csr_b
+from .api import _check, lib, set_csr, set_csr_b, set_lr
 
 
 def env_rank():
@@ -32,17 +32,22 @@ def init_comm(dist=None):
     return rank, world
 
 
-def install_partitioned(gen_rows, n: int, rank: int, world: int, dist=None, metric_rows=None):
+def install_partitioned(gen_rows, n: int, rank: int, world: int, dist=None, metric_rows=None, lr_rows=None):
     """gen_rows(r0, r1) -> (rowptr, col_global, val, diag) for the owned rows.  Localises the
     columns, exchanges the needed ranges and installs matrix + halo plan.  Returns (r0, r1).
     metric_rows(r0, r1) -> (rowptr, col_global, val) optionally installs the metric B of the
-    generalized problem; its remote columns must lie inside the matrix's halo."""
+    generalized problem; its remote columns must lie inside the matrix's halo.
+    lr_rows(r0, r1) -> dict(apb, amb, spd, smd = (rowptr, col_global, val), aa_diag, sigma_diag)
+    optionally installs the linear-response matrices under the same condition."""
     r0, r1 = partition.row_range(n, rank, world)
     rowptr, col, val, diag = gen_rows(r0, r1)
     if world == 1:
         set_csr(rowptr, col, val, diag)
         if metric_rows is not None:
             set_csr_b(*metric_rows(r0, r1))
+        if lr_rows is not None:
+            lr = lr_rows(r0, r1)
+            set_lr(lr["apb"], lr["amb"], lr["spd"], lr["smd"], lr["aa_diag"], lr["sigma_diag"])
         return r0, r1
     needed = partition.needed_ranges(col, n, rank, world)
     all_needed = [None] * world
@@ -54,4 +59,9 @@ def install_partitioned(gen_rows, n: int, rank: int, world: int, dist=None, metr
         b_rowptr, b_col, b_val = metric_rows(r0, r1)
         b_loc, _, _ = partition.localize(b_col, n, rank, world, needed)
         set_csr_b(b_rowptr, b_loc, b_val, n_halo=n_halo)
+    if lr_rows is not None:
+        lr = lr_rows(r0, r1)
+        loc = {k: (lr[k][0], partition.localize(lr[k][1], n, rank, world, needed)[0], lr[k][2])
+               for k in ("apb", "amb", "spd", "smd")}
+        set_lr(loc["apb"], loc["amb"], loc["spd"], loc["smd"], lr["aa_diag"], lr["sigma_diag"], n_halo=n_halo)
     return r0, r1

@@ -171,3 +171,83 @@ def test_two_rank_spmm_bit_exact(oracle, m):
     ref = oracle.csr_matvec(P.guess(n, m))
     got = np.vstack([r[3] for r in res])
     assert np.array_equal(got, ref)
+
+
+def _wide_worker(rank, world, port, case, q):
+    import torch
+    import torch.distributed as dist
+
+    import diaglib_b200 as D
+    from diaglib_b200 import dist as DD, partition
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        D.init(rank)
+        DD.init_comm(dist)
+        n = 1 << 13
+        gen = lambda a, b: P.toy_sparse(n, a, b)  # noqa: E731
+        r0, r1 = partition.row_range(n, rank, world)
+        if case == "caslr_eff":
+            n_targ = 6
+            n_max = P.n_eig_rule(n_targ)
+            DD.install_partitioned(gen, n, rank, world, dist, lr_rows=lambda a, b: P.caslr_like(n, a, b))
+            lr = P.caslr_like(n)
+            g = np.zeros((2 * n, n_max), order="F")
+            g[:n] = P.guess_lowest_diag(lr["aa_diag"] / lr["sigma_diag"], n_max)
+            g += P.guess(2 * n, n_max) * (0.05 / np.sqrt(2 * n / 12.0))
+            ev = np.asfortranarray(np.vstack([g[r0:r1], g[n + r0:n + r1]]))      # local [Y; Z]
+            eig = np.zeros(n_max)
+            ok = D.caslr_eff_driver(False, r1 - r0, 2 * (r1 - r0), n_targ, n_max, 100, 1e-9, 10, None, None, None, None,
+                                    None, eig, ev)
+        else:
+            n_targ = 8
+            n_max = P.n_eig_rule(n_targ)
+            DD.install_partitioned(gen, n, rank, world, dist, metric_rows=lambda a, b: P.metric_like(gen(a, b), r0=a))
+            ev = np.asfortranarray(P.guess(n, n_max, r0, r1))
+            eig = np.zeros(n_max)
+            ok = D.gen_david_driver(False, r1 - r0, n_targ, n_max, 100, 1e-8, 10, 0.0, None, None, None, eig, ev)
+        q.put((rank, ok, len(D.last_history(n_max)["it"]), eig.copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("case", ["gen_david", "caslr_eff"])
+def test_two_rank_widened_drivers(oracle, case):
+    """gen_david_driver and caslr_eff_driver row-partitioned over two ranks against the single-rank oracle"""
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_wide_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 1 << 13
+    if case == "caslr_eff":
+        n_targ = 6
+        n_max = P.n_eig_rule(n_targ)
+        lr = P.caslr_like(n)
+        oracle.set_lr(lr["apb"], lr["amb"], lr["spd"], lr["smd"], lr["aa_diag"], lr["sigma_diag"])
+        g = np.zeros((2 * n, n_max), order="F")
+        g[:n] = P.guess_lowest_diag(lr["aa_diag"] / lr["sigma_diag"], n_max)
+        g += P.guess(2 * n, n_max) * (0.05 / np.sqrt(2 * n / 12.0))
+        ro = oracle.caslr_eff(np.asfortranarray(g), n_targ, 100, 1e-9, 10)
+    else:
+        n_targ = 8
+        n_max = P.n_eig_rule(n_targ)
+        csr = P.toy_sparse(n)
+        oracle.set_csr(*csr)
+        oracle.set_csr_b(*P.metric_like(csr))
+        ro = oracle.gen_david(P.guess(n, n_max), n_targ, 100, 1e-8, 10)
+    for rank, ok, its, eig in res:
+        assert ok and ro["ok"]
+        assert np.abs(eig[:n_targ] - ro["eig"][:n_targ]).max() / np.abs(ro["eig"][:n_targ]).max() < 1e-10
+        assert abs(its - len(ro["it"])) <= 1
+        assert np.array_equal(eig, res[0][3])
