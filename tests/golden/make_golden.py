@@ -9,7 +9,16 @@
       diaglib_b200.problems.guess(seed=1).  Pins the oracle against accidental edits; the
       reference itself records no iteration counts.
 
-Run from the repo root:  python tests/golden/make_golden.py
+  c3_oracle_nx{32,128,256}.json : the oracle's complete LOBPCG solve of the benchmark workload
+      (C3: lap3d nx^3, 32 roots of 37, tol 1e-8, lowest-diagonal start + 10 % noise) as written by
+      `python bench.py --impl reference --nx NX` (gpurun_out/oracle_c3_nxNX.json, copied here).
+      nx = 32 is re-checked against the oracle on CPU (tests/test_oracle.py), nx = 128 is the
+      GPU parity test at 2 M rows (tests/test_gpu_drivers.py), nx = 256 is the headline problem
+      (16.7 M rows, about 8 minutes of host time on the GPU box) and backs bench.py's parity block
+      when no fresh run is present.  The thread count of the generating run is recorded inside.
+
+Run from the repo root:  python tests/golden/make_golden.py   (the first two files)
+                         python bench.py --impl reference --nx 32 && cp gpurun_out/oracle_c3_nx32.json tests/golden/c3_oracle_nx32.json
 """
 import json
 import os

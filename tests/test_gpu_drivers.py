@@ -682,3 +682,32 @@ def test_ortho_qr_fallback(gpu_lib, oracle):
     # same Q up to column signs (Householder R may have negative diagonal entries)
     s = np.sign(np.sum(u * uo, axis=0))
     assert np.abs(u * s - uo).max() < 1e-10
+
+
+def test_c3_bench_workload_nx128_vs_oracle_fixture(gpu_lib):
+    """The benchmark workload itself (bench.py: C3, 32 roots of 37, tol 1e-8, lowest-diagonal start
+    + 10 % noise) at 128^3 = 2 097 152 rows against the oracle's complete solve of the same problem
+    (tests/golden/c3_oracle_nx128.json, written by `bench.py --impl reference --nx 128`; the
+    oracle needs about two minutes for it, hence a fixture): eigenvalues 1e-10 relative,
+    residuals below tol, iteration count within +-1.  diaglib.f90:389-533."""
+    import bench
+    gold = json.load(open(os.path.join(GOLD, "c3_oracle_nx128.json")))
+    nx = gold["nx"]
+    n, n_targ = nx ** 3, bench.N_TARG
+    n_max = P.n_eig_rule(n_targ)
+    assert (gold["n_targ"], gold["tol"], gold["delta"], gold["noise"]) == (n_targ, bench.TOL, bench.DELTA, bench.NOISE)
+    csr = P.lap3d(nx, nx, nx, delta=bench.DELTA)
+    gpu_lib.set_csr(*csr)
+    ev = bench.make_guess(csr[3], n, n_max, 0, n)
+    eig = np.zeros(n_max)
+    ok = gpu_lib.lobpcg_driver(False, False, n, n_targ, n_max, bench.MAX_ITER, bench.TOL, 0.0, None, None, None, eig, ev)
+    hg = gpu_lib.last_history(n_max)
+    par = bench.parity_block(dict(gold, _source="tests/golden/c3_oracle_nx128.json"), len(hg["it"]), eig, hg["rms"][-1],
+                             hg["max"][-1])
+    print(par)
+    assert ok and gold["ok"]
+    assert par["max_rel_eig_err"] <= REL
+    assert abs(par["its_gpu"] - par["its_oracle"]) <= 1
+    assert par["max_rms"] < bench.TOL and par["ok"]
+    check_solution(csr, eig, ev, n_targ, bench.TOL)
+    gpu_lib.lib().diaglib_b200_release_workspace()

@@ -236,3 +236,40 @@ def test_oracle_caslr_eff_matches_dense_pencil(oracle):
     x = ev[:, :n_targ]
     res = af @ x - (sf @ x) * r["eig"][:n_targ]
     assert (np.linalg.norm(res, axis=0) / np.linalg.norm(af @ x, axis=0)).max() < 1e-6
+
+
+@pytest.mark.parametrize("threads", [1, 8])
+def test_c3_workload_golden_nx32(oracle, threads):
+    """The benchmark workload (bench.py, C3) at 32^3: the oracle reproduces the committed fixture
+    written by `bench.py --impl reference --nx 32`, whatever the BLAS thread count (the fixture is
+    what bench.py's parity block and the GPU parity tests compare with at 128^3 and 256^3)."""
+    import bench
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c3_oracle_nx32.json")))
+    nx = gold["nx"]
+    n_max = P.n_eig_rule(bench.N_TARG)
+    csr = P.lap3d(nx, nx, nx, delta=bench.DELTA)
+    oracle.set_threads(threads)
+    try:
+        oracle.set_csr(*csr)
+        ev = bench.make_guess(csr[3], nx ** 3, n_max, 0, nx ** 3)
+        r = oracle.lobpcg(ev, bench.N_TARG, bench.MAX_ITER, bench.TOL)
+    finally:
+        oracle.set_threads(min(8, os.cpu_count() or 1))
+    assert r["ok"] and gold["ok"]
+    assert abs(len(r["it"]) - gold["iterations"]) <= 1
+    e, eg = r["eig"][:bench.N_TARG], np.array(gold["eig"][:bench.N_TARG])
+    assert np.max(np.abs(e - eg) / np.abs(eg)) < 1e-10
+    assert r["rms"][-1][:bench.N_TARG].max() < bench.TOL
+
+
+def test_bench_parity_block_logic():
+    import bench
+    gold = bench.load_oracle_result(32)
+    assert gold is not None and gold["_source"].endswith("c3_oracle_nx32.json")
+    e = np.array(gold["eig"])
+    ok = bench.parity_block(gold, gold["iterations"] + 1, e * (1 + 5e-11), np.array(gold["rms"]), np.array(gold["max"]))
+    assert ok["ok"] and ok["its_oracle"] == gold["iterations"]
+    bad_e = bench.parity_block(gold, gold["iterations"], e * (1 + 1e-9), np.array(gold["rms"]), np.array(gold["max"]))
+    bad_i = bench.parity_block(gold, gold["iterations"] + 2, e, np.array(gold["rms"]), np.array(gold["max"]))
+    bad_r = bench.parity_block(gold, gold["iterations"], e, np.array(gold["rms"]) + 1e-7, np.array(gold["max"]))
+    assert not bad_e["ok"] and not bad_i["ok"] and not bad_r["ok"]
