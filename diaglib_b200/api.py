@@ -73,6 +73,9 @@ def lib():
         L.diaglib_b200_k_residual.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.diaglib_b200_k_sym_eig.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.diaglib_b200_k_set_eig_mode.argtypes = [C.c_int32, C.c_int32]
+        L.diaglib_b200_k_sym_eig_time_ms.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+        L.diaglib_b200_k_sym_eig_time_ms.restype = C.c_double
         L.diaglib_b200_k_chol_inv.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.diaglib_b200_k_get_coeffs.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 3
         L.diaglib_b200_comm_init.argtypes = [C.c_int32, C.c_int32, C.c_void_p]

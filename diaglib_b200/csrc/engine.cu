@@ -1327,6 +1327,8 @@ int32_t diaglib_b200_init(int32_t device) {
   if (const char* ev = std::getenv("DIAGLIB_B200_FUSED_GRAM")) g_use_fused_gram = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_TMA")) g_disable_tma = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_EIG_COOP_MIN_K")) g_eig_coop_min_k = std::atoi(ev);
+  if (const char* ev = std::getenv("DIAGLIB_B200_EIG_MODE")) g_eig_mode = std::atoi(ev);
+  if (const char* ev = std::getenv("DIAGLIB_B200_EIG_BLOCK")) g_eig_block = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_SHORT")) g_spmm_short = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_CHUNK")) g_spmm_chunk = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_BMUL_RT256")) g_bmul_small_tiles = ev[0] != '1';
@@ -1792,7 +1794,39 @@ int32_t diaglib_b200_k_sym_eig(int32_t k, double* a_host, int32_t lda, int32_t u
   DLB_CUDA_CHECK(cudaMemcpyAsync(&h, es, sizeof h, cudaMemcpyDeviceToHost, g.st));
   g.sync();
   buf.release();
-  return h.converged ? h.sweeps : -h.sweeps;
+  // sweeps, +1000 when the one-sided solver (path 1) delivered; negative when not converged
+  return h.converged ? h.sweeps + (h.path == 1 ? 1000 : 0) : -h.sweeps - 1;
+}
+int32_t diaglib_b200_k_set_eig_mode(int32_t mode, int32_t block) {
+  const int prev = g_eig_mode;
+  g_eig_mode = mode;
+  g_eig_block = block;
+  return prev;
+}
+double diaglib_b200_k_sym_eig_time_ms(int32_t k, const double* a_host, int32_t lda, int32_t upper, int32_t reps) {
+  if (!require_init()) return -1.0;
+  DevBuf buf;
+  const size_t ew = eig_work_doubles(k), mat = (size_t)lda * k;
+  if (!buf.ensure((2 * mat + k + ew + 8) * sizeof(double))) return -1.0;
+  double* a0 = buf.as<double>();
+  double* a = a0 + mat;
+  double* w = a + mat;
+  double* work = w + k;
+  EigStatus* es = reinterpret_cast<EigStatus*>(work + ew);
+  DLB_CUDA_CHECK(cudaMemcpyAsync(a0, a_host, mat * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  float ms_all = 0.f, ms_copy = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {   // pass 0: copy + solve (after one warm-up), pass 1: copy only
+    for (int r = (pass == 0 ? -1 : 0); r < reps; ++r) {
+      if (r == 0) DLB_CUDA_CHECK(cudaEventRecord(g.sw0, g.st));
+      DLB_CUDA_CHECK(cudaMemcpyAsync(a, a0, mat * sizeof(double), cudaMemcpyDeviceToDevice, g.st));
+      if (pass == 0) sym_eig(g.st, k, a, lda, upper != 0, w, work, es);
+    }
+    DLB_CUDA_CHECK(cudaEventRecord(g.sw1, g.st));
+    DLB_CUDA_CHECK(cudaEventSynchronize(g.sw1));
+    DLB_CUDA_CHECK(cudaEventElapsedTime(pass == 0 ? &ms_all : &ms_copy, g.sw0, g.sw1));
+  }
+  buf.release();
+  return (double)(ms_all - ms_copy) / reps;
 }
 int32_t diaglib_b200_k_chol_inv(int32_t m, const double* metric_host, double* t_host, double* out5) {
   if (!require_init()) return -1000;

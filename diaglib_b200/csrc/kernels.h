@@ -16,6 +16,8 @@ extern bool g_disable_fused_gram;
 extern bool g_bmul_small_tiles;
 extern bool g_eig_two_sided;
 extern int g_eig_coop_min_k;
+extern int g_eig_mode;
+extern int g_eig_block;
 extern int g_spmm_short;
 extern int g_spmm_chunk;
 
@@ -97,7 +99,7 @@ struct CholStatus {      // written by chol_inv, read back by the host control l
 // `work` must hold 2*m*m doubles.
 void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, double* work, CholStatus* status_dev);
 
-struct EigStatus { int sweeps; int converged; };
+struct EigStatus { int sweeps; int converged; int path; };  // path: 1 = one-sided on the Cholesky factor, 2 = two-sided
 // Symmetric eigensolver replacing dsyev('v',uplo) (315,406,1708): a (k x k, lda) is
 // overwritten by the eigenvectors (ascending eigenvalues in w).  Parallel cyclic Jacobi.
 // `work` must hold 2*kp*kp + 4*kp doubles with kp = k rounded up to even.

@@ -302,10 +302,11 @@ __device__ int jacobi_two_sided(int kp, int lds, double* A, double* Z, double* r
 }
 
 __global__ void __launch_bounds__(SM_THREADS)
-sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, int use_smem, int force_two_sided,
+sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, int use_smem, int gated,
                EigStatus* st) {
   extern __shared__ __align__(16) double dyn[];
   __shared__ int s_flag;
+  if (gated && st->path == 1) return;   // the one-sided solver already delivered (uniform)
   const int kp = (k + 1) & ~1;
   const int lds = kp | 1;  // odd stride: row accesses of the two-sided form are bank-conflict free
   const int half = kp / 2;
@@ -320,7 +321,6 @@ sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, in
 
   if (tid == 0) s_flag = 0;
   eig_load(k, kp, lds, a, lda, upper, A, Z);
-  (void)force_two_sided;
   int converged = 0;
   const int sweeps = jacobi_two_sided(kp, lds, A, Z, rc, rs, rp, &s_flag, &converged);
   for (int i = tid; i < kp; i += nt) ev[i] = A[i + (size_t)i * lds];
@@ -349,7 +349,7 @@ sym_eig_kernel(int k, double* a, int lda, int upper, double* w, double* work, in
     const double sg = rk < 0 ? -1.0 : 1.0;
     a[rr + (size_t)((rk < 0 ? -rk : rk) - 1) * lda] = sg * Z[rr + (size_t)i * lds];
   }
-  if (tid == 0) { st->sweeps = sweeps; st->converged = converged; }
+  if (tid == 0) { st->sweeps = sweeps; st->converged = converged; st->path = 2; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -367,9 +367,10 @@ namespace cg = cooperative_groups;
 
 __global__ void __launch_bounds__(256)
 sym_eig_coop_kernel(int k, const double* a, int lda, int upper, double* A, double* Z, double* rot_c, double* rot_s,
-                    int* partner, int* flags, int max_sweeps, EigStatus* st) {
+                    int* partner, int* flags, int max_sweeps, int gated, EigStatus* st) {
   extern __shared__ __align__(16) double stash[];  // per warp: 2*kp doubles (b_p, b_q)
   cg::grid_group grid = cg::this_grid();
+  if (gated && st->path == 1) return;   // uniform over the grid: nobody reaches a grid.sync
   const int kp = (k + 1) & ~1;
   const int half = kp / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
@@ -467,13 +468,15 @@ sym_eig_coop_kernel(int k, const double* a, int lda, int upper, double* A, doubl
     grid.sync();
     if (!any) { converged = 1; break; }
   }
-  if (gtid == 0) { st->sweeps = sweeps; st->converged = converged; }
+  if (gtid == 0) { st->sweeps = sweeps; st->converged = converged; st->path = 2; }
 }
 
 // eigenvalues = diag(A), ascending order, largest component positive, eigenvectors written to a
 __global__ void __launch_bounds__(1024)
-eig_finish_kernel(int k, int kp, const double* A, const double* Z, double* a, int lda, double* w, int* rank) {
+eig_finish_kernel(int k, int kp, const double* A, const double* Z, double* a, int lda, double* w, int* rank,
+                  const EigStatus* gate) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (gate && gate->path == 1) return;
   for (int i = tid; i < k; i += nt) {
     const double di = A[i + (size_t)i * kp];
     int rk = 0;
@@ -495,6 +498,275 @@ eig_finish_kernel(int k, int kp, const double* A, const double* Z, double* a, in
     const int rk = rank[i];
     a[rr + (size_t)((rk < 0 ? -rk : rk) - 1) * lda] = (rk < 0 ? -1.0 : 1.0) * Z[rr + (size_t)i * kp];
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Positive definite reduced problems (every a_red = V^T A V of a positive definite A): Cholesky
+// factor + ONE-SIDED block Jacobi on the factor (Veselic-Hari).  With P^T A P = L L^T (P sorts
+// the diagonal in descending order) the rotations orthogonalise the COLUMNS of L:
+//     L V = U S   ==>   A = (P U) S^2 (P U)^T,
+// so the eigenvalues are the squared column norms (relative accuracy ~ k eps on graded matrices,
+// better than the two-sided form: the rotations only ever see columns, never differences of
+// matrix entries) and the eigenvectors are the normalised columns themselves - no accumulated
+// Z, no row rotations, half the data of the two-sided kernels.  Eigenvector accuracy is
+// LAPACK-class (norm-wise eps), which is what the reference's dsyev delivers.
+//
+// Parallel form: the kp columns are split into nblk = 2 G blocks of b columns; a sweep is a
+// round-robin tournament of the blocks (nblk - 1 rounds, CTA g owns block pair g of the round)
+// plus one round for the pairs inside a block.  In a round a CTA stages its 2 b columns in
+// shared memory and runs b inner rounds of b disjoint column pairs (one warp per pair, 3 dot
+// products + 1 rotation), so a grid barrier is paid once per b inner rounds and the factor
+// crosses L2 once per block round.  L lives in global memory (L2 resident).  The Cholesky
+// factorisation runs in the same cooperative kernel: right-looking panels, CTA 0 factors a
+// panel in shared memory, all CTAs update the trailing matrix (k <= 158: the whole matrix is
+// one panel and never leaves CTA 0's shared memory).
+// Not positive definite (pivot <= 0) or not converged: status.converged = 0 and `a` is left
+// untouched; the two-sided kernels above then run as the fallback (gate argument).
+// ---------------------------------------------------------------------------------------
+struct OsjCtl {
+  unsigned bar;                      // monotonic grid-barrier counter
+  int fail;                          // Cholesky pivot <= 0 / NaN
+  int pad[2];
+  unsigned long long sweep_max[60];  // per sweep: max |p.q| / (|p| |q|) seen before rotating (double bits)
+};
+constexpr int OSJ_NB = 16;           // Cholesky panel width when the matrix does not fit one CTA
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// grid-wide barrier of a cooperative launch (all CTAs co-resident): one atomic per CTA on a
+// monotonic counter.  `target` is the calling CTA's private running total.
+__device__ __forceinline__ void osj_grid_bar(unsigned* ctr, unsigned& target) {
+  if (gridDim.x == 1) { __syncthreads(); return; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    while (ld_acquire_u32(ctr) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1)
+sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double* w, double* L, int ldl, double* gn,
+                   int* perm, OsjCtl* ctl, int max_sweeps, int nb_chol, EigStatus* st) {
+  extern __shared__ __align__(16) double S[];   // Jacobi: 2 b columns of ldl doubles; Cholesky: one panel
+  __shared__ double s_max[8];
+  const int kp = nblk * b;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  const int gwarp = blockIdx.x * nwarp + warp, twarps = gridDim.x * nwarp;
+  const size_t gtid = (size_t)blockIdx.x * nt + tid, gthreads = (size_t)gridDim.x * nt;
+  unsigned bar_target = 0;
+  const double tol = EPS * sqrt((double)k);
+
+  // ---- 0a: permutation that sorts the diagonal in descending order (ties: lower index first)
+  for (size_t i = gtid; i < (size_t)k; i += gthreads) {
+    const double di = a[i + i * (size_t)lda];
+    int rk = 0;
+    for (int j = 0; j < k; ++j) {
+      const double dj = a[j + (size_t)j * lda];
+      rk += (dj > di || (dj == di && j < (int)i)) ? 1 : 0;
+    }
+    if (!(di > 0.0)) ctl->fail = 1;   // also NaN: the ranks below would collide
+    else perm[rk] = (int)i;
+  }
+  osj_grid_bar(&ctl->bar, bar_target);
+  if (*(volatile int*)&ctl->fail) { if (gtid == 0) { st->sweeps = 0; st->converged = 0; st->path = 0; } return; }
+  // ---- 0b: L = lower triangle of P^T A P, zero elsewhere (padding columns included)
+  for (size_t e = gtid; e < (size_t)ldl * kp; e += gthreads) {
+    const int i = (int)(e % ldl), j = (int)(e / ldl);
+    double v = 0.0;
+    if (i < k && j < k && i >= j) {
+      const int oi = perm[i], oj = perm[j];
+      const int lo = oi < oj ? oi : oj, hi = oi < oj ? oj : oi;
+      v = upper ? a[lo + (size_t)hi * lda] : a[hi + (size_t)lo * lda];
+    }
+    L[e] = v;
+  }
+  osj_grid_bar(&ctl->bar, bar_target);
+  // ---- 0c: right-looking panel Cholesky
+  for (int J = 0; J < k; J += nb_chol) {
+    const int nb = min(nb_chol, k - J), rows = k - J;
+    if (blockIdx.x == 0) {
+      for (int e = tid; e < rows * nb; e += nt) {
+        const int c = e / rows, i = e % rows;
+        S[e] = __ldcg(&L[(J + i) + (size_t)(J + c) * ldl]);
+      }
+      __syncthreads();
+      bool bad = false;
+      for (int c = 0; c < nb; ++c) {
+        const double piv = S[c * rows + c];
+        if (!(piv > 0.0)) { bad = true; break; }   // uniform: every thread reads the same value
+        const double sq = sqrt(piv);
+        __syncthreads();
+        for (int i = c + tid; i < rows; i += nt) S[c * rows + i] = (i == c) ? sq : S[c * rows + i] / sq;
+        __syncthreads();
+        const int ncol = nb - c - 1;
+        for (int e = tid; e < ncol * rows; e += nt) {
+          const int c2 = c + 1 + e / rows, i = e % rows;
+          if (i >= c2) S[c2 * rows + i] = fma(-S[c * rows + i], S[c * rows + c2], S[c2 * rows + i]);
+        }
+        __syncthreads();
+      }
+      if (bad) { if (tid == 0) ctl->fail = 1; }
+      else {
+        for (int e = tid; e < rows * nb; e += nt) {
+          const int c = e / rows, i = e % rows;
+          L[(J + i) + (size_t)(J + c) * ldl] = (i >= c) ? S[e] : 0.0;
+        }
+      }
+    }
+    osj_grid_bar(&ctl->bar, bar_target);
+    if (*(volatile int*)&ctl->fail) { if (gtid == 0) { st->sweeps = 0; st->converged = 0; st->path = 0; } return; }
+    if (J + nb < k) {
+      // trailing update: column j (one warp) -= panel(:, 0:nb) * panel(j, 0:nb)^T, rows >= j
+      for (int j = J + nb + gwarp; j < k; j += twarps) {
+        double lj[OSJ_NB];
+        const double mine = (lane < nb) ? __ldcg(&L[j + (size_t)(J + lane) * ldl]) : 0.0;
+#pragma unroll
+        for (int c = 0; c < OSJ_NB; ++c) lj[c] = __shfl_sync(0xffffffffu, mine, c);
+        for (int i = (j & ~31) + lane; i < k; i += 32) {
+          if (i < j) continue;
+          double acc = __ldcg(&L[i + (size_t)j * ldl]);
+#pragma unroll
+          for (int c = 0; c < OSJ_NB; ++c)
+            if (c < nb) acc = fma(-L[i + (size_t)(J + c) * ldl], lj[c], acc);
+          L[i + (size_t)j * ldl] = acc;
+        }
+      }
+      osj_grid_bar(&ctl->bar, bar_target);
+    }
+  }
+
+  // ---- 1: one-sided block Jacobi sweeps on the columns of L
+  int sweeps = 0, converged = 0;
+  const int g = blockIdx.x;
+  while (sweeps < max_sweeps) {
+    double my_max = 0.0;
+    for (int R = 0; R < nblk; ++R) {
+      int P, Q;
+      const bool cross = R < nblk - 1;
+      if (cross) rr_pair(R, g, nblk, P, Q);
+      else { P = 2 * g; Q = 2 * g + 1; }
+      // stage the 2 b columns (warp w: column w of P and column w of Q)
+      for (int c = warp; c < 2 * b; c += nwarp) {
+        const double* src = L + (size_t)((c < b ? P * b + c : Q * b + (c - b))) * ldl;
+        double* dst = S + (size_t)c * ldl;
+        for (int i = lane; i < ldl; i += 32) dst[i] = __ldcg(&src[i]);
+      }
+      __syncthreads();
+      const int n_inner = cross ? b : b - 1;
+      bool dirty = false;
+      for (int t = 0; t < n_inner; ++t) {
+        for (int pr = warp; pr < b; pr += nwarp) {
+          int cp, cq;
+          if (cross) { cp = pr; cq = b + (pr + t) % b; }
+          else {
+            const int hb = b / 2, off = pr < hb ? 0 : b;
+            rr_pair(t, pr % hb, b, cp, cq);
+            cp += off; cq += off;
+          }
+          double* x = S + (size_t)cp * ldl;
+          double* y = S + (size_t)cq * ldl;
+          double app = 0.0, aqq = 0.0, apq = 0.0;
+          for (int i = lane; i < ldl; i += 32) {
+            const double xv = x[i], yv = y[i];
+            app = fma(xv, xv, app); aqq = fma(yv, yv, aqq); apq = fma(xv, yv, apq);
+          }
+          app = warp_sum(app); aqq = warp_sum(aqq); apq = warp_sum(apq);
+          const double den = app * aqq;
+          if (den > 0.0) {
+            const double rel = fabs(apq) * fast_rsqrt(den);   // den within the float range for these matrices
+            const double relx = (den > 1e-30 && den < 1e30) ? rel : fabs(apq) / sqrt(den);
+            my_max = fmax(my_max, relx);
+            if (relx > tol) {
+              const double zeta = (aqq - app) / (2.0 * apq);
+              double tt;
+              if (fabs(zeta) < 1e8) {
+                const double t2 = 1.0 + zeta * zeta;
+                tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(t2));
+              } else {
+                tt = 0.5 / zeta;
+              }
+              const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = tt * cs;
+              for (int i = lane; i < ldl; i += 32) {
+                const double xv = x[i], yv = y[i];
+                x[i] = cs * xv - sn * yv;
+                y[i] = sn * xv + cs * yv;
+              }
+              dirty = true;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // write the block pair back if any of its columns changed
+      if (__syncthreads_or(dirty ? 1 : 0)) {
+        for (int c = warp; c < 2 * b; c += nwarp) {
+          double* dst = L + (size_t)((c < b ? P * b + c : Q * b + (c - b))) * ldl;
+          const double* src = S + (size_t)c * ldl;
+          for (int i = lane; i < ldl; i += 32) dst[i] = src[i];
+        }
+      }
+      if (R == nblk - 1) {
+        // publish this CTA's largest relative off-diagonal of the sweep before the last barrier
+        if (lane == 0) s_max[warp] = my_max;
+        __syncthreads();
+        if (tid == 0) {
+          double m = 0.0;
+          for (int q = 0; q < nwarp; ++q) m = fmax(m, s_max[q]);
+          atomicMax(&ctl->sweep_max[sweeps], (unsigned long long)__double_as_longlong(m));
+        }
+      }
+      osj_grid_bar(&ctl->bar, bar_target);
+    }
+    const double mx = __longlong_as_double((long long)__ldcg(&ctl->sweep_max[sweeps]));
+    ++sweeps;
+    // quadratic convergence: rotations against off-diagonals below 1e-9 leave k * 1e-18
+    if (mx <= fmax(tol, 1e-9)) { converged = 1; break; }
+  }
+  if (!converged) { if (gtid == 0) { st->sweeps = sweeps; st->converged = 0; st->path = 0; } return; }
+
+  // ---- 2: eigenvalues = squared column norms, ascending; eigenvectors = normalised columns,
+  //         rows back in the caller's order, largest component positive
+  for (int j = gwarp; j < k; j += twarps) {
+    double s = 0.0;
+    for (int i = lane; i < k; i += 32) { const double v = __ldcg(&L[i + (size_t)j * ldl]); s = fma(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) gn[j] = s;
+  }
+  osj_grid_bar(&ctl->bar, bar_target);
+  for (int j = gwarp; j < k; j += twarps) {
+    const double gj = __ldcg(&gn[j]);
+    int rk = 0;
+    for (int i = lane; i < k; i += 32) {
+      const double gi = __ldcg(&gn[i]);
+      rk += (gi < gj || (gi == gj && i < j)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
+    double best = -1.0, bval = 0.0;
+    int bidx = 0x7fffffff;
+    for (int i = lane; i < k; i += 32) {
+      const double v = __ldcg(&L[i + (size_t)j * ldl]);
+      const int oi = perm[i];
+      if (fabs(v) > best || (fabs(v) == best && oi < bidx)) { best = fabs(v); bval = v; bidx = oi; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o), ov = __shfl_xor_sync(0xffffffffu, bval, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) { best = ob; bval = ov; bidx = oi; }
+    }
+    const double nrm = sqrt(gj) * (bval < 0.0 ? -1.0 : 1.0);
+    for (int i = lane; i < k; i += 32) a[perm[i] + (size_t)rk * lda] = __ldcg(&L[i + (size_t)j * ldl]) / nrm;
+    if (lane == 0) w[rk] = gj;
+  }
+  if (gtid == 0) { st->sweeps = sweeps; st->converged = 1; st->path = 1; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -656,11 +928,39 @@ void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, 
   DLB_CUDA_CHECK(cudaGetLastError());
 }
 
+namespace {
+struct OsjPlan { int b, G, nblk, kp, ldl, nb_chol, threads; size_t smem; bool ok; };
+}
+int g_eig_mode = 0;        // DIAGLIB_B200_EIG_MODE: 0 = one-sided on the Cholesky factor, two-sided as fallback; 1 = two-sided only
+int g_eig_block = 0;       // DIAGLIB_B200_EIG_BLOCK: columns per block of the one-sided solver (0 = automatic)
+static OsjPlan osj_plan(int k, int num_sms) {
+  OsjPlan p{};
+  p.b = g_eig_block > 0 ? g_eig_block : (k < 64 ? 4 : 8);
+  if (p.b != 2 && p.b != 4 && p.b != 8) p.b = 8;
+  p.G = (k + 2 * p.b - 1) / (2 * p.b);
+  p.nblk = 2 * p.G;
+  p.kp = p.nblk * p.b;
+  p.ldl = (k + 31) & ~31;
+  const size_t jac = (size_t)2 * p.b * p.ldl;
+  const size_t whole = (size_t)k * k;
+  const size_t cap = (size_t)200 * 1024 / sizeof(double);
+  p.nb_chol = whole <= cap ? k : OSJ_NB;                       // whole matrix in CTA 0's shared memory when it fits
+  const size_t chol = p.nb_chol == k ? whole : (size_t)OSJ_NB * k;
+  p.smem = std::max(jac, chol) * sizeof(double);
+  p.threads = 32 * p.b;
+  p.ok = p.G <= num_sms && p.smem <= (size_t)200 * 1024 && k >= 1;
+  return p;
+}
+
 size_t eig_work_doubles(int k) {
   const int kp = (k + 1) & ~1, lds = kp | 1;
   // single-CTA layout: A, Z (kp x lds) + eigenvalues + rotation tables;
   // cooperative layout: A, Z (kp x kp) + rot_c, rot_s (kp) + partner, rank (kp ints) + flags
-  return 2 * (size_t)kp * lds + 6 * (size_t)kp + 16;
+  const size_t two_sided = 2 * (size_t)kp * lds + 6 * (size_t)kp + 16;
+  // one-sided layout: L (ldl x kp8) + column norms + permutation + control block
+  const int ldl = (k + 31) & ~31, kp8 = ((k + 15) / 16) * 16 + 16;
+  const size_t one_sided = (size_t)ldl * kp8 + 2 * (size_t)kp8 + sizeof(OsjCtl) / sizeof(double) + 16;
+  return std::max(two_sided, one_sided);
 }
 
 bool g_eig_two_sided = false;  // unused (kept for ABI of the A/B switch)
@@ -672,6 +972,7 @@ void sym_eig(cudaStream_t st, int k, double* a, int lda, bool upper, double* w, 
   if (!attr_set) {
     DLB_CUDA_CHECK(cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     DLB_CUDA_CHECK(cudaFuncSetAttribute(sym_eig_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(sym_eig_osj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int dev = 0;
     DLB_CUDA_CHECK(cudaGetDevice(&dev));
     DLB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -679,7 +980,25 @@ void sym_eig(cudaStream_t st, int k, double* a, int lda, bool upper, double* w, 
     attr_set = true;
   }
   const int kp = (k + 1) & ~1;
-  const size_t need = eig_work_doubles(k) * sizeof(double);
+  int gated = 0;
+  if (g_eig_mode == 0 && coop_ok) {
+    const OsjPlan pl = osj_plan(k, num_sms);
+    if (pl.ok) {
+      // one-sided block Jacobi on the Cholesky factor; leaves status.converged = 0 (and `a` untouched)
+      // when the matrix is not positive definite, in which case the gated two-sided solver below runs
+      double* L = work;
+      double* gn = L + (size_t)pl.ldl * pl.kp;
+      int* perm = reinterpret_cast<int*>(gn + pl.kp);
+      OsjCtl* ctl = reinterpret_cast<OsjCtl*>(gn + 2 * (size_t)pl.kp);
+      DLB_CUDA_CHECK(cudaMemsetAsync(ctl, 0, sizeof(OsjCtl), st));
+      int ki = k, bi = pl.b, nblk = pl.nblk, ldai = lda, up = upper ? 1 : 0, ldl = pl.ldl, max_sweeps = 40, nbc = pl.nb_chol;
+      void* args[] = {&ki, &bi, &nblk, &a, &ldai, &up, &w, &L, &ldl, &gn, &perm, &ctl, &max_sweeps, &nbc, &status_dev};
+      DLB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sym_eig_osj_kernel, dim3(pl.G), dim3(pl.threads), args, pl.smem, st));
+      ++g_launches;
+      gated = 1;
+    }
+  }
+  const size_t need = (2 * (size_t)kp * (kp | 1) + 6 * (size_t)kp + 16) * sizeof(double);
   const bool fits = need <= 224 * 1024;
   if (coop_ok && (k >= g_eig_coop_min_k || !fits)) {
     // multi-CTA solver: one CTA per pair and round, stash = 2 kp doubles
@@ -698,18 +1017,17 @@ void sym_eig(cudaStream_t st, int k, double* a, int lda, bool upper, double* w, 
       int* flags = rank + kp;
       int max_sweeps = 40, ki = k, ldai = lda, up = upper ? 1 : 0;
       const double* ain = a;
-      void* args[] = {&ki, &ain, &ldai, &up, &A, &Z, &rot_c, &rot_s, &partner, &flags, &max_sweeps, &status_dev};
+      void* args[] = {&ki, &ain, &ldai, &up, &A, &Z, &rot_c, &rot_s, &partner, &flags, &max_sweeps, &gated, &status_dev};
       DLB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sym_eig_coop_kernel, dim3(grid), dim3(warps * 32), args, smem, st));
       ++g_launches;
-      eig_finish_kernel<<<1, 1024, 0, st>>>(k, kp, A, Z, a, lda, w, rank);
+      eig_finish_kernel<<<1, 1024, 0, st>>>(k, kp, A, Z, a, lda, w, rank, gated ? status_dev : nullptr);
       ++g_launches;
       DLB_CUDA_CHECK(cudaGetLastError());
       return;
     }
   }
   const int use_smem = fits ? 1 : 0;
-  sym_eig_kernel<<<1, SM_THREADS, use_smem ? need : 0, st>>>(k, a, lda, upper ? 1 : 0, w, work, use_smem,
-                                                              g_eig_two_sided ? 1 : 0, status_dev);
+  sym_eig_kernel<<<1, SM_THREADS, use_smem ? need : 0, st>>>(k, a, lda, upper ? 1 : 0, w, work, use_smem, gated, status_dev);
   ++g_launches;
   DLB_CUDA_CHECK(cudaGetLastError());
 }

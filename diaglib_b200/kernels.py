@@ -114,7 +114,21 @@ def sym_eig(a: np.ndarray, upper: bool = False):
     sweeps = lib().diaglib_b200_k_sym_eig(k, _ptr(a), k, 1 if upper else 0, _ptr(w))
     if sweeps < 0:
         raise DiaglibError(f"sym_eig did not converge ({sweeps})")
-    return w, a, sweeps
+    sym_eig.last_path = 1 if sweeps >= 1000 else 2   # 1: one-sided Jacobi on the Cholesky factor, 2: two-sided
+    return w, a, sweeps % 1000
+
+
+def set_eig_mode(mode: int, block: int = 0) -> int:
+    """0: one-sided Jacobi on the Cholesky factor, two-sided fallback (default); 1: two-sided only"""
+    init()
+    return int(lib().diaglib_b200_k_set_eig_mode(int(mode), int(block)))
+
+
+def sym_eig_time_ms(a: np.ndarray, upper: bool = False, reps: int = 10) -> float:
+    init()
+    a = np.asfortranarray(a, dtype=np.float64)
+    k = a.shape[0]
+    return float(lib().diaglib_b200_k_sym_eig_time_ms(k, _ptr(a), k, 1 if upper else 0, reps))
 
 
 def chol_inv(metric: np.ndarray):

@@ -47,8 +47,18 @@ int32_t diaglib_b200_k_residual(int64_t n, int32_t m, const double* ax_dev, int6
                                 int64_t ldx, const double* theta_host, const int32_t* active_host, double* r_dev,
                                 int64_t ldr, double* norms_host);
 /* dsyev('v',uplo) replacement on a host matrix (k x k, lda): a overwritten by eigenvectors,
- * w ascending.  returns sweeps (<0 if not converged).  diaglib.f90:315,406,1708 */
+ * w ascending.  returns sweeps, +1000 when the one-sided solver on the Cholesky factor delivered
+ * (positive definite input), < 0 if not converged.  diaglib.f90:315,406,1708 */
 int32_t diaglib_b200_k_sym_eig(int32_t k, double* a_host, int32_t lda, int32_t upper, double* w_host);
+/* solver selection for the reduced eigenproblems: mode 0 = one-sided block Jacobi on the Cholesky
+ * factor with the two-sided solver as the fallback for matrices that are not positive definite
+ * (default), 1 = two-sided only; block = columns per block of the one-sided solver (0 = automatic,
+ * else 4 or 8).  Returns the previous mode. */
+int32_t diaglib_b200_k_set_eig_mode(int32_t mode, int32_t block);
+/* times `reps` back-to-back reduced eigensolves of the same host matrix on the device (CUDA events
+ * on the library stream, input restored by a device copy before each solve, the copy excluded by
+ * measuring it separately); returns milliseconds per solve */
+double diaglib_b200_k_sym_eig_time_ms(int32_t k, const double* a_host, int32_t lda, int32_t upper, int32_t reps);
 /* one factor+invert step of ortho_cd on a host metric (m x m): T = L^-T (m x m).
  * out5 = {l_norm, linv_norm, shift_used, info_first, n_shifts}; returns hard_fail.
  * diaglib.f90:3261-3316 */

@@ -198,24 +198,128 @@ def test_sym_eig_indefinite_and_plus_minus_pairs(K, oracle):
     assert np.allclose(w3, [-1.0, 1.0]) and np.abs(c @ z3 - z3 * w3).max() < 1e-15
 
 
-def test_sym_eig_graded_matrix_relative_accuracy(K, oracle):
-    """LOBPCG-like reduced matrix: Ritz values 7..44 next to 1e6-1e7 (W block): the small
-    eigenvalues must keep ~1e-13 RELATIVE accuracy (the parity bar is 1e-10 relative)"""
-    rng = np.random.default_rng(12)
-    k = 111
+def graded_lobpcg_like(k=111, seed=12):
+    rng = np.random.default_rng(seed)
     d = np.concatenate([np.arange(7.0, 44.0), 50 + 1e3 * rng.random(37), 1e6 + 1e7 * rng.random(37)])
     cpl = rng.standard_normal((k, k))
     cpl = 1e-3 * (cpl + cpl.T) * np.sqrt(np.outer(d, d)) / d.max() ** 0.5
     a = np.diag(d) + cpl
     np.fill_diagonal(a, d)
-    w, z, sweeps = K.sym_eig(a)
+    return a
+
+
+def rayleigh_ld(a, z):
+    """Rayleigh quotients of the columns of z in extended precision: within |r|^2 / gap of an
+    eigenvalue, i.e. an independent reference for eigenvalues that LAPACK only delivers to
+    eps |A| absolute"""
+    al, zl = a.astype(np.longdouble), z.astype(np.longdouble)
+    return ((zl * (al @ zl)).sum(0) / (zl * zl).sum(0)).astype(np.float64)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sym_eig_graded_matrix_relative_accuracy(K, oracle, mode):
+    """LOBPCG-like reduced matrix: Ritz values 7..44 next to 1e6-1e7 (W block): the small
+    eigenvalues must keep ~1e-13 RELATIVE accuracy (the parity bar is 1e-10 relative).
+    mode 0: one-sided Jacobi on the Cholesky factor (eigenvalues relatively accurate, eigenvectors
+    LAPACK-class: residual eps |A|); mode 1: two-sided Jacobi (residuals relative to each eigenvalue)."""
+    a = graded_lobpcg_like()
+    prev = K.set_eig_mode(mode)
+    try:
+        w, z, sweeps = K.sym_eig(a)
+        path = K.sym_eig.last_path
+    finally:
+        K.set_eig_mode(prev)
+    assert path == (1 if mode == 0 else 2)
     # rigorous check: for symmetric A an eigenvalue lies within |A z - w z| / |z| of w.  Residual in
     # extended precision.  (LAPACK's tridiagonal QR is only absolutely accurate, eps |A| ~ 1e-9 here,
     # so it is not a usable reference for the small eigenvalues of this matrix.)
     al, zl, wl = a.astype(np.longdouble), z.astype(np.longdouble), w.astype(np.longdouble)
     res = np.linalg.norm((al @ zl - zl * wl).astype(np.float64), axis=0) / np.linalg.norm(z, axis=0)
-    assert (res[:37] / np.abs(w[:37])).max() < 1e-12
-    assert (res / np.abs(w)).max() < 1e-11
+    assert np.abs(z.T @ z - np.eye(len(w))).max() < 1e-14
+    if mode == 1:
+        assert (res[:37] / np.abs(w[:37])).max() < 1e-12
+        assert (res / np.abs(w)).max() < 1e-11
+    else:
+        rq = rayleigh_ld(a, z)
+        assert res.max() < 20 * EPS * np.abs(w).max()                  # what dsyev guarantees
+        assert (res ** 2).max() < 1e-13                                 # so rq is an eigenvalue to < 1e-13 absolute
+        assert (np.abs(w - rq) / np.abs(rq)).max() < 1e-13              # every eigenvalue, relative
+        assert sweeps <= 6
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 9, 15, 37, 63, 64, 74, 111, 112, 133, 158, 159, 210, 266, 399, 700, 1330])
+def test_sym_eig_one_sided_positive_definite(K, oracle, k):
+    """positive definite reduced matrices take the one-sided solver (Cholesky factor + block
+    Jacobi): all block sizes / CTA counts, whole-matrix and panel Cholesky (k <= 158 / beyond)"""
+    rng = np.random.default_rng(1000 + k)
+    s = rng.standard_normal((k, k))
+    a = np.diag(np.arange(1.0, k + 1)) + 0.05 * (s + s.T) + (s @ s.T) / (4 * k)
+    w_ref = np.linalg.eigvalsh(a)
+    assert w_ref[0] > 0
+    for upper in (False, True):
+        tri = np.triu(a) if upper else np.tril(a)
+        tri = tri + (np.tril(np.full((k, k), np.nan), -1) if upper else np.triu(np.full((k, k), np.nan), 1))
+        w, z, sweeps = K.sym_eig(tri, upper=upper)
+        assert K.sym_eig.last_path == 1
+        scale = np.abs(w_ref).max()
+        assert np.abs(w - w_ref).max() <= 50 * EPS * scale * max(1, np.sqrt(k))
+        assert np.abs(a @ z - z * w).max() <= 200 * EPS * scale * np.sqrt(k)
+        assert np.abs(z.T @ z - np.eye(k)).max() <= 100 * EPS * np.sqrt(k)
+        assert np.all(np.diff(w) >= 0)
+        assert np.all(z[np.abs(z).argmax(axis=0), np.arange(k)] > 0)
+        assert sweeps <= 12
+
+
+@pytest.mark.parametrize("block", [4, 8])
+def test_sym_eig_one_sided_block_sizes_agree(K, block):
+    a = graded_lobpcg_like()
+    prev = K.set_eig_mode(0, block)
+    try:
+        w, z, _ = K.sym_eig(a)
+        assert K.sym_eig.last_path == 1
+    finally:
+        K.set_eig_mode(prev, 0)
+    rq = rayleigh_ld(a, z)
+    assert (np.abs(w - rq) / np.abs(rq)).max() < 1e-13
+
+
+def test_sym_eig_not_positive_definite_falls_back(K):
+    """zero / negative diagonal, indefinite with positive diagonal, NaN: the one-sided solver
+    declines on the device and the two-sided solver delivers in the same call"""
+    rng = np.random.default_rng(3)
+    k = 37
+    s = rng.standard_normal((k, k))
+    a = np.diag(np.arange(1.0, k + 1)) + 2.0 * (s + s.T)      # positive diagonal, indefinite
+    assert np.linalg.eigvalsh(a)[0] < 0
+    w, z, _ = K.sym_eig(a)
+    assert K.sym_eig.last_path == 2
+    assert np.abs(a @ z - z * w).max() < 1e-12
+    b = a.copy()
+    b[5, 5] = -1.0
+    w, z, _ = K.sym_eig(b)
+    assert K.sym_eig.last_path == 2 and np.abs(b @ z - z * w).max() < 1e-12
+    w, z, _ = K.sym_eig(np.zeros((4, 4)))
+    assert K.sym_eig.last_path == 2 and np.abs(w).max() == 0.0
+
+
+def test_sym_eig_timing_table(K):
+    """not a pass/fail test of speed: prints the per-solve time of both solvers (pytest -s)"""
+    for k in (37, 74, 111, 210, 399, 700, 1330):
+        rng = np.random.default_rng(k)
+        s = rng.standard_normal((k, k))
+        a = np.diag(np.arange(1.0, k + 1)) + 0.02 * (s + s.T) + (s @ s.T) / (4 * k)
+        out = []
+        for mode in (0, 1):
+            if mode == 1 and k > 700:
+                out.append(float("nan"))
+                continue
+            prev = K.set_eig_mode(mode)
+            try:
+                out.append(K.sym_eig_time_ms(a, reps=3 if k > 300 else 10))
+            finally:
+                K.set_eig_mode(prev)
+        print(f"sym_eig k={k}: one-sided {out[0]:.3f} ms, two-sided {out[1]:.3f} ms")
+        assert out[0] > 0
 
 
 # ---- Cholesky factor + inverse + norm estimates (one ortho_cd pass) ---------------------------
