@@ -36,9 +36,11 @@ def install_partitioned(gen_rows, n: int, rank: int, world: int, dist=None, metr
     """gen_rows(r0, r1) -> (rowptr, col_global, val, diag) for the owned rows.  Localises the
     columns, exchanges the needed ranges and installs matrix + halo plan.  Returns (r0, r1).
     metric_rows(r0, r1) -> (rowptr, col_global, val) optionally installs the metric B of the
-    generalized problem; its remote columns must lie inside the matrix's halo.
+    generalized problem.
     lr_rows(r0, r1) -> dict(apb, amb, spd, smd = (rowptr, col_global, val), aa_diag, sigma_diag)
-    optionally installs the linear-response matrices under the same condition."""
+    optionally installs the linear-response matrices.
+    All installed matrices share ONE halo: its ranges are the union of what each of them
+    references on the other ranks."""
     r0, r1 = partition.row_range(n, rank, world)
     rowptr, col, val, diag = gen_rows(r0, r1)
     if world == 1:
@@ -49,18 +51,23 @@ def install_partitioned(gen_rows, n: int, rank: int, world: int, dist=None, metr
             lr = lr_rows(r0, r1)
             set_lr(lr["apb"], lr["amb"], lr["spd"], lr["smd"], lr["aa_diag"], lr["sigma_diag"])
         return r0, r1
-    needed = partition.needed_ranges(col, n, rank, world)
+    metric = metric_rows(r0, r1) if metric_rows is not None else None
+    lr = lr_rows(r0, r1) if lr_rows is not None else None
+    shared = [partition.needed_ranges(col, n, rank, world)]
+    if metric is not None:
+        shared.append(partition.needed_ranges(metric[1], n, rank, world))
+    if lr is not None:
+        shared += [partition.needed_ranges(lr[k][1], n, rank, world) for k in ("apb", "amb", "spd", "smd")]
+    needed = partition.union_ranges(*shared)
     all_needed = [None] * world
     dist.all_gather_object(all_needed, needed)
     col_loc, n_halo, recv = partition.localize(col, n, rank, world, needed)
     plan = partition.halo_plan(recv, all_needed, n, rank, world)
     set_csr(rowptr, col_loc, val, diag, n_halo=n_halo, halo_plan=plan)
-    if metric_rows is not None:
-        b_rowptr, b_col, b_val = metric_rows(r0, r1)
-        b_loc, _, _ = partition.localize(b_col, n, rank, world, needed)
-        set_csr_b(b_rowptr, b_loc, b_val, n_halo=n_halo)
-    if lr_rows is not None:
-        lr = lr_rows(r0, r1)
+    if metric is not None:
+        b_loc, _, _ = partition.localize(metric[1], n, rank, world, needed)
+        set_csr_b(metric[0], b_loc, metric[2], n_halo=n_halo)
+    if lr is not None:
         loc = {k: (lr[k][0], partition.localize(lr[k][1], n, rank, world, needed)[0], lr[k][2])
                for k in ("apb", "amb", "spd", "smd")}
         set_lr(loc["apb"], loc["amb"], loc["spd"], loc["smd"], lr["aa_diag"], lr["sigma_diag"], n_halo=n_halo)

@@ -41,14 +41,26 @@ def needed_ranges(col, n: int, rank: int, size: int):
     return out
 
 
+def union_ranges(*needed_lists):
+    """Element-wise union of several `needed_ranges` results (one per matrix sharing a halo):
+    the smallest range per peer that covers all of them."""
+    out = []
+    for per_peer in zip(*needed_lists):
+        rgs = [rg for rg in per_peer if rg is not None]
+        out.append(None if not rgs else (min(r[0] for r in rgs), max(r[1] for r in rgs)))
+    return out
+
+
 def localize(col, n: int, rank: int, size: int, needed=None):
     """Map global column indices to local ones.  Returns (col_local int32, n_halo, recv) where
-    recv = [(q, lo, hi, halo_offset)] describes the halo layout."""
+    recv = [(q, lo, hi, halo_offset)] describes the halo layout.  Every column must be owned or
+    lie inside one of the `needed` ranges (ValueError otherwise: a column outside the halo would
+    be gathered from an arbitrary address on the device)."""
     col = np.asarray(col, dtype=np.int64)
     r0, r1 = row_range(n, rank, size)
     n_loc = r1 - r0
     needed = needed_ranges(col, n, rank, size) if needed is None else needed
-    out = np.empty(col.shape, dtype=np.int64)
+    out = np.full(col.shape, -1, dtype=np.int64)
     own = (col >= r0) & (col < r1)
     out[own] = col[own] - r0
     off = 0
@@ -61,6 +73,12 @@ def localize(col, n: int, rank: int, size: int, needed=None):
         out[sel] = n_loc + off + (col[sel] - lo)
         recv.append((q, lo, hi, off))
         off += hi - lo
+    if out.size and out.min() < 0:
+        bad = col[out < 0]
+        raise ValueError(f"rank {rank}: {bad.size} column indices (e.g. {int(bad[0])}) are neither owned nor inside the "
+                         f"halo ranges {needed}; build the ranges from the union of all matrices that share the halo")
+    if n_loc + off > np.iinfo(np.int32).max:
+        raise ValueError("local column space (owned rows + halo) exceeds int32")
     return out.astype(np.int32), off, recv
 
 

@@ -1,5 +1,6 @@
 """CPU tests of the stateless problem generators."""
 import numpy as np
+import pytest
 
 from diaglib_b200 import partition, problems as P
 
@@ -92,3 +93,25 @@ def test_partition_localize_roundtrip():
             want = needed_all[q][r]
             if want is not None:
                 assert s0[i] + r0 == want[0] and sc[i] == want[1] - want[0]
+
+
+def test_localize_rejects_columns_outside_the_halo_and_union_covers_them():
+    """a second matrix (metric, linear-response) whose remote columns reach beyond the first
+    matrix's halo: localising it with the first matrix's ranges must fail loudly; with the
+    union of both it must succeed and address the shared halo consistently"""
+    n, size, rank = 512, 4, 1
+    r0, r1 = partition.row_range(n, rank, size)
+    _, c_a, _, _ = P.lap3d(8, 8, 8, r0, r1)                    # reaches one z-plane (64 rows) into the neighbours
+    c_b = np.concatenate([c_a, np.array([r0 - 100, r1 + 99], dtype=c_a.dtype)])   # reaches 100 rows
+    need_a = partition.needed_ranges(c_a, n, rank, size)
+    need_b = partition.needed_ranges(c_b, n, rank, size)
+    with pytest.raises(ValueError):
+        partition.localize(c_b, n, rank, size, need_a)
+    need = partition.union_ranges(need_a, need_b)
+    assert need[rank] is None and need[0] == (r0 - 100, r0) and need[2] == (r1, r1 + 100)
+    la, halo_a, recv_a = partition.localize(c_a, n, rank, size, need)
+    lb, halo_b, recv_b = partition.localize(c_b, n, rank, size, need)
+    assert halo_a == halo_b == 200 and recv_a == recv_b
+    # the same global column maps to the same local index through either matrix
+    assert np.array_equal(la, lb[:len(la)])
+    assert lb[-2] == (r1 - r0) + 0 and lb[-1] == (r1 - r0) + 100 + 99
