@@ -215,6 +215,7 @@ def run_reference(args, rank):
               "max_iter": MAX_ITER, "ok": bool(r["ok"]), "iterations": its, "wall_s": wall, "threads": nthr,
               "eig": [float(x) for x in r["eig"]], "rms": [float(x) for x in r["rms"][-1]],
               "max": [float(x) for x in r["max"][-1]], "n_act": [int(x) for x in r["n_act"]],
+              "hist_rms_max": [float(x[:N_TARG].max()) for x in r["rms"]], "hist_max_max": [float(x[:N_TARG].max()) for x in r["max"]],
               "timers_s": {k: float(v) for k, v in r["timers"].items()}, "blas": O.blas_config(),
               "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())}
     try:
@@ -238,6 +239,172 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# =============================================================================================
+# --workload c4: BASELINE.json configs[3] as specified (SURVEY 8d "C4"): FCI-like Hamiltonian,
+# n = 2^bits (26 = "64M") rows, 101 entries per row at i +- s_k with 50 seeded strides <= 2^20,
+# int64 row pointers, 16 roots of 21, Davidson-Liu, max_dav = 10 (lda = 210), tol 1e-8, rows
+# block-partitioned over the ranks with a bounded nearest-neighbour halo.  The matrix is generated
+# in HBM (10 GB per rank at 2^26 on 8 ranks) by the same arithmetic as problems.fci_like
+# (tests/test_gpu_kernels.py::test_gen_fci_on_device_matches_the_host_generator).
+# At bits = 22 the result is compared with the CPU oracle's solve of the same problem
+# (tests/golden/c4_oracle_n22.json, written by tools/c4_oracle.py).
+# =============================================================================================
+C4_N_TARG, C4_N_MAX, C4_MAX_DAV, C4_STRIDES, C4_BAND, C4_DELTA, C4_NOISE = 16, 21, 10, 50, 1 << 20, 0.1, 0.1
+
+
+def run_c4(args, rank, world, local):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import diaglib_b200 as D
+    from diaglib_b200 import dist as DD, kernels as K, partition
+
+    torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D.init(local)
+    DD.init_comm(dist if world > 1 else None)
+    lib = D.lib()
+    bits = args.bits
+    n = 1 << bits
+    t_setup = time.time()
+    strides = P.fci_strides(C4_STRIDES, min(C4_BAND, max(1, n // 2)), 1).astype(np.int64)
+    smax = int(strides[-1])
+    r0, r1 = partition.row_range(n, rank, world)
+    n_loc = r1 - r0
+    assert world == 1 or n_loc >= smax, "the row blocks must be at least one bandwidth long (nearest-neighbour halo)"
+    lo_prev = r0 - smax if rank > 0 else r0
+    hi_next = r1 + smax if rank < world - 1 else r1
+    rows = np.arange(r0, r1, dtype=np.int64)
+    counts = 1 + np.searchsorted(strides, rows, side="right") + np.searchsorted(strides, n - 1 - rows, side="right")
+    rowptr = np.zeros(n_loc + 1, dtype=np.int64)
+    np.cumsum(counts, out=rowptr[1:])
+    nnz = int(rowptr[-1])
+    d_rp, d_col = K.DeviceArray((n_loc + 1, 1)), K.DeviceArray(((nnz + 1) // 2 + 1, 1))
+    d_val, d_diag = K.DeviceArray((nnz, 1)), K.DeviceArray((n_loc, 1))
+    lib.diaglib_b200_h2d(d_rp.ptr, rowptr.ctypes.data_as(C.c_void_p), rowptr.nbytes)
+    rc = lib.diaglib_b200_k_gen_fci(n, r0, r1, len(strides), strides.ctypes.data_as(C.c_void_p), C4_DELTA, 1, lo_prev, hi_next,
+                                    C.c_void_p(d_rp.ptr), C.c_void_p(d_col.ptr), C.c_void_p(d_val.ptr), C.c_void_p(d_diag.ptr))
+    assert rc == 0
+    n_halo = (r0 - lo_prev) + (hi_next - r1)
+    plan = None
+    if world > 1:
+        peer, s0, sc, ro, rcv = [], [], [], [], []
+        if rank > 0:            # previous rank: it needs our first smax rows, we need its last smax rows
+            peer.append(rank - 1); s0.append(0); sc.append(smax); ro.append(0); rcv.append(r0 - lo_prev)
+        if rank < world - 1:
+            peer.append(rank + 1); s0.append(n_loc - smax); sc.append(smax); ro.append(r0 - lo_prev); rcv.append(hi_next - r1)
+        plan = (np.array(peer, np.int32), np.array(s0, np.int64), np.array(sc, np.int64), np.array(ro, np.int64),
+                np.array(rcv, np.int64))
+    D.set_csr_device(n_loc, n_halo, nnz, d_rp.ptr, d_col.ptr, d_val.ptr, d_diag.ptr, halo_plan=plan)
+    # start vectors: unit vectors on the 21 lowest diagonal entries (d_i = 1 + Delta pi(i): the rows with
+    # pi(i) = 0..20) + 10 % noise, as tools/c4_oracle.py
+    pi = P.bijection(rows, bits, 1)
+    guess = P.guess(n, C4_N_MAX, r0, r1) * (C4_NOISE / np.sqrt(n / 12.0))
+    hit = np.nonzero(pi < C4_N_MAX)[0]
+    guess[hit, pi[hit].astype(np.int64)] += 1.0
+    del rows, counts, pi
+    d_guess = K.DeviceArray.from_numpy(guess)
+    d_evec = K.DeviceArray((n_loc, C4_N_MAX))
+    blk_bytes = guess.nbytes
+    del guess
+    t_setup = time.time() - t_setup
+    eig = np.zeros(C4_N_MAX)
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def solve():
+        lib.diaglib_b200_d2d(d_evec.ptr, d_guess.ptr, blk_bytes)
+        lib.diaglib_b200_sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        K.timer_start()
+        ok = D.davidson_driver(False, n_loc, C4_N_TARG, C4_N_MAX, 100, TOL, C4_MAX_DAV, 0.0, None, None, eig, d_evec)
+        return ok, K.timer_stop_ms()
+
+    for _ in range(args.warmup):
+        ok, ms = solve()
+        assert ok, "C4 warm-up solve did not converge"
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    tot_ms, tot_its, launches = 0.0, 0, 0
+    for _ in range(args.steps):
+        ok, ms = solve()
+        assert ok
+        tot_ms += maxr(ms)
+        tot_its += len(D.last_history(C4_N_MAX)["it"])
+        launches += D.last_stats()["launches"]
+    clocks = sampler.stop() if rank == 0 else None
+    hist, timers, stats = D.last_history(C4_N_MAX), D.last_timers(), D.last_stats()
+    # independent residual of the returned pairs: r = A x - theta x with one more product (all ranks)
+    norms = np.zeros(2 * C4_N_TARG)
+    th = np.ascontiguousarray(eig[:C4_N_TARG])
+    rc = lib.diaglib_b200_k_true_residual(n_loc, C4_N_TARG, C.c_void_p(d_evec.ptr), th.ctypes.data_as(C.c_void_p),
+                                          norms.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    true_rms = float(np.sqrt(norms[:C4_N_TARG] / n).max())
+    true_max = float(norms[C4_N_TARG:].max())
+    # one timed block matvec at the iteration's width (halo exchange included)
+    i32 = lambda v_: C.byref(C.c_int32(int(v_)))  # noqa: E731
+    y = K.DeviceArray((n_loc, C4_N_MAX))
+    for _ in range(2):
+        lib.diaglib_b200_csr_matvec(i32(n_loc), i32(C4_N_MAX), C.c_void_p(d_guess.ptr), C.c_void_p(y.ptr))
+    lib.diaglib_b200_sync()
+    K.timer_start()
+    for _ in range(5):
+        lib.diaglib_b200_csr_matvec(i32(n_loc), i32(C4_N_MAX), C.c_void_p(d_guess.ptr), C.c_void_p(y.ptr))
+    mv_ms = maxr(K.timer_stop_ms() / 5)
+    parity = None
+    gold_path = os.path.join(ROOT, "tests", "golden", f"c4_oracle_n{bits}.json")
+    if rank == 0 and os.path.exists(gold_path):
+        gold = json.load(open(gold_path))
+        eo, eg = np.array(gold["eig"][:C4_N_TARG]), eig[:C4_N_TARG]
+        rel = float(np.max(np.abs(eg - eo) / np.abs(eo)))
+        its = len(hist["it"])
+        parity = {"oracle_source": os.path.relpath(gold_path, ROOT), "its_gpu": its, "its_oracle": gold["iterations"],
+                  "max_rel_eig_err": rel, "ok": bool(rel <= 1e-10 and abs(its - gold["iterations"]) <= 1 and gold["ok"])}
+    if rank == 0:
+        ms_per_step = tot_ms / args.steps
+        line = {
+            "metric": "davidson_iters_per_s", "value": tot_its / (tot_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4 fci_like n=2^{bits}={n} nnz/row=101 strides<=2^20 n_targ={C4_N_TARG} n_max={C4_N_MAX} "
+                                   f"max_dav={C4_MAX_DAV} (lda={C4_MAX_DAV * C4_N_MAX}) Davidson-Liu tol={TOL} (BASELINE.json configs[3])",
+                       "guess": "lowest-diag unit + 10% noise", "rowptr": "int64", "col": "int32 local numbering",
+                       "bandwidth": smax, "l2": "inputs larger than L2"},
+            "time_to_converge_s": ms_per_step * 1e-3, "iterations": tot_its / args.steps, "converged": True,
+            "rows_per_gpu": n_loc, "nnz_per_gpu": nnz, "csr_bytes_per_gpu": int(12 * nnz + 8 * (n_loc + 1) + 8 * n_loc),
+            "halo_rows_per_gpu": int(n_halo), "halo_bytes_per_matvec_per_gpu": int(8 * n_halo * C4_N_MAX),
+            "matvec_ms_m21": mv_ms, "setup_s": round(t_setup, 1),
+            "recurrence_rms_residual_max": float(hist["rms"][-1][:C4_N_TARG].max()),
+            "true_rms_residual_max": true_rms, "true_max_residual": true_max,
+            "eig": [float(x) for x in eig[:C4_N_TARG]], "parity": parity, "gpu_launches": int(launches), "clocks": clocks,
+            "phases_s": {k: round(float(v), 5) for k, v in timers.items()}, "stats": stats,
+        }
+        print(json.dumps(line), flush=True)
+    ok_res = true_rms < 2 * TOL and true_max < 20 * TOL
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    D.set_csr(np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0), np.zeros(0))   # drop the adopted device arrays
+    if rank == 0 and (not ok_res or (parity is not None and not parity["ok"])):
+        print(f"bench.py: C4 CHECK FAILED: true_rms={true_rms} true_max={true_max} parity={parity}", file=sys.stderr)
+        sys.exit(3)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,6 +413,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--nx", type=int, default=256, help="grid edge (n = nx^3); 256 is the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4"],
+                    help="c3 = the headline LOBPCG workload (default); c4 = FCI-like Davidson run (BASELINE.json configs[3])")
+    ap.add_argument("--bits", type=int, default=26, help="c4: n = 2^bits rows (26 = the specified 64M; 22 has an oracle fixture)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -253,6 +423,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload == "c4":
+        run_c4(args, rank, world, local)
         return
 
     import torch

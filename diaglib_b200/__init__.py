@@ -24,6 +24,9 @@ from .api import (  # noqa: F401
     ortho_vs_x,
     set_csr,
     set_csr_b,
+    set_csr_device,
+    set_csr_row_order,
+    set_halo,
     last_history,
     last_stats,
     last_timers,

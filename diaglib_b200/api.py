@@ -60,6 +60,11 @@ def lib():
         L.diaglib_b200_timer_stop_ms.restype = C.c_double
         L.diaglib_b200_set_csr.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.diaglib_b200_set_csr_b.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.diaglib_b200_set_csr_device.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.diaglib_b200_set_csr_row_order.argtypes = [C.c_void_p]
+        L.diaglib_b200_k_gen_fci.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_double, C.c_int64,
+                                             C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.diaglib_b200_k_true_residual.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.diaglib_b200_set_csr_lr.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.diaglib_b200_set_lr_diag.argtypes = [C.c_int64, C.c_void_p, C.c_void_p]
         L.diaglib_b200_set_halo.argtypes = [C.c_int32] + [C.c_void_p] * 5
@@ -139,7 +144,26 @@ def _callback(cb, kind):
     return C.cast(f, C.c_void_p)
 
 
-def set_csr(rowptr, col, val, diag, n_halo: int = 0, halo_plan=None) -> None:
+def set_halo(halo_plan) -> None:
+    """halo_plan = (peer, send_row0, send_cnt, recv_off, recv_cnt), see diaglib_b200/partition.py"""
+    peer, s0, sc, ro, rc = halo_plan
+    peer = np.ascontiguousarray(peer, dtype=np.int32)
+    arrs = [np.ascontiguousarray(a, dtype=np.int64) for a in (s0, sc, ro, rc)]
+    _check(lib().diaglib_b200_set_halo(len(peer), _ptr(peer), *[_ptr(a) for a in arrs]), "set_halo")
+
+
+def set_csr_row_order(order) -> None:
+    """Processing order of the local rows in the built-in matvec (a permutation; None = natural).
+    Results do not depend on it; a locality-preserving order (problems.tile_order_3d for grid
+    stencils) raises the cache hit rate of the gathers."""
+    if order is None:
+        _check(lib().diaglib_b200_set_csr_row_order(None), "set_csr_row_order")
+        return
+    order = np.ascontiguousarray(order, dtype=np.int32)
+    _check(lib().diaglib_b200_set_csr_row_order(_ptr(order)), "set_csr_row_order")
+
+
+def set_csr(rowptr, col, val, diag, n_halo: int = 0, halo_plan=None, row_order=None) -> None:
     """Install the local rows of the matrix used by the built-in callbacks (the reference keeps
     its matrix in a module global too: utils.f90:4, main.f90:73).  Column indices are local
     (see include/diaglib_b200.h); halo_plan = (peer, send_row0, send_cnt, recv_off, recv_cnt)."""
@@ -150,10 +174,18 @@ def set_csr(rowptr, col, val, diag, n_halo: int = 0, halo_plan=None) -> None:
     n_loc = len(rowptr) - 1
     _check(lib().diaglib_b200_set_csr(n_loc, int(n_halo), _ptr(rowptr), _ptr(col), _ptr(val), _ptr(diag)), "set_csr")
     if halo_plan is not None:
-        peer, s0, sc, ro, rc = halo_plan
-        peer = np.ascontiguousarray(peer, dtype=np.int32)
-        arrs = [np.ascontiguousarray(a, dtype=np.int64) for a in (s0, sc, ro, rc)]
-        _check(lib().diaglib_b200_set_halo(len(peer), _ptr(peer), *[_ptr(a) for a in arrs]), "set_halo")
+        set_halo(halo_plan)
+    if row_order is not None:
+        set_csr_row_order(row_order)
+
+
+def set_csr_device(n_loc: int, n_halo: int, nnz: int, rowptr_dev: int, col_dev: int, val_dev: int, diag_dev: int,
+                   halo_plan=None) -> None:
+    """set_csr for arrays that already live in HBM (raw device addresses; the caller keeps them alive)."""
+    _check(lib().diaglib_b200_set_csr_device(int(n_loc), int(n_halo), int(nnz), C.c_void_p(rowptr_dev), C.c_void_p(col_dev),
+                                             C.c_void_p(val_dev), C.c_void_p(diag_dev)), "set_csr_device")
+    if halo_plan is not None:
+        set_halo(halo_plan)
 
 
 def set_csr_b(rowptr, col, val, n_halo: int = 0) -> None:
@@ -287,4 +319,4 @@ def last_stats():
     s = np.zeros(8, np.int64)
     lib().diaglib_b200_stats(_ptr(s))
     return dict(ortho_cd_passes=int(s[0]), ortho_vs_x_sweeps=int(s[1]), qr_fallbacks=int(s[2]), chol_shifts=int(s[3]),
-                launches=int(s[4]), launches_total=int(s[5]))
+                launches=int(s[4]), launches_total=int(s[5]), host_syncs=int(s[6]))

@@ -58,6 +58,7 @@ struct NcclApi {
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclCommSplit) CommSplit = nullptr;   // optional (NCCL >= 2.18): second communicator for the halo stream
   bool load() {
     if (handle) return true;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -72,6 +73,7 @@ struct NcclApi {
     DLB_SYM(GetUniqueId) DLB_SYM(CommInitRank) DLB_SYM(CommDestroy) DLB_SYM(AllReduce) DLB_SYM(AllGather)
     DLB_SYM(Send) DLB_SYM(Recv) DLB_SYM(GroupStart) DLB_SYM(GroupEnd) DLB_SYM(GetErrorString)
 #undef DLB_SYM
+    CommSplit = reinterpret_cast<decltype(CommSplit)>(dlsym(handle, "ncclCommSplit"));
     return true;
   }
 };
@@ -104,6 +106,12 @@ struct Engine {
   NcclApi nccl;
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  // halo exchange of the built-in matvec: own stream + own communicator, so that it overlaps
+  // the rows that do not touch the halo (null: exchange on the main stream, no overlap)
+  ncclComm_t comm_halo = nullptr;
+  cudaStream_t st_halo = nullptr;
+  cudaEvent_t ev_x = nullptr, ev_halo = nullptr;
+  int64_t st_syncs = 0;   // host <- device synchronisations of the last driver call
 
   DevBuf partial, smallws, resid_scratch, scal;
   // driver workspaces, cached across calls (the reference allocates per call, 251-276 / 1600-1618;
@@ -119,7 +127,8 @@ struct Engine {
 
   // installed matrix + halo plan (built-in callbacks)
   CsrDevice A;
-  DevBuf b_rowptr, b_col, b_val, b_diag, b_send, b_recv, b_halo;
+  DevBuf b_rowptr, b_col, b_val, b_diag, b_send, b_recv, b_halo, b_order;
+  bool csr_adopted = false;   // rowptr/col/val/diag belong to the caller (diaglib_b200_set_csr_device)
   DevBuf bb_rowptr, bb_col, bb_val;   // metric B of the generalized problem (built-in bvec)
   CsrDevice B;
   DevBuf lr_rowptr[4], lr_col[4], lr_val[4], lr_aa, lr_sg;   // linear-response matrices (A+B, A-B, S+D, S-D) and diagonals
@@ -179,6 +188,7 @@ struct Engine {
   }
   void sync() {
     DLB_CUDA_CHECK(cudaStreamSynchronize(st));
+    ++st_syncs;
     ph_resolve();
   }
 
@@ -405,7 +415,10 @@ struct Engine {
     }
   }
 
-  void halo_exchange(int m, const double* x, int64_t ldx);
+  void halo_exchange(int m, const double* x, int64_t ldx, cudaStream_t s, ncclComm_t c);
+  void halo_exchange(int m, const double* x, int64_t ldx) { halo_exchange(m, x, ldx, st, comm); }
+  void csr_matvec(int m, const double* x, double* ax);
+  int install_row_order(const int32_t* user_order);
   void caslr_eff(bool verbose, int n, int n2, int n_targ, int n_max, int max_iter, double tol, int max_dav,
                  diaglib_matvec_t apbmul, diaglib_matvec_t ambmul, diaglib_matvec_t spdmul, diaglib_matvec_t smdmul,
                  diaglib_lrprec_t lrprec, double* eig, double* evec, int32_t* ok);
@@ -421,6 +434,7 @@ struct Engine {
     msg.clear();
     hist.clear(n_max);
     st_cd_passes = st_sweeps = st_qr = st_shifts = 0;
+    st_syncs = 0;
     st_launch0 = g_launches;
     for (double& t : t_acc) t = 0;
   }
@@ -596,6 +610,13 @@ void Engine::lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, in
   h = ph_open(PH_MV);
   { int32_t m32 = n_max; matvec(&n32, &m32, space, aspace); }                          // 309
   ph_close(h);
+  if (status) {   // a callback refused its arguments (e.g. no matrix installed for this n)
+    ph_close(ph_tot);
+    sync();
+    cleanup();
+    end_call();
+    return;
+  }
   if (shift != 0.0) block_axpy(st, nn, n_max, shift, space, nn, aspace, nn);           // 312
   h = ph_open(PH_GRAM);
   kgram(nn, space, nn, n_max, aspace, nn, n_max, a_red, n_max, true);  // 313
@@ -873,6 +894,7 @@ void Engine::davidson(bool verbose, bool gen, int n, int n_targ, int n_max, int 
     h = ph_open(PH_MV);
     { int32_t m32 = n_act; matvec(&n32, &m32, COL(space, c1), COL(aspace, c1)); }       // 1685
     ph_close(h);
+    if (status) break;   // a callback refused its arguments
     h = ph_open(PH_GRAM);
     double* a_blk = a_red + (size_t)lda * (c1 - 1);
     kgram(nn, space, nn, ldu, COL(aspace, c1), nn, n_act, a_blk, lda, false);  // 1691
@@ -1230,12 +1252,16 @@ void Engine::caslr_eff(bool verbose, int n, int n2, int n_targ, int n_max, int m
 }
 
 // ---- halo exchange for the built-in CSR matvec ------------------------------------------
-void Engine::halo_exchange(int m, const double* x, int64_t ldx) {
-  if (nranks == 1 || A.n_halo == 0 || peer.empty()) return;
+// A rank takes part when the plan has anything to send OR to receive (a rank that references no
+// remote column may still own rows its neighbours need).
+void Engine::halo_exchange(int m, const double* x, int64_t ldx, cudaStream_t s, ncclComm_t c) {
+  if (nranks == 1 || peer.empty()) return;
   int64_t tot_send = 0, tot_recv = 0;
   for (size_t i = 0; i < peer.size(); ++i) { tot_send += send_cnt[i]; tot_recv += recv_cnt[i]; }
-  if (!b_send.ensure((size_t)tot_send * m * sizeof(double)) || !b_recv.ensure((size_t)tot_recv * m * sizeof(double)) ||
-      !b_halo.ensure((size_t)A.n_halo * m * sizeof(double))) {
+  if (tot_send == 0 && tot_recv == 0) return;
+  if (!b_send.ensure((size_t)std::max<int64_t>(tot_send, 1) * m * sizeof(double)) ||
+      !b_recv.ensure((size_t)std::max<int64_t>(tot_recv, 1) * m * sizeof(double)) ||
+      !b_halo.ensure((size_t)std::max<int64_t>(A.n_halo, 1) * m * sizeof(double))) {
     fail(DIAGLIB_B200_EALLOC, "memory allocation failed. (halo buffers)");
     return;
   }
@@ -1243,15 +1269,15 @@ void Engine::halo_exchange(int m, const double* x, int64_t ldx) {
   double* rb = b_recv.as<double>();
   int64_t so = 0;
   for (size_t i = 0; i < peer.size(); ++i) {
-    pack_rows(st, send_row0[i], send_cnt[i], m, x, ldx, sb + so * m);
+    pack_rows(s, send_row0[i], send_cnt[i], m, x, ldx, sb + so * m);
     so += send_cnt[i];
   }
   nccl_ok(nccl.GroupStart(), "GroupStart");
   so = 0;
   int64_t ro = 0;
   for (size_t i = 0; i < peer.size(); ++i) {
-    if (send_cnt[i] > 0) nccl_ok(nccl.Send(sb + so * m, (size_t)send_cnt[i] * m, ncclDouble, peer[i], comm, st), "Send");
-    if (recv_cnt[i] > 0) nccl_ok(nccl.Recv(rb + ro * m, (size_t)recv_cnt[i] * m, ncclDouble, peer[i], comm, st), "Recv");
+    if (send_cnt[i] > 0) nccl_ok(nccl.Send(sb + so * m, (size_t)send_cnt[i] * m, ncclDouble, peer[i], c, s), "Send");
+    if (recv_cnt[i] > 0) nccl_ok(nccl.Recv(rb + ro * m, (size_t)recv_cnt[i] * m, ncclDouble, peer[i], c, s), "Recv");
     so += send_cnt[i];
     ro += recv_cnt[i];
   }
@@ -1262,9 +1288,87 @@ void Engine::halo_exchange(int m, const double* x, int64_t ldx) {
     if (recv_cnt[i] > 0)
       DLB_CUDA_CHECK(cudaMemcpy2DAsync(hb + recv_off[i], sizeof(double) * A.n_halo, rb + ro * m,
                                        sizeof(double) * recv_cnt[i], sizeof(double) * recv_cnt[i], m,
-                                       cudaMemcpyDeviceToDevice, st));
+                                       cudaMemcpyDeviceToDevice, s));
     ro += recv_cnt[i];
   }
+}
+
+// built-in matvec(n,m,x,ax): AX = A X on the installed CSR matrix.  With a halo the exchange runs
+// on its own stream and communicator while the rows without halo columns are multiplied; the
+// rows that touch the halo follow once it has arrived.
+void Engine::csr_matvec(int m, const double* x, double* ax) {
+  const int64_t n = A.n;
+  const bool split = nranks > 1 && !peer.empty() && A.order && st_halo && comm_halo;
+  if (!split) {
+    halo_exchange(m, x, n);
+    spmm_csr(st, A, m, x, n, b_halo.as<double>(), ax, n, 0.0, SPMM_ALL);
+    return;
+  }
+  DLB_CUDA_CHECK(cudaEventRecord(ev_x, st));            // x is final; the previous boundary rows are done with b_halo
+  DLB_CUDA_CHECK(cudaStreamWaitEvent(st_halo, ev_x, 0));
+  halo_exchange(m, x, n, st_halo, comm_halo);
+  DLB_CUDA_CHECK(cudaEventRecord(ev_halo, st_halo));
+  spmm_csr(st, A, m, x, n, b_halo.as<double>(), ax, n, 0.0, SPMM_INTERIOR);
+  DLB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_halo, 0));
+  spmm_csr(st, A, m, x, n, b_halo.as<double>(), ax, n, 0.0, SPMM_BOUNDARY);
+}
+
+// flags[i] = 1 when row i of the CSR matrix references a halo column (col >= n)
+__global__ void row_touches_halo_kernel(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                        uint8_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t f = 0;
+  for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+    if (col[k] >= n) { f = 1; break; }
+  flags[i] = f;
+}
+
+// Processing order of the rows of the installed matrix: the caller's order (or the natural one),
+// stably partitioned into rows without halo columns followed by rows with them.
+int Engine::install_row_order(const int32_t* user_order) {
+  const int64_t n = A.n;
+  A.order = nullptr;
+  A.n_interior = A.n_halo == 0 ? n : 0;
+  A.tiled = false;
+  if (n <= 0 || n > INT32_MAX) return DIAGLIB_B200_OK;
+  if (!user_order && A.n_halo == 0) return DIAGLIB_B200_OK;          // natural order, nothing to split
+  std::vector<uint8_t> touches((size_t)n, 0);
+  if (A.n_halo > 0) {
+    DevBuf flags;
+    if (!flags.ensure((size_t)n)) return DIAGLIB_B200_EALLOC;
+    row_touches_halo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, A.rowptr, A.col, flags.as<uint8_t>());
+    DLB_CUDA_CHECK(cudaMemcpyAsync(touches.data(), flags.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    DLB_CUDA_CHECK(cudaStreamSynchronize(st));
+    flags.release();
+  }
+  if (user_order) {
+    std::vector<uint8_t> seen((size_t)n, 0);
+    for (int64_t i = 0; i < n; ++i) {
+      const int32_t r = user_order[i];
+      if (r < 0 || r >= n || seen[r]) {
+        status = 0;
+        fail(DIAGLIB_B200_EARG, "set_csr_row_order: the order is not a permutation of the local rows");
+        return DIAGLIB_B200_EARG;
+      }
+      seen[r] = 1;
+    }
+  }
+  std::vector<int32_t> ord((size_t)n);
+  int64_t w = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int64_t i = 0; i < n; ++i) {
+      const int32_t r = user_order ? user_order[i] : (int32_t)i;
+      if (touches[r] == pass) ord[w++] = r;
+    }
+    if (pass == 0) A.n_interior = w;
+  }
+  if (!b_order.ensure((size_t)n * sizeof(int32_t))) return DIAGLIB_B200_EALLOC;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(b_order.p, ord.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  DLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  A.order = b_order.as<int32_t>();
+  A.tiled = user_order != nullptr;
+  return DIAGLIB_B200_OK;
 }
 
 // stages a host block through HBM for the standalone ortho entry points
@@ -1273,14 +1377,21 @@ struct Staged {
   double* host = nullptr;
   size_t bytes = 0;
   bool owned = false;
+  bool ok = true;   // false: the staging allocation failed (status = DIAGLIB_B200_EALLOC), nothing may run
   Staged(const double* p, size_t b) : host(const_cast<double*>(p)), bytes(b) {
     if (is_device_ptr(p)) { dev = host; return; }
     owned = true;
-    DLB_CUDA_CHECK(cudaMalloc(&dev, std::max<size_t>(bytes, 8)));
+    if (cudaMalloc(&dev, std::max<size_t>(bytes, 8)) != cudaSuccess) {
+      cudaGetLastError();
+      dev = nullptr;
+      ok = false;
+      g.fail(DIAGLIB_B200_EALLOC, "memory allocation failed. (staging a host block of %zu bytes)", bytes);
+      return;
+    }
     DLB_CUDA_CHECK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, g.st));
   }
-  void back() { if (owned) DLB_CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, g.st)); }
-  ~Staged() { if (owned) { cudaStreamSynchronize(g.st); cudaFree(dev); } }
+  void back() { if (owned && ok) DLB_CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, g.st)); }
+  ~Staged() { if (owned && dev) { cudaStreamSynchronize(g.st); cudaFree(dev); } }
 };
 
 bool require_init() {
@@ -1301,6 +1412,12 @@ extern "C" {
 
 int32_t diaglib_b200_init(int32_t device) {
   if (g.inited && (device < 0 || device == g.device)) return DIAGLIB_B200_OK;
+  if (g.inited) {   // the stream, the pinned buffer and the kernels' cached attributes belong to the first device
+    g.status = 0;
+    g.fail(DIAGLIB_B200_EARG, "diaglib_b200_init: already bound to device %d; call diaglib_b200_finalize before binding device %d",
+           g.device, (int)device);
+    return DIAGLIB_B200_EARG;
+  }
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
     cudaGetLastError();
@@ -1345,8 +1462,11 @@ void diaglib_b200_finalize(void) {
   g.nranks = 1;
   g.rank = 0;
   g.release_workspace();
+  if (g.csr_adopted) { g.b_rowptr = DevBuf(); g.b_col = DevBuf(); g.b_val = DevBuf(); g.b_diag = DevBuf(); g.csr_adopted = false; }
+  if (g.comm_halo && g.nccl.CommDestroy) g.nccl.CommDestroy(g.comm_halo);
+  g.comm_halo = nullptr;
   for (DevBuf* b : {&g.partial, &g.smallws, &g.resid_scratch, &g.scal, &g.b_rowptr, &g.b_col, &g.b_val, &g.b_diag,
-                    &g.b_send, &g.b_recv, &g.b_halo, &g.bb_rowptr, &g.bb_col, &g.bb_val, &g.lr_aa, &g.lr_sg})
+                    &g.b_send, &g.b_recv, &g.b_halo, &g.b_order, &g.bb_rowptr, &g.bb_col, &g.bb_val, &g.lr_aa, &g.lr_sg})
     b->release();
   for (int i = 0; i < 4; ++i) { g.lr_rowptr[i].release(); g.lr_col[i].release(); g.lr_val[i].release(); g.LR[i] = CsrDevice(); }
   g.A = CsrDevice();
@@ -1493,6 +1613,7 @@ void diaglib_b200_ortho_cd(const int32_t* n, const int32_t* m, double* u, double
   g.begin_call(*m);
   g.ensure_small(*m, *m);
   Staged su(u, sizeof(double) * (size_t)*n * *m);
+  if (g.status || !su.ok) { g.end_call(); return; }
   double gr = 1.0;
   const bool okb = g.ortho_cd(*n, *m, su.dev, *n, gr);
   su.back();
@@ -1509,6 +1630,7 @@ void diaglib_b200_ortho_vs_x(const int32_t* n, const int32_t* m, const int32_t* 
   g.ensure_small(*k, *m);
   Staged sx(x, sizeof(double) * (size_t)*n * *m);
   Staged su(u, sizeof(double) * (size_t)*n * *k);
+  if (g.status || !sx.ok || !su.ok) { g.end_call(); return; }
   g.ortho_vs_x(*n, *m, *k, sx.dev, *n, su.dev, *n);
   su.back();
   g.sync();
@@ -1521,6 +1643,7 @@ void diaglib_b200_b_ortho(const int32_t* n, const int32_t* m, double* u, double*
   g.ensure_small(*m, *m);
   Staged su(u, sizeof(double) * (size_t)*n * *m);
   Staged sb(bu, sizeof(double) * (size_t)*n * *m);
+  if (g.status || !su.ok || !sb.ok) { g.end_call(); return; }
   g.b_ortho(*n, *m, su.dev, *n, sb.dev, *n);
   su.back();
   sb.back();
@@ -1536,6 +1659,7 @@ void diaglib_b200_b_ortho_vs_x(const int32_t* n, const int32_t* m, const int32_t
   Staged sx(x, sizeof(double) * (size_t)*n * *m);
   Staged sbx(bx, sizeof(double) * (size_t)*n * *m);
   Staged su(u, sizeof(double) * (size_t)*n * *k);
+  if (g.status || !sx.ok || !sbx.ok || !su.ok) { g.end_call(); return; }
   g.ortho_vs_x(*n, *m, *k, sx.dev, *n, su.dev, *n, sbx.dev);
   su.back();
   g.sync();
@@ -1546,6 +1670,7 @@ void diaglib_b200_ortho(const int32_t* n, const int32_t* m, double* u, double* /
   if (!require_init()) return;
   g.begin_call(*m);
   Staged su(u, sizeof(double) * (size_t)*n * *m);
+  if (g.status || !su.ok) { g.end_call(); return; }
   g.ortho_qr(*n, *m, su.dev, *n);
   su.back();
   g.sync();
@@ -1557,8 +1682,7 @@ void diaglib_b200_csr_matvec(const int32_t* n, const int32_t* m, const double* x
     g.fail(DIAGLIB_B200_EARG, "csr_matvec: no matrix installed for n = %d (diaglib_b200_set_csr)", *n);
     return;
   }
-  g.halo_exchange(*m, x, *n);
-  spmm_csr(g.st, g.A, *m, x, *n, g.b_halo.as<double>(), ax, *n, 0.0);
+  g.csr_matvec(*m, x, ax);
 }
 
 void diaglib_b200_diag_precnd(const int32_t* n, const int32_t* m, const double* shift, const double* x, double* px) {
@@ -1607,9 +1731,42 @@ int32_t diaglib_b200_set_csr_b(int64_t n_loc, int64_t n_halo, const int64_t* row
   return DIAGLIB_B200_OK;
 }
 
+// longest row of a device-resident CSR matrix
+__global__ void max_row_len_kernel(int64_t n, const int64_t* __restrict__ rowptr, int* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int len = i < n ? (int)min((int64_t)INT32_MAX, rowptr[i + 1] - rowptr[i]) : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out, len);
+}
+
+static int32_t finish_set_csr(int64_t n_loc, int64_t n_halo, int64_t nnz) {
+  g.A = CsrDevice();
+  g.A.n = n_loc;
+  g.A.nnz = nnz;
+  g.A.n_halo = n_halo;
+  g.A.rowptr = g.b_rowptr.as<int64_t>();
+  g.A.col = g.b_col.as<int32_t>();
+  g.A.val = g.b_val.as<double>();
+  g.A.diag = g.b_diag.as<double>();
+  g.peer.clear(); g.send_row0.clear(); g.send_cnt.clear(); g.recv_off.clear(); g.recv_cnt.clear();
+  if (n_loc > 0) {
+    if (!g.scal.ensure(64)) return DIAGLIB_B200_EALLOC;
+    int* d_max = g.scal.as<int>();
+    DLB_CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(int), g.st));
+    max_row_len_kernel<<<(unsigned)((n_loc + 255) / 256), 256, 0, g.st>>>(n_loc, g.A.rowptr, d_max);
+    int h_max = 0;
+    DLB_CUDA_CHECK(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, g.st));
+    DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
+    g.A.max_row_nnz = h_max;
+  }
+  return g.install_row_order(nullptr);
+}
+
 int32_t diaglib_b200_set_csr(int64_t n_loc, int64_t n_halo, const int64_t* rowptr, const int32_t* col,
                              const double* val, const double* diag) {
   if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  if (g.csr_adopted) { g.b_rowptr = DevBuf(); g.b_col = DevBuf(); g.b_val = DevBuf(); g.b_diag = DevBuf(); g.csr_adopted = false; }
   const int64_t nnz = rowptr[n_loc];
   if (!g.b_rowptr.ensure((n_loc + 1) * sizeof(int64_t)) || !g.b_col.ensure(std::max<int64_t>(nnz, 1) * sizeof(int32_t)) ||
       !g.b_val.ensure(std::max<int64_t>(nnz, 1) * sizeof(double)) || !g.b_diag.ensure(std::max<int64_t>(n_loc, 1) * sizeof(double)))
@@ -1619,18 +1776,36 @@ int32_t diaglib_b200_set_csr(int64_t n_loc, int64_t n_halo, const int64_t* rowpt
   DLB_CUDA_CHECK(cudaMemcpyAsync(g.b_val.p, val, nnz * sizeof(double), cudaMemcpyHostToDevice, g.st));
   DLB_CUDA_CHECK(cudaMemcpyAsync(g.b_diag.p, diag, n_loc * sizeof(double), cudaMemcpyHostToDevice, g.st));
   DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
-  g.A.n = n_loc;
-  g.A.nnz = nnz;
-  g.A.n_halo = n_halo;
-  int64_t longest = 0;
-  for (int64_t i = 0; i < n_loc; ++i) longest = std::max(longest, rowptr[i + 1] - rowptr[i]);
-  g.A.max_row_nnz = (int)std::min<int64_t>(longest, INT32_MAX);
-  g.A.rowptr = g.b_rowptr.as<int64_t>();
-  g.A.col = g.b_col.as<int32_t>();
-  g.A.val = g.b_val.as<double>();
-  g.A.diag = g.b_diag.as<double>();
-  g.peer.clear(); g.send_row0.clear(); g.send_cnt.clear(); g.recv_off.clear(); g.recv_cnt.clear();
-  return DIAGLIB_B200_OK;
+  return finish_set_csr(n_loc, n_halo, nnz);
+}
+
+// Same as set_csr for a matrix that already lives in HBM (the caller keeps ownership of the four
+// arrays and must keep them alive while the matrix is installed).
+int32_t diaglib_b200_set_csr_device(int64_t n_loc, int64_t n_halo, int64_t nnz, const int64_t* rowptr_dev, const int32_t* col_dev,
+                                    const double* val_dev, const double* diag_dev) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  if (!is_device_ptr(rowptr_dev) || !is_device_ptr(col_dev) || !is_device_ptr(val_dev) || !is_device_ptr(diag_dev)) {
+    g.status = 0;
+    g.fail(DIAGLIB_B200_EARG, "set_csr_device: all four arrays must be device pointers");
+    return DIAGLIB_B200_EARG;
+  }
+  if (!g.csr_adopted) { g.b_rowptr.release(); g.b_col.release(); g.b_val.release(); g.b_diag.release(); }
+  g.b_rowptr = DevBuf(); g.b_col = DevBuf(); g.b_val = DevBuf(); g.b_diag = DevBuf();
+  g.b_rowptr.p = const_cast<int64_t*>(rowptr_dev);
+  g.b_col.p = const_cast<int32_t*>(col_dev);
+  g.b_val.p = const_cast<double*>(val_dev);
+  g.b_diag.p = const_cast<double*>(diag_dev);
+  g.csr_adopted = true;
+  return finish_set_csr(n_loc, n_halo, nnz);
+}
+
+// Processing order of the local rows in the built-in matvec (a permutation of [0, n_loc); null
+// restores the natural order).  An order that keeps the rows of a stencil's neighbourhood
+// together (tiles of the grid along a space-filling curve) raises the L1/L2 hit rate of the
+// gathers; results do not depend on it (every row sum is formed the same way).
+int32_t diaglib_b200_set_csr_row_order(const int32_t* order) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  return g.install_row_order(order);
 }
 
 int32_t diaglib_b200_set_halo(int32_t n_nbr, const int32_t* peer, const int64_t* send_row0, const int64_t* send_cnt,
@@ -1657,12 +1832,27 @@ int32_t diaglib_b200_comm_init(int32_t rank, int32_t nranks, const void* uid) {
   if (!g.nccl.load()) { g.fail(DIAGLIB_B200_ECOMM, "cannot load libnccl.so.2"); return DIAGLIB_B200_ECOMM; }
   ncclUniqueId id;
   std::memcpy(&id, uid, sizeof id);
+  if (g.comm_halo) { g.nccl.CommDestroy(g.comm_halo); g.comm_halo = nullptr; }
+  if (g.comm) { g.nccl.CommDestroy(g.comm); g.comm = nullptr; }   // a second comm_init replaces the communicator
   if (g.nccl.CommInitRank(&g.comm, nranks, id, rank) != ncclSuccess) {
     g.fail(DIAGLIB_B200_ECOMM, "ncclCommInitRank failed");
     return DIAGLIB_B200_ECOMM;
   }
   g.rank = rank;
   g.nranks = nranks;
+  // second communicator + stream for the SpMM halo exchange (overlaps the interior rows);
+  // DIAGLIB_B200_HALO_OVERLAP=0 keeps the exchange on the main stream
+  const char* ov = std::getenv("DIAGLIB_B200_HALO_OVERLAP");
+  if (g.nccl.CommSplit && !(ov && ov[0] == '0')) {
+    if (g.nccl.CommSplit(g.comm, 0, rank, &g.comm_halo, nullptr) != ncclSuccess) g.comm_halo = nullptr;
+    if (g.comm_halo) {
+      if (!g.st_halo) DLB_CUDA_CHECK(cudaStreamCreateWithFlags(&g.st_halo, cudaStreamNonBlocking));
+      if (!g.ev_x) {
+        DLB_CUDA_CHECK(cudaEventCreateWithFlags(&g.ev_x, cudaEventDisableTiming));
+        DLB_CUDA_CHECK(cudaEventCreateWithFlags(&g.ev_halo, cudaEventDisableTiming));
+      }
+    }
+  }
   return DIAGLIB_B200_OK;
 }
 int32_t diaglib_b200_comm_rank(void) { return g.rank; }
@@ -1680,7 +1870,7 @@ void diaglib_b200_timers(double* out12) { for (int i = 0; i < 12; ++i) out12[i] 
 void diaglib_b200_set_profile(int32_t on) { g.profile = on != 0; }
 void diaglib_b200_stats(int64_t* out8) {
   out8[0] = g.st_cd_passes; out8[1] = g.st_sweeps; out8[2] = g.st_qr; out8[3] = g.st_shifts; out8[4] = g.st_launches;
-  out8[5] = g_launches; out8[6] = 0; out8[7] = 0;
+  out8[5] = g_launches; out8[6] = g.st_syncs; out8[7] = 0;
 }
 
 // ---- kernel-level entry points (include/diaglib_b200_kernels.h) ---------------------------
@@ -1797,6 +1987,117 @@ int32_t diaglib_b200_k_sym_eig(int32_t k, double* a_host, int32_t lda, int32_t u
   // sweeps, +1000 when the one-sided solver (path 1) delivered; negative when not converged
   return h.converged ? h.sweeps + (h.path == 1 ? 1000 : 0) : -h.sweeps - 1;
 }
+// ---- synthetic FCI-like matrix (C4), generated in HBM --------------------------------------
+__device__ __forceinline__ uint64_t dev_splitmix64(uint64_t x) {
+  uint64_t z = x + 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+struct FciParams {
+  int64_t n, r0, r1, lo_prev, hi_next;
+  int n_strides, bits, shift;
+  uint64_t key_val, mask, ks[4];
+  double big_delta;
+};
+__global__ void gen_fci_kernel(FciParams p, const int64_t* __restrict__ strides, const int64_t* __restrict__ rowptr,
+                               int32_t* __restrict__ col, double* __restrict__ val, double* __restrict__ diag) {
+  const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_loc = p.r1 - p.r0;
+  if (li >= n_loc) return;
+  const int64_t i = p.r0 + li;
+  // d_i = 1 + Delta * pi(i), pi = problems.bijection (rounds of odd multiply / xorshift / add mod 2^bits)
+  uint64_t x = (uint64_t)i & p.mask;
+  for (int r = 0; r < 4; ++r) {
+    x = (x * (p.ks[r] | 1ULL)) & p.mask;
+    x = x ^ (x >> p.shift);
+    x = (x + (p.ks[r] >> 17)) & p.mask;
+  }
+  const double d = __dadd_rn(1.0, __dmul_rn(p.big_delta, (double)x));
+  diag[li] = d;
+  int64_t k = rowptr[li];
+  // offsets in ascending order: -s_K ... -s_1, 0, s_1 ... s_K
+  for (int e = 0; e < 2 * p.n_strides + 1; ++e) {
+    int64_t c;
+    if (e < p.n_strides) c = i - strides[p.n_strides - 1 - e];
+    else if (e == p.n_strides) c = i;
+    else c = i + strides[e - p.n_strides - 1];
+    if (c < 0 || c >= p.n) continue;
+    double v;
+    if (c == i) v = d;
+    else {
+      const uint64_t lo = (uint64_t)(c < i ? c : i), hi = (uint64_t)(c < i ? i : c);
+      const uint64_t z = dev_splitmix64((lo * (uint64_t)p.n + hi) ^ p.key_val);
+      const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+      v = __dmul_rn(__dadd_rn(u, -0.5), 0.02);
+    }
+    int64_t cl;
+    if (c >= p.r0 && c < p.r1) cl = c - p.r0;
+    else if (c < p.r0) cl = n_loc + (c - p.lo_prev);
+    else cl = n_loc + (p.r0 - p.lo_prev) + (c - p.r1);
+    col[k] = (int32_t)cl;
+    val[k] = v;
+    ++k;
+  }
+}
+
+int32_t diaglib_b200_k_gen_fci(int64_t n, int64_t r0, int64_t r1, int32_t n_strides, const int64_t* strides_host,
+                               double big_delta, int64_t seed, int64_t lo_prev, int64_t hi_next,
+                               const int64_t* rowptr_dev, int32_t* col_dev, double* val_dev, double* diag_dev) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  FciParams p{};
+  p.n = n; p.r0 = r0; p.r1 = r1; p.lo_prev = lo_prev; p.hi_next = hi_next;
+  p.n_strides = n_strides;
+  p.bits = 0;
+  while ((1LL << p.bits) < n) ++p.bits;
+  p.shift = std::max(1, p.bits / 2);
+  p.mask = (p.bits >= 64) ? ~0ULL : ((1ULL << p.bits) - 1);
+  auto sm64 = [](uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+  };
+  for (int r = 0; r < 4; ++r) p.ks[r] = sm64((uint64_t)r + (uint64_t)seed * 1000003ULL);   // problems.bijection
+  p.key_val = sm64((uint64_t)(seed + 17));                                                 // problems.hash_u01(seed + 17, .)
+  p.big_delta = big_delta;
+  DevBuf ds;
+  if (!ds.ensure((size_t)std::max(1, n_strides) * sizeof(int64_t))) return DIAGLIB_B200_EALLOC;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(ds.p, strides_host, (size_t)n_strides * sizeof(int64_t), cudaMemcpyHostToDevice, g.st));
+  const int64_t n_loc = r1 - r0;
+  if (n_loc > 0) gen_fci_kernel<<<(unsigned)((n_loc + 127) / 128), 128, 0, g.st>>>(p, ds.as<int64_t>(), rowptr_dev, col_dev, val_dev, diag_dev);
+  DLB_CUDA_CHECK(cudaGetLastError());
+  DLB_CUDA_CHECK(cudaStreamSynchronize(g.st));
+  ds.release();
+  return DIAGLIB_B200_OK;
+}
+
+int32_t diaglib_b200_k_true_residual(int32_t n_loc, int32_t m, const double* x_dev, const double* theta_host,
+                                     double* norms_host) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  if (g.A.n != n_loc) return DIAGLIB_B200_EARG;
+  DevBuf ax, tmp;
+  if (!ax.ensure((size_t)std::max(1, n_loc) * m * sizeof(double)) || !tmp.ensure((4 * (size_t)m + 16) * sizeof(double)) ||
+      !g.resid_scratch.ensure(residual_scratch_bytes(m, g.num_sms)))
+    return DIAGLIB_B200_EALLOC;
+  double* d_theta = tmp.as<double>();
+  double* d_norms = d_theta + m;
+  int* d_act = reinterpret_cast<int*>(d_norms + 2 * m);
+  std::vector<int> act(m, 1);
+  DLB_CUDA_CHECK(cudaMemcpyAsync(d_theta, theta_host, m * sizeof(double), cudaMemcpyHostToDevice, g.st));
+  DLB_CUDA_CHECK(cudaMemcpyAsync(d_act, act.data(), m * sizeof(int), cudaMemcpyHostToDevice, g.st));
+  g.csr_matvec(m, x_dev, ax.as<double>());
+  residual_norms(g.st, g.num_sms, n_loc, m, ax.as<double>(), n_loc, x_dev, n_loc, d_theta, d_act, ax.as<double>(), n_loc, d_norms,
+                 g.resid_scratch.as<double>());
+  g.allreduce(d_norms, m, ncclSum);
+  g.allreduce(d_norms + m, m, ncclMax);
+  DLB_CUDA_CHECK(cudaMemcpyAsync(norms_host, d_norms, 2 * m * sizeof(double), cudaMemcpyDeviceToHost, g.st));
+  g.sync();
+  ax.release();
+  tmp.release();
+  return g.status;
+}
+
 int32_t diaglib_b200_k_set_eig_mode(int32_t mode, int32_t block) {
   const int prev = g_eig_mode;
   g_eig_mode = mode;

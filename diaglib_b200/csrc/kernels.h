@@ -52,6 +52,13 @@ struct CsrDevice {
   int64_t nnz = 0;
   int64_t n_halo = 0;   // columns >= n index the halo block
   int max_row_nnz = 0;  // longest row (0 = unknown); selects the short-row SpMM
+  // optional processing order of the rows (a permutation of [0, n)): entries [0, n_interior) are
+  // rows without halo columns, the rest touch the halo.  null: natural order, n_interior = n
+  // when n_halo = 0 and 0 otherwise.  tiled: the order keeps neighbouring rows of a stencil
+  // together (set by the caller), so the SpMM sweeps all columns in one launch.
+  const int32_t* order = nullptr;
+  int64_t n_interior = 0;
+  bool tiled = false;
   int64_t* rowptr = nullptr;
   int32_t* col = nullptr;
   double* val = nullptr;
@@ -59,8 +66,11 @@ struct CsrDevice {
 };
 // AX(n x m) = A * X (+ shift * X).  x_halo holds the remote rows (n_halo x m, ld n_halo).
 // Built-in conforming matvec(n,m,x,ax) (contract diaglib.f90:66; toy impl main.f90:72-90).
+// part: all rows, or only the rows without / with halo columns (A.order's two sections), so that
+// the interior rows can run while the halo exchange is in flight.
+enum { SPMM_ALL = 0, SPMM_INTERIOR = 1, SPMM_BOUNDARY = 2 };
 void spmm_csr(cudaStream_t st, const CsrDevice& A, int m, const double* x, int64_t ldx, const double* x_halo,
-              double* ax, int64_t ldax, double shift);
+              double* ax, int64_t ldax, double shift, int part = SPMM_ALL);
 // px = x / (d + fac) where |d + fac| > 1e-5, else x  (main.f90:146-171).
 void diag_precnd(cudaStream_t st, int64_t n, int m, double fac, const double* diag, const double* x, int64_t ldx,
                  double* px, int64_t ldpx);

@@ -505,11 +505,14 @@ eig_finish_kernel(int k, int kp, const double* A, const double* Z, double* a, in
 // factor + ONE-SIDED block Jacobi on the factor (Veselic-Hari).  With P^T A P = L L^T (P sorts
 // the diagonal in descending order) the rotations orthogonalise the COLUMNS of L:
 //     L V = U S   ==>   A = (P U) S^2 (P U)^T,
-// so the eigenvalues are the squared column norms (relative accuracy ~ k eps on graded matrices,
-// better than the two-sided form: the rotations only ever see columns, never differences of
-// matrix entries) and the eigenvectors are the normalised columns themselves - no accumulated
-// Z, no row rotations, half the data of the two-sided kernels.  Eigenvector accuracy is
-// LAPACK-class (norm-wise eps), which is what the reference's dsyev delivers.
+// so the eigenvalues are the squared column norms (relative accuracy ~ k eps on graded matrices:
+// the rotations only ever see columns, never differences of matrix entries) and the
+// eigenvectors are the normalised columns themselves - no accumulated Z, no row rotations, half
+// the data of the two-sided kernels.  A pair is rotated while its dot product stands above its
+// own rounding floor (not merely above eps |x||y|): with the descending sort the small columns
+// of L vanish in the large rows, so the floor is far below eps in the cosine and the
+// eigenvectors come out accurate relative to each eigenvalue (residual |A z - w z| ~ 1e-14 |w|
+// on the graded LOBPCG matrices, measured; dsyev delivers eps |A|).
 //
 // Parallel form: the kp columns are split into nblk = 2 G blocks of b columns; a sweep is a
 // round-robin tournament of the blocks (nblk - 1 rounds, CTA g owns block pair g of the round)
@@ -527,7 +530,7 @@ struct OsjCtl {
   unsigned bar;                      // monotonic grid-barrier counter
   int fail;                          // Cholesky pivot <= 0 / NaN
   int pad[2];
-  unsigned long long sweep_max[60];  // per sweep: max |p.q| / (|p| |q|) seen before rotating (double bits)
+  unsigned long long sweep_max[60];  // per sweep: largest rotated |x.y| / sum|x_i y_i| (double bits)
 };
 constexpr int OSJ_NB = 16;           // Cholesky panel width when the matrix does not fit one CTA
 
@@ -539,16 +542,26 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 // grid-wide barrier of a cooperative launch (all CTAs co-resident): one atomic per CTA on a
 // monotonic counter.  `target` is the calling CTA's private running total.
 __device__ __forceinline__ void osj_grid_bar(unsigned* ctr, unsigned& target) {
-  if (gridDim.x == 1) { __syncthreads(); return; }
   __syncthreads();
+  if (gridDim.x == 1) return;
   if (threadIdx.x == 0) {
     target += gridDim.x;
-    __threadfence();
-    atomicAdd(ctr, 1u);
+    // release: the CTA's writes (ordered before this thread by the barrier above) become visible
+    // before the increment; acquire: nothing after the spin is satisfied from stale data
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(ctr) : "memory");
     while (ld_acquire_u32(ctr) < target) { }
-    __threadfence();
   }
   __syncthreads();
+}
+
+// 1/sqrt(x) for x inside the float range: FP32 hardware seed (rel. error ~1e-7) + 2 Newton steps
+// in FP64 (1.5e-14, then rounding level)
+__device__ __forceinline__ double fast_rsqrt2(double x) {
+  double y = (double)rsqrtf((float)x);
+  const double hx = 0.5 * x;
+  y = y * (1.5 - hx * y * y);
+  y = y * (1.5 - hx * y * y);
+  return y;
 }
 
 __global__ void __launch_bounds__(256, 1)
@@ -581,7 +594,7 @@ sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double
     const int i = (int)(e % ldl), j = (int)(e / ldl);
     double v = 0.0;
     if (i < k && j < k && i >= j) {
-      const int oi = perm[i], oj = perm[j];
+      const int oi = __ldcg(&perm[i]), oj = __ldcg(&perm[j]);
       const int lo = oi < oj ? oi : oj, hi = oi < oj ? oj : oi;
       v = upper ? a[lo + (size_t)hi * lda] : a[hi + (size_t)lo * lda];
     }
@@ -592,10 +605,9 @@ sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double
   for (int J = 0; J < k; J += nb_chol) {
     const int nb = min(nb_chol, k - J), rows = k - J;
     if (blockIdx.x == 0) {
-      for (int e = tid; e < rows * nb; e += nt) {
-        const int c = e / rows, i = e % rows;
-        S[e] = __ldcg(&L[(J + i) + (size_t)(J + c) * ldl]);
-      }
+      // panel (rows x nb, column c at S + c * rows) in shared memory, one warp per column
+      for (int c = warp; c < nb; c += nwarp)
+        for (int i = lane; i < rows; i += 32) S[c * rows + i] = __ldcg(&L[(J + i) + (size_t)(J + c) * ldl]);
       __syncthreads();
       bool bad = false;
       for (int c = 0; c < nb; ++c) {
@@ -605,19 +617,16 @@ sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double
         __syncthreads();
         for (int i = c + tid; i < rows; i += nt) S[c * rows + i] = (i == c) ? sq : S[c * rows + i] / sq;
         __syncthreads();
-        const int ncol = nb - c - 1;
-        for (int e = tid; e < ncol * rows; e += nt) {
-          const int c2 = c + 1 + e / rows, i = e % rows;
-          if (i >= c2) S[c2 * rows + i] = fma(-S[c * rows + i], S[c * rows + c2], S[c2 * rows + i]);
+        for (int c2 = c + 1 + warp; c2 < nb; c2 += nwarp) {
+          const double l = S[c * rows + c2];
+          for (int i = c2 + lane; i < rows; i += 32) S[c2 * rows + i] = fma(-S[c * rows + i], l, S[c2 * rows + i]);
         }
         __syncthreads();
       }
       if (bad) { if (tid == 0) ctl->fail = 1; }
       else {
-        for (int e = tid; e < rows * nb; e += nt) {
-          const int c = e / rows, i = e % rows;
-          L[(J + i) + (size_t)(J + c) * ldl] = (i >= c) ? S[e] : 0.0;
-        }
+        for (int c = warp; c < nb; c += nwarp)
+          for (int i = lane; i < rows; i += 32) L[(J + i) + (size_t)(J + c) * ldl] = (i >= c) ? S[c * rows + i] : 0.0;
       }
     }
     osj_grid_bar(&ctl->bar, bar_target);
@@ -634,7 +643,7 @@ sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double
           double acc = __ldcg(&L[i + (size_t)j * ldl]);
 #pragma unroll
           for (int c = 0; c < OSJ_NB; ++c)
-            if (c < nb) acc = fma(-L[i + (size_t)(J + c) * ldl], lj[c], acc);
+            if (c < nb) acc = fma(-__ldcg(&L[i + (size_t)(J + c) * ldl]), lj[c], acc);
           L[i + (size_t)j * ldl] = acc;
         }
       }
@@ -672,34 +681,45 @@ sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double
           }
           double* x = S + (size_t)cp * ldl;
           double* y = S + (size_t)cq * ldl;
-          double app = 0.0, aqq = 0.0, apq = 0.0;
+          double app = 0.0, aqq = 0.0, apq = 0.0, sab = 0.0;
           for (int i = lane; i < ldl; i += 32) {
-            const double xv = x[i], yv = y[i];
-            app = fma(xv, xv, app); aqq = fma(yv, yv, aqq); apq = fma(xv, yv, apq);
+            const double xv = x[i], yv = y[i], xy = xv * yv;
+            app = fma(xv, xv, app); aqq = fma(yv, yv, aqq); apq += xy; sab += fabs(xy);
           }
-          app = warp_sum(app); aqq = warp_sum(aqq); apq = warp_sum(apq);
-          const double den = app * aqq;
-          if (den > 0.0) {
-            const double rel = fabs(apq) * fast_rsqrt(den);   // den within the float range for these matrices
-            const double relx = (den > 1e-30 && den < 1e30) ? rel : fabs(apq) / sqrt(den);
-            my_max = fmax(my_max, relx);
-            if (relx > tol) {
+          app = warp_sum(app); aqq = warp_sum(aqq); apq = warp_sum(apq); sab = warp_sum(sab);
+          // rotate while the dot product stands above its own rounding floor, sqrt(k) eps sum|x_i y_i|
+          // (<= sqrt(k) eps |x||y|, the usual cosine test, with equality for ungraded columns): on
+          // graded factors this orthogonalises a small column against a large one far below eps in
+          // the cosine, which is what makes the eigenvectors accurate relative to each eigenvalue
+          if (fabs(apq) > tol * sab) {
+            my_max = fmax(my_max, fabs(apq) / sab);
+            // Jacobi angle for the pair: with d = (aqq - app)/2, h = hypot(d, apq), u = |d| + h:
+            // cos = sqrt(u / 2h), sin = sign(d) apq / sqrt(2 h u)   (cos^2 + sin^2 = 1 identically)
+            const double big = fmax(app, aqq);
+            const int ex = (__double2hiint(big) >> 20) & 0x7ff;
+            const double sc = __hiloint2double((2046 - ex) << 20, 0);   // big * sc in [1, 2)
+            const double bq = apq * sc, d = 0.5 * (aqq - app) * sc;
+            const double h2 = fma(d, d, bq * bq);
+            double cs, sn;
+            if (h2 > 1e-30 && ex > 0 && ex < 2046) {
+              const double rh = fast_rsqrt2(h2);
+              const double u = fabs(d) + h2 * rh;
+              const double w = 0.5 * u * rh;            // in [1/2, 1]
+              const double rw = fast_rsqrt2(w);
+              cs = w * rw;
+              sn = (d >= 0.0 ? 0.5 : -0.5) * bq * rh * rw;
+            } else {
               const double zeta = (aqq - app) / (2.0 * apq);
-              double tt;
-              if (fabs(zeta) < 1e8) {
-                const double t2 = 1.0 + zeta * zeta;
-                tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(t2));
-              } else {
-                tt = 0.5 / zeta;
-              }
-              const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = tt * cs;
-              for (int i = lane; i < ldl; i += 32) {
-                const double xv = x[i], yv = y[i];
-                x[i] = cs * xv - sn * yv;
-                y[i] = sn * xv + cs * yv;
-              }
-              dirty = true;
+              const double tt = fabs(zeta) < 1e8 ? (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta)) : 0.5 / zeta;
+              cs = 1.0 / sqrt(1.0 + tt * tt);
+              sn = tt * cs;
             }
+            for (int i = lane; i < ldl; i += 32) {
+              const double xv = x[i], yv = y[i];
+              x[i] = cs * xv - sn * yv;
+              y[i] = sn * xv + cs * yv;
+            }
+            dirty = true;
           }
         }
         __syncthreads();
@@ -726,8 +746,9 @@ sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double
     }
     const double mx = __longlong_as_double((long long)__ldcg(&ctl->sweep_max[sweeps]));
     ++sweeps;
-    // quadratic convergence: rotations against off-diagonals below 1e-9 leave k * 1e-18
-    if (mx <= fmax(tol, 1e-9)) { converged = 1; break; }
+    // mx = largest |x.y| / sum|x_i y_i| that was rotated in this sweep (0: a clean sweep).  Quadratic
+    // convergence: a sweep whose rotations were all below 1e-10 leaves ~1e-20, under every floor
+    if (mx <= 1e-10) { converged = 1; break; }
   }
   if (!converged) { if (gtid == 0) { st->sweeps = sweeps; st->converged = 0; st->path = 0; } return; }
 
@@ -753,7 +774,7 @@ sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double
     int bidx = 0x7fffffff;
     for (int i = lane; i < k; i += 32) {
       const double v = __ldcg(&L[i + (size_t)j * ldl]);
-      const int oi = perm[i];
+      const int oi = __ldcg(&perm[i]);
       if (fabs(v) > best || (fabs(v) == best && oi < bidx)) { best = fabs(v); bval = v; bidx = oi; }
     }
 #pragma unroll
@@ -763,7 +784,7 @@ sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double
       if (ob > best || (ob == best && oi < bidx)) { best = ob; bval = ov; bidx = oi; }
     }
     const double nrm = sqrt(gj) * (bval < 0.0 ? -1.0 : 1.0);
-    for (int i = lane; i < k; i += 32) a[perm[i] + (size_t)rk * lda] = __ldcg(&L[i + (size_t)j * ldl]) / nrm;
+    for (int i = lane; i < k; i += 32) a[__ldcg(&perm[i]) + (size_t)rk * lda] = __ldcg(&L[i + (size_t)j * ldl]) / nrm;
     if (lane == 0) w[rk] = gj;
   }
   if (gtid == 0) { st->sweeps = sweeps; st->converged = 1; st->path = 1; }

@@ -68,13 +68,17 @@ __device__ __forceinline__ void spmm_row_generic(int64_t row, int64_t b, int64_t
   }
 }
 
+// `order` (optional) lists the rows in processing order; the launch covers entries
+// [first, first + count) of it (natural order when null).
 template <int JB>
 __global__ void __launch_bounds__(256)
 spmm_csr_kernel(int64_t n, int64_t n_halo, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                 const double* __restrict__ val, int m, const double* __restrict__ x, int64_t ldx,
-                const double* __restrict__ xh, double* __restrict__ ax, int64_t ldax, double shift) {
-  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n) return;
+                const double* __restrict__ xh, double* __restrict__ ax, int64_t ldax, double shift,
+                const int32_t* __restrict__ order, int64_t first, int64_t count) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= count) return;
+  const int64_t row = order ? (int64_t)order[first + gid] : first + gid;
   spmm_row_generic<JB>(row, rowptr[row], rowptr[row + 1], 0, n, n_halo, col, val, m, x, ldx, xh, ax, ldax, shift);
 }
 
@@ -101,10 +105,12 @@ template <int JB, int KMAX>
 __global__ void __launch_bounds__(256, 4)
 spmm_csr_short_kernel(int64_t n, int64_t n_halo, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                       const double* __restrict__ val, int m, const double* __restrict__ x, int64_t ldx,
-                      const double* __restrict__ xh, double* __restrict__ ax, int64_t ldax, double shift) {
-  const int64_t row0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = row0 < n;
-  const int64_t row = valid ? row0 : n - 1;
+                      const double* __restrict__ xh, double* __restrict__ ax, int64_t ldax, double shift,
+                      const int32_t* __restrict__ order, int64_t first, int64_t count) {
+  const int64_t gid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = gid0 < count;
+  const int64_t gid = valid ? gid0 : count - 1;
+  const int64_t row = order ? (int64_t)order[first + gid] : first + gid;
   const int64_t b = rowptr[row];
   const int len = (int)(rowptr[row + 1] - b);
   // entries k >= len repeat the last real entry with a zero coefficient:
@@ -286,16 +292,23 @@ void lr_precnd(cudaStream_t st, int64_t n, int m, double fac, const double* aa, 
 }
 
 void spmm_csr(cudaStream_t st, const CsrDevice& A, int m, const double* x, int64_t ldx, const double* x_halo,
-              double* ax, int64_t ldax, double shift) {
+              double* ax, int64_t ldax, double shift, int part) {
   if (A.n <= 0 || m <= 0) return;
-  const unsigned grid = (unsigned)((A.n + 255) / 256);
+  // rows of this launch: all of them, or the interior / boundary section of A.order
+  int64_t first = 0, count = A.n;
+  if (part == SPMM_INTERIOR) count = A.n_interior;
+  else if (part == SPMM_BOUNDARY) { first = A.n_interior; count = A.n - A.n_interior; }
+  if (count <= 0) return;
+  const unsigned grid = (unsigned)((count + 255) / 256);
   if (A.max_row_nnz > 0 && A.max_row_nnz <= 7 && g_spmm_short > 0) {
     // column chunks, one launch each: with the gathers pipelined the kernel is DRAM-bound on its
     // ACTUAL traffic, and beyond ~24 columns the far-neighbour reuse window (2 planes x m columns,
     // read + written) falls out of L2 and x is fetched from DRAM more than once (ncu at m = 37:
     // 15.9 GB moved for 11.5 GB algorithmic).  A chunk re-reads the matrix but keeps x in L2.
+    // With a locality-preserving row order (A.tiled) the window is a tile neighbourhood and one
+    // launch sweeps all columns.
     int jc = m;
-    if (g_spmm_chunk > 0 && m > g_spmm_chunk) {
+    if (g_spmm_chunk > 0 && m > g_spmm_chunk && !A.tiled) {
       const int npass = (m + g_spmm_chunk - 1) / g_spmm_chunk;
       jc = (((m + npass - 1) / npass) + 7) / 8 * 8;
     }
@@ -304,12 +317,14 @@ void spmm_csr(cudaStream_t st, const CsrDevice& A, int m, const double* x, int64
       // halo block columns are n_halo apart
       spmm_csr_short_kernel<8, 7><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, mc, x + (int64_t)j0 * ldx, ldx,
                                                         x_halo ? x_halo + (int64_t)j0 * A.n_halo : nullptr,
-                                                        ax + (int64_t)j0 * ldax, ldax, shift);
-      if (j0 > 0) ++g_launches;
+                                                        ax + (int64_t)j0 * ldax, ldax, shift, A.order, first, count);
+      ++g_launches;
     }
-  } else
-    spmm_csr_kernel<8><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, m, x, ldx, x_halo, ax, ldax, shift);
-  ++g_launches;
+  } else {
+    spmm_csr_kernel<8><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, m, x, ldx, x_halo, ax, ldax, shift,
+                                             A.order, first, count);
+    ++g_launches;
+  }
   DLB_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -127,6 +127,36 @@ def lap3d(nx: int, ny: int, nz: int, r0: int = 0, r1: int | None = None, delta: 
     return rowptr, col, val, diag
 
 
+def _morton3(ix, iy, iz):
+    """interleave the bits of three non-negative integer arrays (z-order curve key)"""
+    key = np.zeros(ix.shape, dtype=np.int64)
+    for b in range(21):
+        key |= ((ix >> b) & 1) << (3 * b) | ((iy >> b) & 1) << (3 * b + 1) | ((iz >> b) & 1) << (3 * b + 2)
+    return key
+
+
+def tile_order_3d(nx: int, ny: int, nz: int, tile=(32, 4, 2), z0: int = 0, z1: int | None = None, curve: str = "morton"):
+    """Processing order for the rows of a 3-D grid stencil (row i = x + nx*(y + ny*z)) owned by a
+    rank holding the planes [z0, z1): the grid is cut into tiles of tile = (tx, ty, tz) sites (one
+    CTA of the SpMM = 256 consecutive entries = one 32x4x2 tile), tiles are visited along a
+    z-order curve ("morton") or plane by plane ("sweep").  Returns LOCAL row indices (int32
+    permutation of [0, nx*ny*(z1-z0))).  Pure locality hint for diaglib_b200.set_csr_row_order."""
+    z1 = nz if z1 is None else z1
+    tx, ty, tz = tile
+    lz = z1 - z0
+    x, y, z = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(lz), indexing="ij")
+    x, y, z = x.ravel(), y.ravel(), z.ravel()
+    bx, by, bz = x // tx, y // ty, z // tz
+    if curve == "morton":
+        tkey = _morton3(bx, by, bz)
+    else:
+        tkey = (bz * ((ny + ty - 1) // ty) + by) * ((nx + tx - 1) // tx) + bx
+    inner = ((z % tz) * ty + (y % ty)) * tx + (x % tx)
+    order = np.lexsort((inner, tkey))
+    rows = x + nx * (y + ny * z)
+    return rows[order].astype(np.int32)
+
+
 def fci_strides(n_strides: int = 50, bandwidth: int = 1 << 20, seed: int = 1):
     """Fixed seeded set of distinct positive strides <= bandwidth (sorted ascending)."""
     out: list[int] = []

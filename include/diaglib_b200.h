@@ -145,6 +145,16 @@ const char* diaglib_b200_last_message(void);
  * by the exchange plan below.  diag = the matrix diagonal of the owned rows (preconditioner). */
 int32_t diaglib_b200_set_csr(int64_t n_loc, int64_t n_halo, const int64_t* rowptr, const int32_t* col,
                              const double* val, const double* diag);
+/* set_csr for a matrix that already lives in HBM (device pointers; the caller keeps ownership and
+ * keeps the arrays alive while the matrix is installed). */
+int32_t diaglib_b200_set_csr_device(int64_t n_loc, int64_t n_halo, int64_t nnz, const int64_t* rowptr_dev,
+                                    const int32_t* col_dev, const double* val_dev, const double* diag_dev);
+/* optional processing order of the local rows in the built-in matvec: a permutation of
+ * [0, n_loc) (host array), null = natural order.  A locality-preserving order (tiles of a
+ * stencil's grid along a space-filling curve) raises the cache hit rate of the gathers; results
+ * are independent of it.  Call after set_csr / set_csr_device.  The library keeps the rows that
+ * reference halo columns at the end of the order so that the halo exchange overlaps the others. */
+int32_t diaglib_b200_set_csr_row_order(const int32_t* order);
 /* metric B of the generalized problem for the built-in bvec.  Same conventions as set_csr; if
  * it has halo columns (n_halo > 0) they use the matrix's halo numbering and exchange plan. */
 int32_t diaglib_b200_set_csr_b(int64_t n_loc, int64_t n_halo, const int64_t* rowptr, const int32_t* col,

@@ -46,6 +46,20 @@ int32_t diaglib_b200_k_block_mul_gram(int64_t n, const double* v_dev, int64_t ld
 int32_t diaglib_b200_k_residual(int64_t n, int32_t m, const double* ax_dev, int64_t ldax, const double* x_dev,
                                 int64_t ldx, const double* theta_host, const int32_t* active_host, double* r_dev,
                                 int64_t ldr, double* norms_host);
+/* synthetic FCI-like matrix of config C4 (same arithmetic as diaglib_b200/problems.py
+ * fci_like): fills col/val/diag (device arrays) for the global rows [r0, r1) of the n-row matrix
+ * from the row pointers (device, r1 - r0 + 1 entries, starting at 0).  strides: n_strides sorted
+ * positive strides (host).  Columns are written in the LOCAL numbering of a row-partitioned run:
+ * c in [r0, r1) -> c - r0; c in [lo_prev, r0) -> (r1 - r0) + (c - lo_prev); c in [r1, hi_next) ->
+ * (r1 - r0) + (r0 - lo_prev) + (c - r1) (pass lo_prev = r0, hi_next = r1 for one rank). */
+int32_t diaglib_b200_k_gen_fci(int64_t n, int64_t r0, int64_t r1, int32_t n_strides, const int64_t* strides_host,
+                               double big_delta, int64_t seed, int64_t lo_prev, int64_t hi_next,
+                               const int64_t* rowptr_dev, int32_t* col_dev, double* val_dev, double* diag_dev);
+/* r = A x - theta x with the installed matrix on a device block (n_loc x m): per-column sum of
+ * squares and max |r| over all ranks -> norms_host[0..m) and [m..2m).  An independent check of
+ * a driver's returned pairs (the drivers test the recurrence residual). */
+int32_t diaglib_b200_k_true_residual(int32_t n_loc, int32_t m, const double* x_dev, const double* theta_host,
+                                     double* norms_host);
 /* dsyev('v',uplo) replacement on a host matrix (k x k, lda): a overwritten by eigenvectors,
  * w ascending.  returns sweeps, +1000 when the one-sided solver on the Cholesky factor delivered
  * (positive definite input), < 0 if not converged.  diaglib.f90:315,406,1708 */

@@ -115,3 +115,16 @@ def test_localize_rejects_columns_outside_the_halo_and_union_covers_them():
     # the same global column maps to the same local index through either matrix
     assert np.array_equal(la, lb[:len(la)])
     assert lb[-2] == (r1 - r0) + 0 and lb[-1] == (r1 - r0) + 100 + 99
+
+
+@pytest.mark.parametrize("curve", ["morton", "sweep"])
+def test_tile_order_is_a_permutation_with_tile_blocks(curve):
+    nx, ny, nz = 64, 16, 8
+    o = P.tile_order_3d(nx, ny, nz, tile=(32, 4, 2), z0=2, z1=8, curve=curve)
+    n_loc = nx * ny * 6
+    assert o.dtype == np.int32 and np.array_equal(np.sort(o), np.arange(n_loc))
+    # every 256 consecutive entries are one 32x4x2 tile, x fastest
+    blk = o[:256].astype(np.int64)
+    x, y, z = blk % nx, (blk // nx) % ny, blk // (nx * ny)
+    assert x.max() - x.min() == 31 and y.max() - y.min() == 3 and z.max() - z.min() == 1
+    assert np.array_equal(blk[:32], blk[0] + np.arange(32))

@@ -51,6 +51,54 @@ __global__ void kfma(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// mixed mode: does the FP64 tensor pipe (DMMA) run beside the plain FP64 pipe (DFMA)?  Every warp
+// issues NM independent DMMAs and NF independent DFMAs per iteration; if the two were separate
+// pipes the combined rate would exceed either peak.  (round-2 question of the judge.)
+template <int NM, int NF>
+__global__ void kmix(double* out, int iters) {
+  double c[NM][2], f[NF];
+  for (int i = 0; i < NM; ++i) c[i][0] = c[i][1] = 0.0;
+  for (int i = 0; i < NF; ++i) f[i] = i;
+  double a = threadIdx.x * 1e-3 + 1.0, b = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < (NM > NF ? NM : NF); ++i) {
+      if (i < NM)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+      if (i < NF) f[i] = fma(f[i], a, b);
+    }
+  }
+  double s = 0;
+  for (int i = 0; i < NM; ++i) s += c[i][0] + c[i][1];
+  for (int i = 0; i < NF; ++i) s += f[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// warp-specialised mix: even warps only DMMA, odd warps only DFMA
+__global__ void ksplit(double* out, int iters) {
+  double c[8][2], f[16];
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+  for (int i = 0; i < 16; ++i) f[i] = i;
+  double a = threadIdx.x * 1e-3 + 1.0, b = 1e-9;
+  if ((threadIdx.x >> 5) & 1) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = fma(f[i], a, b);
+    }
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+  }
+  double s = 0;
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  for (int i = 0; i < 16; ++i) s += f[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class F>
 double timeit(F f) {
   cudaEvent_t e0, e1;
@@ -87,6 +135,23 @@ int main() {
     ms = timeit([&] { kfma<16><<<grid, threads>>>(out, iters); });
     fl = (double)grid * threads * iters * 16 * 2.0;
     printf("DFMA     acc=16 warps/SM=%2d : %.2f TFLOP/s\n", 2 * threads / 32, fl / ms / 1e9);
+  }
+  // mixed DMMA + DFMA
+  for (int warps : {8, 16, 32}) {
+    int grid = sms * 2, threads = warps * 32 / 2;
+    double ms = timeit([&] { kmix<8, 16><<<grid, threads>>>(out, iters); });
+    double fl_m = (double)grid * (threads / 32) * iters * 8 * 512.0, fl_f = (double)grid * threads * iters * 16 * 2.0;
+    printf("MIX 8 DMMA + 16 DFMA per warp-iteration, warps/SM=%2d : %.2f TFLOP/s total (DMMA %.2f + DFMA %.2f)\n",
+           2 * threads / 32, (fl_m + fl_f) / ms / 1e9, fl_m / ms / 1e9, fl_f / ms / 1e9);
+    ms = timeit([&] { kmix<8, 4><<<grid, threads>>>(out, iters); });
+    fl_f = (double)grid * threads * iters * 4 * 2.0;
+    printf("MIX 8 DMMA +  4 DFMA per warp-iteration, warps/SM=%2d : %.2f TFLOP/s total (DMMA %.2f + DFMA %.2f)\n",
+           2 * threads / 32, (fl_m + fl_f) / ms / 1e9, fl_m / ms / 1e9, fl_f / ms / 1e9);
+    ms = timeit([&] { ksplit<<<grid, threads>>>(out, iters); });
+    fl_m = (double)grid * (threads / 64) * iters * 8 * 512.0;
+    fl_f = (double)grid * (threads / 2) * iters * 16 * 2.0;
+    printf("SPLIT even warps DMMA / odd warps DFMA, warps/SM=%2d : %.2f TFLOP/s total (DMMA %.2f + DFMA %.2f)\n",
+           2 * threads / 32, (fl_m + fl_f) / ms / 1e9, fl_m / ms / 1e9, fl_f / ms / 1e9);
   }
   return 0;
 }
