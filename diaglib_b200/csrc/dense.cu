@@ -15,6 +15,7 @@
 #include <vector>
 
 namespace dlb {
+const int* g_live = nullptr;   // see kernels.h
 
 bool g_disable_ws = false;
 bool g_disable_tma = false;
@@ -114,7 +115,8 @@ template <bool ALIGN16>
 __global__ void __launch_bounds__(GR_THREADS, 1)
 gram_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const double* __restrict__ B, int64_t ldb,
             int q, int same, int KT, const __grid_constant__ GramSched sched, double* __restrict__ partial, int PB,
-            int QB) {
+            int QB, const int* __restrict__ live) {
+  if (live && *live == 0) return;   // predicated step of a speculative ortho chain (engine.cu)
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = KT + 4;
@@ -189,7 +191,8 @@ constexpr int GRW_CONS = GR_WARPS - 1;
 __global__ void __launch_bounds__(GRW_THREADS, 1)
 gram_ws_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const double* __restrict__ B, int64_t ldb,
                int q, int same, int KT, const __grid_constant__ GramSched sched, double* __restrict__ partial, int PB,
-               int QB) {
+               int QB, const int* __restrict__ live) {
+  if (live && *live == 0) return;   // predicated step of a speculative ortho chain (engine.cu)
   extern __shared__ __align__(16) double smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + GR_STAGES;
@@ -292,7 +295,8 @@ template <bool ALIGN16>
 __global__ void __launch_bounds__(GR_THREADS, 1)
 gram_wsc_kernel(int64_t n, const double* __restrict__ A, int64_t lda, int p, const double* __restrict__ B, int64_t ldb,
                 int q, int same, int KT, const __grid_constant__ GramSched sched, double* __restrict__ partial, int PB,
-                int QB) {
+                int QB, const int* __restrict__ live) {
+  if (live && *live == 0) return;   // predicated step of a speculative ortho chain (engine.cu)
   extern __shared__ __align__(16) double smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + GR_STAGES;
@@ -421,7 +425,8 @@ __device__ __forceinline__ void gram_task_tma_dispatch(int nc0, int nc1, double 
 
 __global__ void __launch_bounds__(GR_THREADS, 1)
 gram_tma_kernel(int64_t n, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int same,
-                int KT, const __grid_constant__ GramSched sched, double* __restrict__ partial, int PB, int QB) {
+                int KT, const __grid_constant__ GramSched sched, double* __restrict__ partial, int PB, int QB, const int* __restrict__ live) {
+  if (live && *live == 0) return;   // predicated step of a speculative ortho chain (engine.cu)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // [ring: GR_STAGES x (nbox x (PB + QB) lines of 128 B)] [barriers]
   const int nbox = KT / GT_BOX_ROWS;
@@ -546,7 +551,9 @@ bool make_tmap(CUtensorMap* tm, const double* base, int64_t n, int ncols, int64_
 
 // deterministic (fixed-order) sum of the per-CTA partials; mirrors the lower triangle if sym
 __global__ void gram_reduce_kernel(const double* __restrict__ partial, int ncta, int PB, int QB, int p, int q,
-                                   int sym, double* __restrict__ C, int ldc, double* __restrict__ Ct) {
+                                   int sym, double* __restrict__ C, int ldc, double* __restrict__ Ct,
+                                   const int* __restrict__ live) {
+  if (live && *live == 0) return;   // predicated step of a speculative ortho chain (engine.cu)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p * q) return;
   const int i = idx % p, j = idx / p;
@@ -704,33 +711,33 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
           const int64_t nch = (n + kt - 1) / kt;
           const int g = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, nch));
           const size_t sm = (size_t)GR_STAGES * cols * kt * 8 + 2 * GR_STAGES * sizeof(uint64_t) + 1024;
-          gram_tma_kernel<<<g, GR_THREADS, sm, st>>>(n, tmA, tmB, same, kt, sch, partial, PB, QB);
+          gram_tma_kernel<<<g, GR_THREADS, sm, st>>>(n, tmA, tmB, same, kt, sch, partial, PB, QB, g_live);
           ++g_launches;
           const int tot = pb * qb;
           double* Cblk = C + p0 + (size_t)q0 * ldc;
           double* Cmir = (sym_lower && !diag_blk) ? C + q0 + (size_t)p0 * ldc : nullptr;
-          gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, g, PB, QB, pb, qb, diag_blk ? 1 : 0, Cblk, ldc, Cmir);
+          gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, g, PB, QB, pb, qb, diag_blk ? 1 : 0, Cblk, ldc, Cmir, g_live);
           ++g_launches;
           launched = true;
         }
       }
       if (launched) continue;
       if (use_bulk)
-        gram_ws_kernel<<<grid, GRW_THREADS, smem_ws, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
+        gram_ws_kernel<<<grid, GRW_THREADS, smem_ws, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB, g_live);
       else if (use_wsc && al16)
-        gram_wsc_kernel<true><<<grid, GR_THREADS, smem_ws, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
+        gram_wsc_kernel<true><<<grid, GR_THREADS, smem_ws, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB, g_live);
       else if (use_wsc)
-        gram_wsc_kernel<false><<<grid, GR_THREADS, smem_ws, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
+        gram_wsc_kernel<false><<<grid, GR_THREADS, smem_ws, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB, g_live);
       else if (al16)
-        gram_kernel<true><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
+        gram_kernel<true><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB, g_live);
       else
-        gram_kernel<false><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB);
+        gram_kernel<false><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB, g_live);
       ++g_launches;
       const int tot = pb * qb;
       double* Cblk = C + p0 + (size_t)q0 * ldc;
       double* Cmir = (sym_lower && !diag_blk) ? C + q0 + (size_t)p0 * ldc : nullptr;
       gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, grid, PB, QB, pb, qb, diag_blk ? 1 : 0, Cblk,
-                                                            ldc, Cmir);
+                                                            ldc, Cmir, g_live);
       ++g_launches;
     }
   DLB_CUDA_CHECK(cudaGetLastError());
@@ -751,7 +758,8 @@ constexpr int BM_STAGES = 4;
 template <int NQT, bool ALIGN16>
 __global__ void __launch_bounds__(BM_THREADS)
 blockmul_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, const double* __restrict__ C, int ldc,
-                int q, double alpha, double beta, double* Y, int64_t ldy) {
+                int q, double alpha, double beta, double* Y, int64_t ldy, const int* __restrict__ live) {
+  if (live && *live == 0) return;   // predicated step of a speculative ortho chain (engine.cu)
   extern __shared__ __align__(16) double smem[];
   constexpr int QB = NQT * 8;
   constexpr int STAGE = BM_KC * BM_SV + QB * BM_SC;
@@ -850,7 +858,8 @@ blockmul_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, con
 template <int NQT, bool ALIGN16>
 __global__ void __launch_bounds__(BM_THREADS)
 blockmul_persistent_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, const double* __restrict__ C,
-                           int ldc, int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri) {
+                           int ldc, int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri, const int* __restrict__ live) {
+  if (live && *live == 0) return;   // predicated step of a speculative ortho chain (engine.cu)
   extern __shared__ __align__(16) double smem[];
   constexpr int QB = NQT * 8;
   constexpr int STAGE = BM_KC * BM_SV;
@@ -982,7 +991,8 @@ constexpr int BMW_STAGES = 4;
 template <int NQT, int NCONS, bool GRAM>
 __global__ void __launch_bounds__((NCONS + 1) * 32)
 blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, const double* __restrict__ C, int ldc,
-                   int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri, double* gpartial) {
+                   int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri, double* gpartial, const int* __restrict__ live) {
+  if (live && *live == 0) return;   // predicated step of a speculative ortho chain (engine.cu)
   extern __shared__ __align__(16) double smem[];
   constexpr int QB = NQT * 8;
   constexpr int BMW_CONS = NCONS;
@@ -1188,7 +1198,7 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
     if (NQT == 5 && smem16 <= 220 * 1024 && n >= 256 * 2 && !g_bmul_small_tiles) {
       const int64_t nt16 = (n + 255) / 256;
       const unsigned grid = (unsigned)std::min<int64_t>(nt16, (int64_t)num_sms);
-      blockmul_ws_kernel<5, 16, false><<<grid, 17 * 32, smem16, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr);
+      blockmul_ws_kernel<5, 16, false><<<grid, 17 * 32, smem16, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr, g_live);
       ++g_launches;
       return;
     }
@@ -1196,7 +1206,7 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
       // two CTAs per SM while C (p x q) is small enough to be resident twice, one beyond (Davidson:
       // p = ldu up to ~400 with q <= 40)
       const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * (smem8 <= 110 * 1024 ? 2 : 1));
-      blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr);
+      blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr, g_live);
       ++g_launches;
       return;
     }
@@ -1210,17 +1220,17 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
     (void)occ_a; (void)occ_u;
     const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * std::max(1, occ));
     if (al16)
-      blockmul_persistent_kernel<NQT, true><<<grid, BM_THREADS, smem_p, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0);
+      blockmul_persistent_kernel<NQT, true><<<grid, BM_THREADS, smem_p, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, g_live);
     else
-      blockmul_persistent_kernel<NQT, false><<<grid, BM_THREADS, smem_p, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0);
+      blockmul_persistent_kernel<NQT, false><<<grid, BM_THREADS, smem_p, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, g_live);
     ++g_launches;
     return;
   }
   const unsigned grid = (unsigned)ntiles;
   if (al16)
-    blockmul_kernel<NQT, true><<<grid, BM_THREADS, smem, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy);
+    blockmul_kernel<NQT, true><<<grid, BM_THREADS, smem, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, g_live);
   else
-    blockmul_kernel<NQT, false><<<grid, BM_THREADS, smem, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy);
+    blockmul_kernel<NQT, false><<<grid, BM_THREADS, smem, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, g_live);
   ++g_launches;
 }
 
@@ -1293,10 +1303,10 @@ void block_mul_gram(cudaStream_t st, int num_sms, int64_t n, const double* V, in
     DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blockmul_ws_kernel<NQT, 8, true>, 9 * 32, smem));
     const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * std::max(1, occ));
     blockmul_ws_kernel<NQT, 8, true><<<grid, 9 * 32, smem, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS,
-                                                                  upper_tri ? 1 : 0, partial);
+                                                                  upper_tri ? 1 : 0, partial, g_live);
     ++g_launches;
     const int tot = q * q;
-    gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, (int)grid, QB, QB, q, q, 1, G, ldg, nullptr);
+    gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, (int)grid, QB, QB, q, q, 1, G, ldg, nullptr, g_live);
     ++g_launches;
     DLB_CUDA_CHECK(cudaGetLastError());
     return;

@@ -140,6 +140,8 @@ struct Engine {
   // small-matrix workspace (device)
   double *d_metric = nullptr, *d_T = nullptr, *d_cholwork = nullptr, *d_xu = nullptr;
   CholStatus* d_cholst = nullptr;
+  OrthoCtl* d_octl = nullptr;      // control block of the speculative ortho chains
+  bool spec_ortho = true;          // DIAGLIB_B200_SPEC_ORTHO=0: one host decision per ortho_cd pass (round-1 behaviour)
 
   // statistics / history / timers of the last driver call
   Hist hist;
@@ -204,7 +206,7 @@ struct Engine {
 
   void ensure_small(int m, int xrows) {
     const size_t mm = (size_t)m * m;
-    const size_t need = (4 * mm + (size_t)xrows * m + 64) * sizeof(double) + sizeof(CholStatus);
+    const size_t need = (4 * mm + (size_t)xrows * m + 64) * sizeof(double) + sizeof(CholStatus) + sizeof(OrthoCtl) + 64;
     if (!smallws.ensure(need)) { fail(DIAGLIB_B200_EALLOC, "memory allocation failed. (small workspace)"); return; }
     double* b = smallws.as<double>();
     d_metric = b;
@@ -212,10 +214,11 @@ struct Engine {
     d_cholwork = b + 2 * mm;
     d_xu = b + 4 * mm;
     d_cholst = reinterpret_cast<CholStatus*>(b + 4 * mm + (size_t)xrows * m + 8);
+    d_octl = reinterpret_cast<OrthoCtl*>(b + 4 * mm + (size_t)xrows * m + 16 + sizeof(CholStatus) / sizeof(double));
   }
 
   void read_back(void* host_dst, const void* dev_src, size_t bytes) {
-    if (bytes <= h_pin_bytes) {
+    if (bytes <= h_pin_bytes - 256) {   // (the last 256 bytes of the pinned buffer carry get_coeffs' status)
       DLB_CUDA_CHECK(cudaMemcpyAsync(h_pin, dev_src, bytes, cudaMemcpyDeviceToHost, st));
       sync();
       std::memcpy(host_dst, h_pin, bytes);
@@ -255,16 +258,18 @@ struct Engine {
   }
 
   // ---- ortho_cd, diaglib.f90:3185-3341 ------------------------------------------------
-  // one host synchronisation per pass (the CholStatus read-back decides macro_done).
+  // Host-driven form: one host synchronisation per pass (the CholStatus read-back decides
+  // macro_done).  Used to CONTINUE a speculative chain that ran out of enqueued passes (it_start,
+  // growth carried over) and when DIAGLIB_B200_SPEC_ORTHO=0.
   // Optional (DIAGLIB_B200_FUSED_GRAM=1, off by default): when another pass is known to follow,
   // the dtrmm of this pass and the metric of the next one are a single kernel (block_mul_gram).
   // Measured in round 1: the fused kernel needs 142 registers -> one CTA per SM, and these
   // HBM-bound shapes lose more from the halved occupancy (+0.40 s per solve) than the saved
   // re-read of u gains (-0.12 s), so the separate kernels stay the default.
-  bool ortho_cd(int64_t n, int m, double* u, int64_t ldu, double& growth, bool have_metric = false) {
+  bool ortho_cd_host(int64_t n, int m, double* u, int64_t ldu, double& growth, bool have_metric = false, int it_start = 0) {
     const int maxit = 10;
-    growth = 1.0;
-    for (int it = 1;; ++it) {
+    if (it_start == 0) growth = 1.0;
+    for (int it = it_start + 1;; ++it) {
       if (it > maxit) {  // 3248-3254
         std::printf("  ortho_cd failed with the following error: maximum number of iterations reached.\n");
         return false;
@@ -300,6 +305,65 @@ struct Engine {
       }
       if (macro_done) return true;
     }
+  }
+
+  // ---- speculative chains: the passes / sweeps the reference is expected to need are enqueued
+  // at once, each step predicated on a cell of OrthoCtl that only chol_inv sets (kernels.h), and
+  // the host reads the control block back ONCE.  Two passes per ortho_cd (the first does the work,
+  // the second confirms eps*rcond^2 < tol: 3331-3332) and two sweeps per ortho_vs_x are the normal
+  // case; anything beyond is continued by the host-driven forms, so the arithmetic and the
+  // decisions are the reference's in every case.
+  static constexpr int SPEC_PASSES = 2, SPEC_SWEEPS = 2, SPEC_CELLS = 2 * SPEC_PASSES + 1;
+  static int cell_pass(int phase, int pass) { return phase * SPEC_CELLS + 2 * (pass - 1); }
+  static int cell_trmm(int phase, int pass) { return cell_pass(phase, pass) + 1; }
+  static int cell_head(int phase) { return (phase - 1) * SPEC_CELLS + 2 * SPEC_PASSES; }   // projection step of sweep `phase` >= 1
+  void chain_begin() {
+    DLB_CUDA_CHECK(cudaMemsetAsync(d_octl, 0, sizeof(OrthoCtl), st));
+    DLB_CUDA_CHECK(cudaMemsetAsync(&d_octl->live[cell_pass(0, 1)], 1, sizeof(int), st));   // any non-zero value
+  }
+  void chain_cd_passes(int64_t n, int m, double* u, int64_t ldu, int phase, bool check_vsx, bool sweep_follows) {
+    for (int p = 1; p <= SPEC_PASSES; ++p) {
+      g_live = &d_octl->live[cell_pass(phase, p)];
+      kgram(n, u, ldu, m, u, ldu, m, d_metric, m, true);         // 3256
+      g_live = nullptr;
+      allreduce(d_metric, (size_t)m * m);                        // (on a stale metric when the pass is not live: unused)
+      CholLink lk;
+      lk.ctl = d_octl;
+      lk.self = cell_pass(phase, p);
+      lk.trmm = cell_trmm(phase, p);
+      lk.next_pass = p < SPEC_PASSES ? cell_pass(phase, p + 1) : -1;
+      lk.next_head = sweep_follows ? cell_head(phase + 1) : -1;
+      lk.next_first = sweep_follows ? cell_pass(phase + 1, 1) : -1;
+      lk.phase = phase;
+      lk.pass = p;
+      lk.check_vsx = check_vsx ? 1 : 0;
+      chol_inv(st, m, d_metric, m, d_T, d_cholwork, d_cholst, lk);   // 3261-3316 + the decisions
+      g_live = &d_octl->live[cell_trmm(phase, p)];
+      ktrmm(n, u, ldu, m, d_T);                                  // 3327
+      g_live = nullptr;
+    }
+  }
+  bool chain_end(OrthoCtl& c) {
+    read_back(&c, d_octl, sizeof c);
+    st_cd_passes += c.passes;
+    st_shifts += c.shifts;
+    if (c.halt == 2) {  // 3276-3284
+      fail(DIAGLIB_B200_ECHOL,
+           "ortho_cd failed with the following error: maximum number of iterations for factorization reached.");
+      return false;
+    }
+    return true;
+  }
+
+  bool ortho_cd(int64_t n, int m, double* u, int64_t ldu, double& growth) {
+    if (!spec_ortho || g_use_fused_gram) return ortho_cd_host(n, m, u, ldu, growth);
+    chain_begin();
+    chain_cd_passes(n, m, u, ldu, 0, false, false);
+    OrthoCtl c;
+    if (!chain_end(c)) return false;
+    growth = c.growth;
+    if (c.pdone[0]) return true;
+    return ortho_cd_host(n, m, u, ldu, growth, false, SPEC_PASSES);   // halt == 3: more passes, host-driven
   }
 
   // ---- ortho (QR fallback), diaglib.f90:3052-3092 --------------------------------------
@@ -347,21 +411,19 @@ struct Engine {
   }
 
   // ---- ortho_vs_x, diaglib.f90:3481-3574; with bx != nullptr b_ortho_vs_x, 3576-3663 ------
-  void ortho_vs_x(int64_t n, int m, int k, const double* x, int64_t ldx, double* u, int64_t ldu,
-                  const double* bx = nullptr) {
-    const double* gx = bx ? bx : x;   // the overlap is taken with B x in the generalized case (3632)
+  // sweeps `it_done`+1, ... of the reference's loop, host-driven (one decision per ortho_cd pass)
+  void ortho_vs_x_sweeps(int64_t n, int m, int k, const double* x, int64_t ldx, double* u, int64_t ldu, const double* gx,
+                         int it_done) {
     const int maxit = 10;
     bool done = false;
-    int it = 0;
+    int it = it_done;
     double growth = 1.0;
-    bool ok = ortho_cd(n, k, u, ldu, growth);       // 3533
-    if (status) return;
-    if (!ok) ortho_qr(n, k, u, ldu);                // 3534
     while (!done) {
       ++it;
       ++st_sweeps;
       kgram(n, gx, ldx, m, u, ldu, k, d_xu, m, false);  // 3543 / 3632
       allreduce(d_xu, (size_t)m * k);
+      bool ok;
       if (k <= 40 && g_use_fused_gram) {
         // 3544 fused with the first metric (3256) of the ortho_cd that follows
         PhaseHandle hh;
@@ -369,31 +431,82 @@ struct Engine {
         block_mul_gram(st, num_sms, n, x, ldx, m, d_xu, m, k, -1.0, 1.0, u, ldu, false, d_metric, k, partial.as<double>());
         if (profile) ph_close(hh);
         allreduce(d_metric, (size_t)k * k);
-        ok = ortho_cd(n, k, u, ldu, growth, true);                                           // 3548
+        ok = ortho_cd_host(n, k, u, ldu, growth, true);                                      // 3548
       } else {
         kbmul(n, x, ldx, m, d_xu, m, k, -1.0, 1.0, u, ldu);                          // 3544
-        ok = ortho_cd(n, k, u, ldu, growth);                                                 // 3548
+        ok = ortho_cd_host(n, k, u, ldu, growth);                                            // 3548
       }
       if (status) return;
-      double xu_norm;
-      if (!ok) {                                                                             // 3549,3558-3560
-        ortho_qr(n, k, u, ldu);
-        kgram(n, gx, ldx, m, u, ldu, k, d_xu, m, false);
-        allreduce(d_xu, (size_t)m * k);
-        std::vector<double> h((size_t)m * k);
-        read_back(h.data(), d_xu, h.size() * sizeof(double));
-        double s = 0.0;
-        for (double v : h) s += v * v;
-        xu_norm = std::sqrt(s);
-      } else {
-        xu_norm = growth * EPS;                                                              // 3562
-      }
-      done = xu_norm < TOL_ORTHO;
+      done = sweep_verdict(n, m, k, gx, ldx, u, ldu, ok, growth);
+      if (status) return;
       if (it > maxit && !done) {                                                             // 3568
         fail(DIAGLIB_B200_EORTHO, " catastrophic failure of ortho_vs_x");
         return;
       }
     }
+  }
+  // end of a sweep (3549-3566): QR fallback + explicit overlap norm when ortho_cd gave up,
+  // growth * eps otherwise
+  bool sweep_verdict(int64_t n, int m, int k, const double* gx, int64_t ldx, double* u, int64_t ldu, bool ok, double growth) {
+    double xu_norm;
+    if (!ok) {                                                                               // 3549,3558-3560
+      ortho_qr(n, k, u, ldu);
+      kgram(n, gx, ldx, m, u, ldu, k, d_xu, m, false);
+      allreduce(d_xu, (size_t)m * k);
+      std::vector<double> h((size_t)m * k);
+      read_back(h.data(), d_xu, h.size() * sizeof(double));
+      double s = 0.0;
+      for (double v : h) s += v * v;
+      xu_norm = std::sqrt(s);
+    } else {
+      xu_norm = growth * EPS;                                                                // 3562
+    }
+    return xu_norm < TOL_ORTHO;
+  }
+
+  void ortho_vs_x(int64_t n, int m, int k, const double* x, int64_t ldx, double* u, int64_t ldu,
+                  const double* bx = nullptr) {
+    const double* gx = bx ? bx : x;   // the overlap is taken with B x in the generalized case (3632)
+    if (!spec_ortho || g_use_fused_gram) {
+      double growth = 1.0;
+      const bool ok = ortho_cd_host(n, k, u, ldu, growth);   // 3533
+      if (status) return;
+      if (!ok) ortho_qr(n, k, u, ldu);                       // 3534
+      ortho_vs_x_sweeps(n, m, k, x, ldx, u, ldu, gx, 0);
+      return;
+    }
+    // speculative chain: ortho_cd (3533), then SPEC_SWEEPS x { u -= x (gx^T u) (3543-3544), ortho_cd (3548) }
+    chain_begin();
+    chain_cd_passes(n, k, u, ldu, 0, false, true);
+    for (int sw = 1; sw <= SPEC_SWEEPS; ++sw) {
+      const int* head = &d_octl->live[cell_head(sw)];
+      g_live = head;
+      kgram(n, gx, ldx, m, u, ldu, k, d_xu, m, false);           // 3543 / 3632
+      g_live = nullptr;
+      allreduce(d_xu, (size_t)m * k);
+      g_live = head;
+      kbmul(n, x, ldx, m, d_xu, m, k, -1.0, 1.0, u, ldu);        // 3544
+      g_live = nullptr;
+      chain_cd_passes(n, k, u, ldu, sw, true, sw < SPEC_SWEEPS);
+    }
+    OrthoCtl c;
+    if (!chain_end(c)) return;
+    st_sweeps += c.last_phase;
+    if (c.done_vsx) return;
+    // the chain stopped short of the reference's loop: pick it up where it stands
+    int sweeps_done = c.last_phase;
+    if (c.halt == 3) {   // ortho_cd number last_phase wants more passes than were enqueued
+      double growth = c.growth;
+      const bool ok = ortho_cd_host(n, k, u, ldu, growth, false, SPEC_PASSES);
+      if (status) return;
+      if (c.last_phase == 0) {
+        if (!ok) ortho_qr(n, k, u, ldu);                          // 3534
+      } else {
+        const bool done = sweep_verdict(n, m, k, gx, ldx, u, ldu, ok, growth);
+        if (status || done) return;
+      }
+    }
+    ortho_vs_x_sweeps(n, m, k, x, ldx, u, ldu, gx, sweeps_done);
   }
 
   // global row count / offset of this rank's row block
@@ -741,6 +854,10 @@ void Engine::lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, in
     ind_w = ind_p + n_act;
     h = ph_open(PH_DIAG);
     get_coeffs(st, len_u, len_u, n_max, n_act, a_red, u_p, cf_work, d_cfst);            // 488
+    // its status travels to pinned memory behind the kernel and is looked at after the next
+    // synchronisation of the stream (the ortho_vs_x below), not with a blocking copy
+    CoeffStatus* h_cfst = reinterpret_cast<CoeffStatus*>(static_cast<char*>(h_pin) + h_pin_bytes - 256);
+    DLB_CUDA_CHECK(cudaMemcpyAsync(h_cfst, d_cfst, sizeof(CoeffStatus), cudaMemcpyDeviceToHost, st));
     ph_close(h);
     // p = space u_p, ap = aspace u_p (495-498), written straight into the p columns of the next
     // space / aspace; x_new / ax_new already sit in its first n_max columns (510-511 need no copy)
@@ -770,9 +887,8 @@ void Engine::lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, in
       b_ortho(nn, n_act, COL(space, ind_w), nn, COL(bspace, ind_w), nn);
       ph_close(h);
     }
-    {
-      CoeffStatus cs;  // checked lazily: the ortho_vs_x above has synchronised the stream
-      DLB_CUDA_CHECK(cudaMemcpy(&cs, d_cfst, sizeof cs, cudaMemcpyDeviceToHost));
+    if (status == 0) {
+      const CoeffStatus cs = *h_cfst;  // the ortho_vs_x above has synchronised the stream since the copy was enqueued
       st_sweeps += cs.sweeps;
       st_cd_passes += cs.cd_passes;
       st_qr += cs.qr;
@@ -1442,12 +1558,16 @@ int32_t diaglib_b200_init(int32_t device) {
   if (!g.partial.ensure(gram_scratch_bytes(128, 128, g.num_sms))) return DIAGLIB_B200_EALLOC;
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_WS")) g_disable_ws = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_FUSED_GRAM")) g_use_fused_gram = ev[0] == '1';
+  if (const char* ev = std::getenv("DIAGLIB_B200_SPEC_ORTHO")) g.spec_ortho = ev[0] != '0';
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_TMA")) g_disable_tma = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_EIG_COOP_MIN_K")) g_eig_coop_min_k = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_EIG_MODE")) g_eig_mode = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_EIG_BLOCK")) g_eig_block = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_SHORT")) g_spmm_short = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_CHUNK")) g_spmm_chunk = std::atoi(ev);
+  if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_TAIL")) g_spmm_tail = std::atoi(ev);
+  if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_MINB")) g_spmm_minb = std::atoi(ev);
+  if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_CHUNK_TILED")) g_spmm_chunk_tiled = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_BMUL_RT256")) g_bmul_small_tiles = ev[0] != '1';
   g.inited = true;
   g.status = 0;
@@ -2076,6 +2196,7 @@ int32_t diaglib_b200_k_true_residual(int32_t n_loc, int32_t m, const double* x_d
                                      double* norms_host) {
   if (!require_init()) return DIAGLIB_B200_ENODEVICE;
   if (g.A.n != n_loc) return DIAGLIB_B200_EARG;
+  g.status = 0;
   DevBuf ax, tmp;
   if (!ax.ensure((size_t)std::max(1, n_loc) * m * sizeof(double)) || !tmp.ensure((4 * (size_t)m + 16) * sizeof(double)) ||
       !g.resid_scratch.ensure(residual_scratch_bytes(m, g.num_sms)))
@@ -2098,6 +2219,11 @@ int32_t diaglib_b200_k_true_residual(int32_t n_loc, int32_t m, const double* x_d
   return g.status;
 }
 
+int32_t diaglib_b200_k_set_spec_ortho(int32_t on) {
+  const int prev = g.spec_ortho ? 1 : 0;
+  g.spec_ortho = on != 0;
+  return prev;
+}
 int32_t diaglib_b200_k_set_eig_mode(int32_t mode, int32_t block) {
   const int prev = g_eig_mode;
   g_eig_mode = mode;

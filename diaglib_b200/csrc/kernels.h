@@ -18,8 +18,16 @@ extern bool g_eig_two_sided;
 extern int g_eig_coop_min_k;
 extern int g_eig_mode;
 extern int g_eig_block;
+// Predicate of the dense kernels (gram_tn, block_mul, block_trmm_inplace, block_mul_gram): while it
+// points to a device int, every kernel these wrappers launch returns at once when that int is 0.
+// The engine sets it around the steps of a speculative ortho_cd / ortho_vs_x chain, whose control
+// flow (another pass? another sweep?) is decided on the device by chol_inv (OrthoCtl below).
+extern const int* g_live;
 extern int g_spmm_short;
 extern int g_spmm_chunk;
+extern int g_spmm_tail;
+extern int g_spmm_minb;
+extern int g_spmm_chunk_tiled;
 
 // ---- dense.cu -------------------------------------------------------------------------
 // C(p x q, ldc) = A(n x p, lda)^T * B(n x q, ldb).  Replaces dgemm('t','n',p,q,n,...) at
@@ -103,11 +111,37 @@ struct CholStatus {      // written by chol_inv, read back by the host control l
   int hard_fail;         // shift loop exhausted (3276-3284)
   int pad;
 };
+// Device-side control of a speculative ortho_cd / ortho_vs_x chain (diaglib.f90:3246-3333,
+// 3533-3568): the host enqueues the passes and sweeps it expects without reading anything back;
+// each step group runs only if its cell of `live` is set, and the only kernel that sets cells is
+// chol_inv, which holds the reference's decisions (macro_done 3331-3332, xu_norm < tol 3562-3566).
+struct OrthoCtl {
+  int live[48];          // live[g] != 0: the kernels of step group g run
+  int halt;              // 0 = ran to the end of what was decided; 2 = Cholesky shift loop exhausted (3276-3284);
+                         // 3 = the passes enqueued for an ortho_cd did not reach macro_done
+  int done_vsx;          // 1: xu_norm = growth * eps fell below tol_ortho (ortho_vs_x finished)
+  int last_phase;        // ortho_cd instance of the last factorisation that ran (0 = the initial one, s = after sweep s)
+  int last_pass;         // its pass number (1-based)
+  int passes, shifts;    // totals of the chain (statistics)
+  int pdone[8];          // per ortho_cd instance: the pass that reached macro_done (0 = none yet)
+  double growth;         // of the current ortho_cd (3323)
+};
+struct CholLink {        // where a chol_inv call sits in the chain (ctl = null: plain call)
+  OrthoCtl* ctl = nullptr;
+  int self = 0;          // cell that enables this pass (gram + chol_inv)
+  int trmm = 0;          // cell chol_inv sets for the triangular multiply of this pass
+  int next_pass = -1;    // cell of the next pass of the same ortho_cd (-1: none enqueued)
+  int next_head = -1;    // cell of the next sweep's projection step (-1: none enqueued)
+  int next_first = -1;   // cell of the first pass of the ortho_cd after that sweep
+  int phase = 0, pass = 1;
+  int check_vsx = 0;     // this ortho_cd closes a sweep of ortho_vs_x: test xu_norm when it is done
+};
 // metric (m x m, ldm) -> Linv_t_full (m x m, ld m): the matrix T = L^-T (upper triangular,
 // explicit zeros below) such that U_ortho = U * T.  Follows dpotrf('l') 3261, the shift loop
 // 3265-3295, dtrtri('l','n') 3310 and norm_est 3314-3315.
 // `work` must hold 2*m*m doubles.
-void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, double* work, CholStatus* status_dev);
+void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, double* work, CholStatus* status_dev,
+              const CholLink& link = CholLink());
 
 struct EigStatus { int sweeps; int converged; int path; };  // path: 1 = one-sided on the Cholesky factor, 2 = two-sided
 // Symmetric eigensolver replacing dsyev('v',uplo) (315,406,1708): a (k x k, lda) is

@@ -154,9 +154,11 @@ __device__ void cta_chol_inv(int m, const double* G, int ldg, double* L, double*
 }
 
 __global__ void __launch_bounds__(SM_THREADS)
-chol_inv_kernel(int m, const double* G, int ldg, double* T, double* work, CholStatus* st) {
+chol_inv_kernel(int m, const double* G, int ldg, double* T, double* work, CholStatus* st, CholLink link) {
   __shared__ double s_red[32];
   extern __shared__ __align__(16) double dyn[];
+  OrthoCtl* ctl = link.ctl;
+  if (ctl && ctl->live[link.self] == 0) return;   // this pass was not decided (uniform)
   double* L = work;
   double* Li = work + (size_t)m * m;
   if (2 * m * m * (int)sizeof(double) <= 96 * 1024) {  // keep the factors on chip when small
@@ -164,6 +166,27 @@ chol_inv_kernel(int m, const double* G, int ldg, double* T, double* work, CholSt
     Li = dyn + (size_t)m * m;
   }
   cta_chol_inv(m, G, ldg, L, Li, T, st, s_red);
+  if (ctl && threadIdx.x == 0) {
+    // the reference's control flow of ortho_cd / ortho_vs_x, decided here instead of on the host
+    ctl->passes += 1;
+    ctl->shifts += st->n_shifts;
+    ctl->last_phase = link.phase;
+    ctl->last_pass = link.pass;
+    if (st->hard_fail) { ctl->halt = 2; return; }                 // 3276-3284: nothing after this runs
+    ctl->live[link.trmm] = 1;                                      // 3327
+    const double growth = (link.pass == 1 ? 1.0 : ctl->growth) * st->linv_norm;   // 3323
+    ctl->growth = growth;
+    const double rcond = st->l_norm * st->linv_norm;
+    if (EPS * rcond * rcond < TOL_ORTHO) {                         // macro_done, 3331-3332
+      ctl->pdone[link.phase] = link.pass;
+      if (link.check_vsx && growth * EPS < TOL_ORTHO) { ctl->done_vsx = 1; return; }   // 3562-3566
+      if (link.next_head >= 0) { ctl->live[link.next_head] = 1; ctl->live[link.next_first] = 1; }
+    } else if (link.next_pass >= 0) {
+      ctl->live[link.next_pass] = 1;
+    } else {
+      ctl->halt = 3;                                               // the host continues this ortho_cd
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -935,7 +958,8 @@ get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_re
 
 }  // namespace
 
-void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, double* work, CholStatus* status_dev) {
+void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, double* work, CholStatus* status_dev,
+              const CholLink& link) {
   static bool attr_set = false;
   if (!attr_set) {
     DLB_CUDA_CHECK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -944,7 +968,7 @@ void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, 
   const size_t need = 2 * (size_t)m * m * sizeof(double);
   const size_t smem = need <= 96 * 1024 ? need : 0;
   const int threads = m <= 48 ? 256 : SM_THREADS;
-  chol_inv_kernel<<<1, threads, smem, st>>>(m, metric, ldm, T, work, status_dev);
+  chol_inv_kernel<<<1, threads, smem, st>>>(m, metric, ldm, T, work, status_dev, link);
   ++g_launches;
   DLB_CUDA_CHECK(cudaGetLastError());
 }

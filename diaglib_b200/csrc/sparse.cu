@@ -8,6 +8,9 @@
 namespace dlb {
 int g_spmm_short = 1;
 int g_spmm_chunk = 24;
+int g_spmm_tail = 1;     // DIAGLIB_B200_SPMM_TAIL=0: the m mod 8 remainder through the generic row loop (round 1)
+int g_spmm_minb = 4;     // DIAGLIB_B200_SPMM_MINB=3: three instead of four CTAs per SM (85 registers)
+int g_spmm_chunk_tiled = 0;   // DIAGLIB_B200_SPMM_CHUNK_TILED=1: column chunks also with a caller-given row order
 namespace {
 
 // ---------------------------------------------------------------------------------------
@@ -101,8 +104,11 @@ __device__ __forceinline__ int32_t ld_nc_s32(const int32_t* p) {
   return v;
 }
 
-template <int JB, int KMAX>
-__global__ void __launch_bounds__(256, 4)
+// TAIL (0..JB-1) = m mod JB, known at compile time: the last, narrower column block runs through
+// the same register-resident loop as the full blocks (a generic tail loop for 5 of 37 columns
+// used to cost as much as a full block of 8).
+template <int JB, int KMAX, int TAIL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 spmm_csr_short_kernel(int64_t n, int64_t n_halo, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                       const double* __restrict__ val, int m, const double* __restrict__ x, int64_t ldx,
                       const double* __restrict__ xh, double* __restrict__ ax, int64_t ldax, double shift,
@@ -153,8 +159,32 @@ spmm_csr_short_kernel(int64_t n, int64_t n_halo, const int64_t* __restrict__ row
       }
     }
   }
-  if (valid && j0 < m)
+  if (TAIL == 0 && valid && j0 < m)   // (only when the tail instantiations are switched off)
     spmm_row_generic<JB>(row, b, b + len, j0, n, n_halo, col, val, m, x, ldx, xh, ax, ldax, shift);
+  if (TAIL > 0) {   // m - j0 == TAIL by construction (the launcher picks the instantiation)
+    constexpr int JT = TAIL > 0 ? TAIL : 1;
+    double acc[JT];
+#pragma unroll
+    for (int jj = 0; jj < JT; ++jj) acc[jj] = 0.0;
+    const double* xb = x + (int64_t)j0 * ldx;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int kk = len > 0 ? (k < len ? k : len - 1) : 0;
+      double v = len > 0 ? ld_nc_f64(val + b + kk) : 0.0;
+      v = k < len ? v : 0.0;
+      const double* xp = xb + c[k];
+#pragma unroll
+      for (int jj = 0; jj < JT; ++jj) acc[jj] = fma(v, ld_nc_f64(xp + (int64_t)jj * ldx), acc[jj]);
+    }
+    if (valid) {
+#pragma unroll
+      for (int jj = 0; jj < JT; ++jj) {
+        double s = acc[jj];
+        if (shift != 0.0) s = fma(shift, xb[row + (int64_t)jj * ldx], s);
+        ax[row + (int64_t)(j0 + jj) * ldax] = s;
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -308,16 +338,27 @@ void spmm_csr(cudaStream_t st, const CsrDevice& A, int m, const double* x, int64
     // With a locality-preserving row order (A.tiled) the window is a tile neighbourhood and one
     // launch sweeps all columns.
     int jc = m;
-    if (g_spmm_chunk > 0 && m > g_spmm_chunk && !A.tiled) {
+    if (g_spmm_chunk > 0 && m > g_spmm_chunk && (!A.tiled || g_spmm_chunk_tiled)) {
       const int npass = (m + g_spmm_chunk - 1) / g_spmm_chunk;
       jc = (((m + npass - 1) / npass) + 7) / 8 * 8;
     }
     for (int j0 = 0; j0 < m; j0 += jc) {
       const int mc = std::min(jc, m - j0);
       // halo block columns are n_halo apart
-      spmm_csr_short_kernel<8, 7><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, mc, x + (int64_t)j0 * ldx, ldx,
-                                                        x_halo ? x_halo + (int64_t)j0 * A.n_halo : nullptr,
-                                                        ax + (int64_t)j0 * ldax, ldax, shift, A.order, first, count);
+      const double* xc = x + (int64_t)j0 * ldx;
+      const double* hc = x_halo ? x_halo + (int64_t)j0 * A.n_halo : nullptr;
+      double* axc = ax + (int64_t)j0 * ldax;
+#define DLB_SHORT(T)                                                                                                      \
+  case T:                                                                                                                 \
+    if (g_spmm_minb == 3)                                                                                                 \
+      spmm_csr_short_kernel<8, 7, T, 3><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, mc, xc, ldx, hc, axc, ldax, \
+                                                              shift, A.order, first, count);                             \
+    else                                                                                                                  \
+      spmm_csr_short_kernel<8, 7, T, 4><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, mc, xc, ldx, hc, axc, ldax, \
+                                                              shift, A.order, first, count);                             \
+    break;
+      switch (g_spmm_tail ? mc % 8 : 0) { DLB_SHORT(0) DLB_SHORT(1) DLB_SHORT(2) DLB_SHORT(3) DLB_SHORT(4) DLB_SHORT(5) DLB_SHORT(6) DLB_SHORT(7) }
+#undef DLB_SHORT
       ++g_launches;
     }
   } else {

@@ -124,6 +124,12 @@ def set_eig_mode(mode: int, block: int = 0) -> int:
     return int(lib().diaglib_b200_k_set_eig_mode(int(mode), int(block)))
 
 
+def set_spec_ortho(on: bool) -> bool:
+    """speculative (device-decided) ortho_cd / ortho_vs_x chains on/off; returns the previous setting"""
+    init()
+    return bool(lib().diaglib_b200_k_set_spec_ortho(1 if on else 0))
+
+
 def sym_eig_time_ms(a: np.ndarray, upper: bool = False, reps: int = 10) -> float:
     init()
     a = np.asfortranarray(a, dtype=np.float64)

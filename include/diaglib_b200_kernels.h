@@ -69,6 +69,10 @@ int32_t diaglib_b200_k_sym_eig(int32_t k, double* a_host, int32_t lda, int32_t u
  * (default), 1 = two-sided only; block = columns per block of the one-sided solver (0 = automatic,
  * else 4 or 8).  Returns the previous mode. */
 int32_t diaglib_b200_k_set_eig_mode(int32_t mode, int32_t block);
+/* ortho_cd / ortho_vs_x control: 1 = speculative chains decided on the device, one host
+ * synchronisation per call (default); 0 = one host decision per ortho_cd pass.  Same arithmetic
+ * and same decisions either way.  Returns the previous setting. */
+int32_t diaglib_b200_k_set_spec_ortho(int32_t on);
 /* times `reps` back-to-back reduced eigensolves of the same host matrix on the device (CUDA events
  * on the library stream, input restored by a device copy before each solve, the copy excluded by
  * measuring it separately); returns milliseconds per solve */

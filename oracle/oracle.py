@@ -258,6 +258,12 @@ def diag_precnd(x, fac):
     return px
 
 
+def set_accurate_eig(on: bool):
+    """DIAGNOSTIC: reduced eigenproblems through dpotrf + dgesvj (high relative accuracy) instead of
+    dsyev; never the default (see diaglib_oracle.cpp, reduced_eig)"""
+    lib().oracle_set_accurate_eig(1 if on else 0)
+
+
 def set_threads(n):
     lib().oracle_set_threads(int(n))
 

@@ -686,16 +686,22 @@ def test_ortho_qr_fallback(gpu_lib, oracle):
 
 def test_c3_bench_workload_nx128_vs_oracle_fixture(gpu_lib):
     """The benchmark workload itself (bench.py: C3, 32 roots of 37, tol 1e-8, lowest-diagonal start
-    + 10 % noise) at 128^3 = 2 097 152 rows against the oracle's complete solve of the same problem
-    (tests/golden/c3_oracle_nx128.json, written by `bench.py --impl reference --nx 128`; the
-    oracle needs about two minutes for it, hence a fixture): eigenvalues 1e-10 relative,
-    residuals below tol, iteration count within +-1.  diaglib.f90:389-533."""
+    + 10 % noise) at 128^3 = 2 097 152 rows against the oracle's complete solves of the same problem
+    (fixtures: the oracle needs one to two minutes each).  diaglib.f90:389-533.
+      * eigenvalues 1e-10 relative against the literal reference (dsyev), residuals below tol;
+      * iteration count: the dsyev oracle needs 27, the same oracle with LAPACK's accurate route for
+        the reduced problem (dpotrf + dgesvj) 23 -- dsyev's eps*|a_red| eigenvector error
+        (|a_red| ~ n) holds max|r| up near the 1e-7 threshold; the GPU path's Jacobi solvers do not
+        have that floor.  Required: within +-1 of the accurate-eigensolver oracle and never more
+        iterations than the dsyev oracle (bench.parity_block documents the same at 256^3)."""
     import bench
     gold = json.load(open(os.path.join(GOLD, "c3_oracle_nx128.json")))
+    gold_acc = json.load(open(os.path.join(GOLD, "c3_oracle_acc_nx128.json")))
     nx = gold["nx"]
     n, n_targ = nx ** 3, bench.N_TARG
     n_max = P.n_eig_rule(n_targ)
     assert (gold["n_targ"], gold["tol"], gold["delta"], gold["noise"]) == (n_targ, bench.TOL, bench.DELTA, bench.NOISE)
+    assert gold_acc["nx"] == nx and gold_acc["accurate_eig"] and gold_acc["ok"]
     csr = P.lap3d(nx, nx, nx, delta=bench.DELTA)
     gpu_lib.set_csr(*csr)
     ev = bench.make_guess(csr[3], n, n_max, 0, n)
@@ -703,11 +709,49 @@ def test_c3_bench_workload_nx128_vs_oracle_fixture(gpu_lib):
     ok = gpu_lib.lobpcg_driver(False, False, n, n_targ, n_max, bench.MAX_ITER, bench.TOL, 0.0, None, None, None, eig, ev)
     hg = gpu_lib.last_history(n_max)
     par = bench.parity_block(dict(gold, _source="tests/golden/c3_oracle_nx128.json"), len(hg["it"]), eig, hg["rms"][-1],
-                             hg["max"][-1])
+                             hg["max"][-1], gold_acc)
     print(par)
     assert ok and gold["ok"]
-    assert par["max_rel_eig_err"] <= REL
-    assert abs(par["its_gpu"] - par["its_oracle"]) <= 1
-    assert par["max_rms"] < bench.TOL and par["ok"]
+    assert par["max_rel_eig_err"] <= REL and par["max_rel_eig_err_vs_accurate_eig_oracle"] <= REL
+    assert par["max_rms"] < bench.TOL and par["max_abs_residual"] < 10 * bench.TOL
+    assert abs(par["its_gpu"] - par["its_oracle_accurate_eig"]) <= 1
+    assert par["its_gpu"] <= par["its_oracle"]
+    assert par["ok"]
     check_solution(csr, eig, ev, n_targ, bench.TOL)
     gpu_lib.lib().diaglib_b200_release_workspace()
+
+
+@pytest.mark.parametrize("driver", ["lobpcg", "davidson"])
+def test_speculative_ortho_chains_change_nothing_but_the_sync_count(gpu_lib, driver):
+    """ortho_cd / ortho_vs_x decided on the device (one read-back per call) against the
+    host-driven form (one per pass): same decisions, same arithmetic -> bit-identical histories
+    and pass / sweep counts; at most 3 host synchronisations per LOBPCG iteration
+    (diaglib.f90:3246-3333, 3533-3568)."""
+    from diaglib_b200 import kernels as K
+    csr = P.lap3d(32, 32, 16, delta=1.0)
+    n, n_targ = 1 << 14, 6
+    n_max = P.n_eig_rule(n_targ)
+    gpu_lib.set_csr(*csr)
+    g = noisy_unit_guess(csr, n_max, eps=0.03)
+    runs = {}
+    for spec in (True, False):
+        prev = K.set_spec_ortho(spec)
+        try:
+            ev, eig = g.copy(order="F"), np.zeros(n_max)
+            if driver == "lobpcg":
+                ok = gpu_lib.lobpcg_driver(False, False, n, n_targ, n_max, 200, 1e-8, 0.0, None, None, None, eig, ev)
+            else:
+                ok = gpu_lib.davidson_driver(False, n, n_targ, n_max, 200, 1e-8, 10, 0.0, None, None, eig, ev)
+            runs[spec] = (ok, eig, ev, gpu_lib.last_history(n_max), gpu_lib.last_stats())
+        finally:
+            K.set_spec_ortho(prev)
+    (ok1, e1, v1, h1, s1), (ok0, e0, v0, h0, s0) = runs[True], runs[False]
+    assert ok1 and ok0
+    assert np.array_equal(h1["eig"], h0["eig"]) and np.array_equal(h1["rms"], h0["rms"]) and np.array_equal(e1, e0)
+    assert np.array_equal(v1, v0)
+    assert (s1["ortho_cd_passes"], s1["ortho_vs_x_sweeps"], s1["qr_fallbacks"]) == (s0["ortho_cd_passes"], s0["ortho_vs_x_sweeps"], s0["qr_fallbacks"])
+    its = len(h1["it"])
+    print(f"{driver}: {its} iterations, host syncs speculative {s1['host_syncs']} vs host-driven {s0['host_syncs']}")
+    assert s1["host_syncs"] < s0["host_syncs"]
+    if driver == "lobpcg":
+        assert s1["host_syncs"] <= 3 * its + 8     # set-up + final copy on top of <= 3 per iteration

@@ -273,3 +273,43 @@ def test_bench_parity_block_logic():
     bad_i = bench.parity_block(gold, gold["iterations"] + 2, e, np.array(gold["rms"]), np.array(gold["max"]))
     bad_r = bench.parity_block(gold, gold["iterations"], e, np.array(gold["rms"]) + 1e-7, np.array(gold["max"]))
     assert not bad_e["ok"] and not bad_i["ok"] and not bad_r["ok"]
+
+
+def test_oracle_accurate_reduced_eig_is_a_diagnostic_not_the_default(oracle):
+    """the oracle's reduced eigenproblems go through LAPACK dsyev like the reference
+    (diaglib.f90:315,406,1708); oracle_set_accurate_eig(1) switches them to dpotrf + dgesvj for ONE
+    purpose: to measure how much of an iteration-count difference is dsyev's absolute accuracy
+    (bench.parity_block).  On a graded LOBPCG-like matrix dsyev leaves residuals ~eps*|A|, the
+    diagnostic route residuals relative to each eigenvalue."""
+    import ctypes as C
+    rng = np.random.default_rng(12)
+    k = 111
+    d = np.concatenate([np.arange(7.0, 44.0), 50 + 1e3 * rng.random(37), 1e6 + 1e7 * rng.random(37)])
+    cpl = rng.standard_normal((k, k))
+    cpl = 1e-3 * (cpl + cpl.T) * np.sqrt(np.outer(d, d)) / d.max() ** 0.5
+    a = np.diag(d) + cpl
+    np.fill_diagonal(a, d)
+
+    def red(upper):
+        z = np.asfortranarray((np.triu(a) if upper else np.tril(a)).copy())
+        w, info = np.zeros(k), C.c_int32(0)
+        oracle.lib().oracle_reduced_eig(C.byref(C.c_int32(k)), z.ctypes.data_as(C.c_void_p), C.byref(C.c_int32(k)),
+                                        w.ctypes.data_as(C.c_void_p), C.byref(info), C.byref(C.c_int32(1 if upper else 0)))
+        assert info.value == 0
+        al, zl, wl = a.astype(np.longdouble), z.astype(np.longdouble), w.astype(np.longdouble)
+        res = np.linalg.norm((al @ zl - zl * wl).astype(np.float64), axis=0)
+        return w, z, res
+
+    w0, z0, r0 = red(False)                      # default = dsyev
+    oracle.set_accurate_eig(True)
+    try:
+        for upper in (False, True):
+            w1, z1, r1 = red(upper)
+            assert (r1[:37] / w1[:37]).max() < 1e-12
+            assert np.abs(z1.T @ z1 - np.eye(k)).max() < 1e-13
+            assert np.abs(w1 - w0).max() < 1e-8 * 10 and np.all(np.diff(w1) > 0)
+    finally:
+        oracle.set_accurate_eig(False)
+    assert (r0[:37] / w0[:37]).max() > 1e-11     # what the reference's dsyev delivers on this matrix
+    w2, _, _ = red(False)
+    assert np.array_equal(w2, w0)                # the switch is off again

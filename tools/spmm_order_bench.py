@@ -25,10 +25,17 @@ x = K.DeviceArray((n, mmax))
 y = K.DeviceArray((n, mmax))
 lib.diaglib_b200_k_fill_uniform(x.ptr, n, mmax, n, 1)
 out = []
+# usage: spmm_order_bench.py NX [label] [tile specs like 64x2x2 ...]   (default: a sweep of shapes)
+label = sys.argv[2] if len(sys.argv) > 2 else ""
 orders = [("natural", None)]
-for tile in [(32, 4, 2), (16, 4, 4), (32, 8, 1), (32, 2, 4), (64, 2, 2), (32, 4, 2)]:
-    for curve in ("morton", "sweep"):
-        orders.append((f"tile{tile}-{curve}", (tile, curve)))
+if len(sys.argv) > 3:
+    for spec in sys.argv[3:]:
+        tile = tuple(int(v) for v in spec.split("x"))
+        orders.append((f"tile{tile}-morton", (tile, "morton")))
+else:
+    for tile in [(32, 4, 2), (16, 4, 4), (32, 8, 1), (32, 2, 4), (64, 2, 2), (32, 4, 2)]:
+        for curve in ("morton", "sweep"):
+            orders.append((f"tile{tile}-{curve}", (tile, curve)))
 seen = set()
 for name, spec in orders:
     if name in seen:
@@ -45,7 +52,7 @@ for name, spec in orders:
             lib.diaglib_b200_csr_matvec(i32(n), i32(m), C.c_void_p(x.ptr), C.c_void_p(y.ptr))
         ms = K.timer_stop_ms() / reps
         b = 12.0 * nnz + 8.0 * (n + 1) + 16.0 * n * m
-        rec = {"order": name, "m": m, "ms": round(ms, 4), "gbs": round(b / ms / 1e6, 1), "frac_hbm": round(b / ms / 1e6 / peak, 4)}
+        rec = {"label": label, "order": name, "m": m, "ms": round(ms, 4), "gbs": round(b / ms / 1e6, 1), "frac_hbm": round(b / ms / 1e6 / peak, 4)}
         out.append(rec)
         print(json.dumps(rec), flush=True)
-json.dump(out, open("gpurun_out/spmm_order_bench.json", "w"), indent=1)
+json.dump(out, open(f"gpurun_out/spmm_order_bench{('_' + label) if label else ''}.json", "w"), indent=1)
