@@ -141,6 +141,7 @@ struct Engine {
   double *d_metric = nullptr, *d_T = nullptr, *d_cholwork = nullptr, *d_xu = nullptr;
   CholStatus* d_cholst = nullptr;
   OrthoCtl* d_octl = nullptr;      // control block of the speculative ortho chains
+  bool reference_restart = false;  // gen_david_driver: reproduce diaglib.f90:2200 literally (off: keep B * restart vectors)
   bool spec_ortho = true;          // DIAGLIB_B200_SPEC_ORTHO=0: one host decision per ortho_cd pass (round-1 behaviour)
 
   // statistics / history / timers of the last driver call
@@ -1111,6 +1112,9 @@ void Engine::davidson(bool verbose, bool gen, int n, int n_targ, int n_max, int 
         h = ph_open(PH_ORTHO);
         b_ortho(nn, n_max, space, nn, bspace, nn);
         ph_close(h);
+        // DIAGLIB_B200_REFERENCE_RESTART=1: the reference's literal `bspace = zero` (2200), which
+        // discards B times the restart vectors (the run then reports ok with wrong eigenvalues)
+        if (reference_restart) DLB_CUDA_CHECK(cudaMemsetAsync(bspace, 0, big, st));
       }
       DLB_CUDA_CHECK(cudaMemsetAsync(aspace, 0, big, st));
       DLB_CUDA_CHECK(cudaMemsetAsync(a_red, 0, (size_t)lda * lda * sizeof(double), st));
@@ -1559,6 +1563,7 @@ int32_t diaglib_b200_init(int32_t device) {
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_WS")) g_disable_ws = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_FUSED_GRAM")) g_use_fused_gram = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_SPEC_ORTHO")) g.spec_ortho = ev[0] != '0';
+  if (const char* ev = std::getenv("DIAGLIB_B200_REFERENCE_RESTART")) g.reference_restart = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_TMA")) g_disable_tma = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_EIG_COOP_MIN_K")) g_eig_coop_min_k = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_EIG_MODE")) g_eig_mode = std::atoi(ev);
@@ -2219,6 +2224,11 @@ int32_t diaglib_b200_k_true_residual(int32_t n_loc, int32_t m, const double* x_d
   return g.status;
 }
 
+int32_t diaglib_b200_k_set_reference_restart(int32_t on) {
+  const int prev = g.reference_restart ? 1 : 0;
+  g.reference_restart = on != 0;
+  return prev;
+}
 int32_t diaglib_b200_k_set_spec_ortho(int32_t on) {
   const int prev = g.spec_ortho ? 1 : 0;
   g.spec_ortho = on != 0;

@@ -223,8 +223,14 @@ __device__ __forceinline__ double fast_rcp(double x) {
 
 __device__ __forceinline__ void rr_pair(int r, int idx, int kp, int& p, int& q) {
   // round-robin tournament: round r (0..kp-2), pair idx (0..kp/2-1)
+  // (0 <= r, idx < kp - 1, so one conditional subtraction replaces each modulo)
   if (idx == 0) { p = kp - 1; q = r; }
-  else { p = (r + idx) % (kp - 1); q = (r - idx + (kp - 1)) % (kp - 1); }
+  else {
+    p = r + idx;
+    if (p >= kp - 1) p -= kp - 1;
+    q = r - idx;
+    if (q < 0) q += kp - 1;
+  }
   if (p > q) { const int t = p; p = q; q = t; }
 }
 
@@ -696,7 +702,7 @@ sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double
       for (int t = 0; t < n_inner; ++t) {
         for (int pr = warp; pr < b; pr += nwarp) {
           int cp, cq;
-          if (cross) { cp = pr; cq = b + (pr + t) % b; }
+          if (cross) { cp = pr; cq = b + ((pr + t) & (b - 1)); }
           else {
             const int hb = b / 2, off = pr < hb ? 0 : b;
             rr_pair(t, pr % hb, b, cp, cq);
@@ -715,12 +721,14 @@ sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double
           // graded factors this orthogonalises a small column against a large one far below eps in
           // the cosine, which is what makes the eigenvectors accurate relative to each eigenvalue
           if (fabs(apq) > tol * sab) {
-            my_max = fmax(my_max, fabs(apq) / sab);
             // Jacobi angle for the pair: with d = (aqq - app)/2, h = hypot(d, apq), u = |d| + h:
             // cos = sqrt(u / 2h), sin = sign(d) apq / sqrt(2 h u)   (cos^2 + sin^2 = 1 identically)
             const double big = fmax(app, aqq);
             const int ex = (__double2hiint(big) >> 20) & 0x7ff;
             const double sc = __hiloint2double((2046 - ex) << 20, 0);   // big * sc in [1, 2)
+            // largest rotated ratio of the sweep: only compared with 1e-10, single precision is plenty
+            // (scaled so that neither term leaves the float range; an underflow reads as "large")
+            my_max = fmax(my_max, (double)__fdividef((float)(fabs(apq) * sc), fmaxf((float)(sab * sc), 1e-37f)));
             const double bq = apq * sc, d = 0.5 * (aqq - app) * sc;
             const double h2 = fma(d, d, bq * bq);
             double cs, sn;

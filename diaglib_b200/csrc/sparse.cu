@@ -8,7 +8,7 @@
 namespace dlb {
 int g_spmm_short = 1;
 int g_spmm_chunk = 24;
-int g_spmm_tail = 1;     // DIAGLIB_B200_SPMM_TAIL=0: the m mod 8 remainder through the generic row loop (round 1)
+int g_spmm_tail = 0;     // DIAGLIB_B200_SPMM_TAIL: m mod 8 remainder: 0 generic row loop, 1 inlined tail block (slow), 2 tail function
 int g_spmm_minb = 4;     // DIAGLIB_B200_SPMM_MINB=3: three instead of four CTAs per SM (85 registers)
 int g_spmm_chunk_tiled = 0;   // DIAGLIB_B200_SPMM_CHUNK_TILED=1: column chunks also with a caller-given row order
 namespace {
@@ -104,6 +104,37 @@ __device__ __forceinline__ int32_t ld_nc_s32(const int32_t* p) {
   return v;
 }
 
+// The m mod JB remainder of the short-row kernel as a separate, NOT inlined function: the same
+// register-resident scheme for JT < JB columns, but compiled on its own so that it cannot disturb
+// the register allocation / load scheduling of the main loop (an inlined tail block made the whole
+// kernel 20-60 % slower: profiles/spmm_variants_r02.json).  Re-reads the row's column indices.
+template <int JT, int KMAX>
+__device__ __noinline__ void spmm_short_tail(int64_t row, int64_t b, int len, bool valid, const int32_t* __restrict__ col,
+                                             const double* __restrict__ val, const double* __restrict__ xb, int64_t ldx,
+                                             double* __restrict__ axb, int64_t ldax, double shift) {
+  double acc[JT];
+#pragma unroll
+  for (int jj = 0; jj < JT; ++jj) acc[jj] = 0.0;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int kk = len > 0 ? (k < len ? k : len - 1) : 0;
+    const int32_t c = len > 0 ? ld_nc_s32(col + b + kk) : (int32_t)row;
+    double v = len > 0 ? ld_nc_f64(val + b + kk) : 0.0;
+    v = k < len ? v : 0.0;
+    const double* xp = xb + c;
+#pragma unroll
+    for (int jj = 0; jj < JT; ++jj) acc[jj] = fma(v, ld_nc_f64(xp + (int64_t)jj * ldx), acc[jj]);
+  }
+  if (valid) {
+#pragma unroll
+    for (int jj = 0; jj < JT; ++jj) {
+      double s = acc[jj];
+      if (shift != 0.0) s = fma(shift, xb[row + (int64_t)jj * ldx], s);
+      axb[row + (int64_t)jj * ldax] = s;
+    }
+  }
+}
+
 // TAIL (0..JB-1) = m mod JB, known at compile time: the last, narrower column block runs through
 // the same register-resident loop as the full blocks (a generic tail loop for 5 of 37 columns
 // used to cost as much as a full block of 8).
@@ -161,6 +192,11 @@ spmm_csr_short_kernel(int64_t n, int64_t n_halo, const int64_t* __restrict__ row
   }
   if (TAIL == 0 && valid && j0 < m)   // (only when the tail instantiations are switched off)
     spmm_row_generic<JB>(row, b, b + len, j0, n, n_halo, col, val, m, x, ldx, xh, ax, ldax, shift);
+  if (TAIL > JB) {   // TAIL = JB + t: the t remaining columns through the not-inlined function
+    spmm_short_tail<(TAIL > JB ? TAIL - JB : 1), KMAX>(row, b, len, valid, col, val, x + (int64_t)j0 * ldx, ldx,
+                                                       ax + (int64_t)j0 * ldax, ldax, shift);
+    return;
+  }
   if (TAIL > 0) {   // m - j0 == TAIL by construction (the launcher picks the instantiation)
     constexpr int JT = TAIL > 0 ? TAIL : 1;
     double acc[JT];
@@ -357,7 +393,11 @@ void spmm_csr(cudaStream_t st, const CsrDevice& A, int m, const double* x, int64
       spmm_csr_short_kernel<8, 7, T, 4><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, mc, xc, ldx, hc, axc, ldax, \
                                                               shift, A.order, first, count);                             \
     break;
-      switch (g_spmm_tail ? mc % 8 : 0) { DLB_SHORT(0) DLB_SHORT(1) DLB_SHORT(2) DLB_SHORT(3) DLB_SHORT(4) DLB_SHORT(5) DLB_SHORT(6) DLB_SHORT(7) }
+      // g_spmm_tail: 0 = remainder through the generic row loop, 1 = inlined tail block, 2 = not-inlined tail function
+      switch (g_spmm_tail == 0 || mc % 8 == 0 ? 0 : (g_spmm_tail == 2 ? 8 + mc % 8 : mc % 8)) {
+        DLB_SHORT(0) DLB_SHORT(1) DLB_SHORT(2) DLB_SHORT(3) DLB_SHORT(4) DLB_SHORT(5) DLB_SHORT(6) DLB_SHORT(7)
+        DLB_SHORT(9) DLB_SHORT(10) DLB_SHORT(11) DLB_SHORT(12) DLB_SHORT(13) DLB_SHORT(14) DLB_SHORT(15)
+      }
 #undef DLB_SHORT
       ++g_launches;
     }

@@ -124,6 +124,12 @@ def set_eig_mode(mode: int, block: int = 0) -> int:
     return int(lib().diaglib_b200_k_set_eig_mode(int(mode), int(block)))
 
 
+def set_reference_restart(on: bool) -> bool:
+    """gen_david_driver: reproduce the reference's `bspace = zero` at a restart (diaglib.f90:2200) literally"""
+    init()
+    return bool(lib().diaglib_b200_k_set_reference_restart(1 if on else 0))
+
+
 def set_spec_ortho(on: bool) -> bool:
     """speculative (device-decided) ortho_cd / ortho_vs_x chains on/off; returns the previous setting"""
     init()

@@ -69,6 +69,10 @@ int32_t diaglib_b200_k_sym_eig(int32_t k, double* a_host, int32_t lda, int32_t u
  * (default), 1 = two-sided only; block = columns per block of the one-sided solver (0 = automatic,
  * else 4 or 8).  Returns the previous mode. */
 int32_t diaglib_b200_k_set_eig_mode(int32_t mode, int32_t block);
+/* gen_david_driver restart: 0 (default) keeps B times the restart vectors in bspace, 1 executes the
+ * reference's literal `bspace = zero` (diaglib.f90:2200; also DIAGLIB_B200_REFERENCE_RESTART=1).
+ * Returns the previous setting. */
+int32_t diaglib_b200_k_set_reference_restart(int32_t on);
 /* ortho_cd / ortho_vs_x control: 1 = speculative chains decided on the device, one host
  * synchronisation per call (default); 0 = one host decision per ortho_cd pass.  Same arithmetic
  * and same decisions either way.  Returns the previous setting. */

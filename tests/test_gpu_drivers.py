@@ -755,3 +755,30 @@ def test_speculative_ortho_chains_change_nothing_but_the_sync_count(gpu_lib, dri
     assert s1["host_syncs"] < s0["host_syncs"]
     if driver == "lobpcg":
         assert s1["host_syncs"] <= 3 * its + 8     # set-up + final copy on top of <= 3 per iteration
+
+
+def test_gen_david_reference_restart_switch(gpu_lib, oracle):
+    """DIAGLIB_B200_REFERENCE_RESTART=1 / k_set_reference_restart(1): the library executes the
+    reference's literal `bspace = zero` after a restart (diaglib.f90:2200) and then reproduces the
+    oracle's literal mode -- including its wrong eigenvalues; the default keeps B * restart vectors"""
+    from diaglib_b200 import kernels as K
+    n, n_targ, n_max = 600, 4, 9
+    csr = P.toy_sparse(n)
+    bcsr = P.metric_like(csr)
+    oracle.set_csr(*csr)
+    oracle.set_csr_b(*bcsr)
+    gpu_lib.set_csr(*csr)
+    gpu_lib.set_csr_b(*bcsr)
+    lit = oracle.gen_david(P.guess(n, n_max), n_targ, 100, 1e-8, 10, reference_restart=True)
+    good = oracle.gen_david(P.guess(n, n_max), n_targ, 100, 1e-8, 10)
+    assert np.abs(lit["eig"][:n_targ] - good["eig"][:n_targ]).max() > 1e-3
+    prev = K.set_reference_restart(True)
+    try:
+        ev, eig = P.guess(n, n_max), np.zeros(n_max)
+        gpu_lib.gen_david_driver(False, n, n_targ, n_max, 100, 1e-8, 10, 0.0, None, None, None, eig, ev)
+        hg = gpu_lib.last_history(n_max)
+    finally:
+        K.set_reference_restart(prev)
+    # same (wrong) answer as the literal oracle, same iteration count within 1
+    assert np.abs(eig[:n_targ] - lit["eig"][:n_targ]).max() / np.abs(lit["eig"][:n_targ]).max() < 1e-6
+    assert abs(len(hg["it"]) - len(lit["it"])) <= 1

@@ -121,7 +121,7 @@ def test_two_rank_parity(oracle, case):
     assert np.abs(x.T @ bx - np.eye(n_targ)).max() < (1e-10 if gen_eig else 1e-11)
 
 
-def _spmm_worker(rank, world, port, m, q):
+def _spmm_worker(rank, world, port, m, tiled, q):
     import ctypes as C
 
     import torch
@@ -140,6 +140,8 @@ def _spmm_worker(rank, world, port, m, q):
         n = 32 * 32 * 16
         DD.install_partitioned(lambda a, b: P.lap3d(32, 32, 16, a, b, delta=1.0), n, rank, world, dist)
         r0, r1 = partition.row_range(n, rank, world)
+        if tiled:   # grid tiles along a z-order curve inside this rank's slab of planes
+            D.set_csr_row_order(P.tile_order_3d(32, 32, 16, tile=(32, 4, 2), z0=r0 // 1024, z1=r1 // 1024))
         x = np.asfortranarray(P.guess(n, m, r0, r1))
         dx, dax = K.DeviceArray.from_numpy(x), K.DeviceArray((r1 - r0, m))
         i32 = lambda v_: C.byref(C.c_int32(v_))  # noqa: E731
@@ -151,15 +153,17 @@ def _spmm_worker(rank, world, port, m, q):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("m", [37, 8])
-def test_two_rank_spmm_bit_exact(oracle, m):
-    """halo exchange + the column-chunked short-row SpMM (m > 24: two launches, halo block offset per
-    chunk) reproduce the single-rank oracle product bit for bit"""
+@pytest.mark.parametrize("m,tiled", [(37, False), (8, False), (37, True), (5, True)])
+def test_two_rank_spmm_bit_exact(oracle, m, tiled):
+    """halo exchange (own stream and communicator, overlapped with the rows that do not touch the
+    halo) + the column-chunked short-row SpMM (m > 24: two launches, halo block offset per chunk),
+    in the natural and in a tiled processing order, reproduce the single-rank oracle product bit
+    for bit"""
     import torch.multiprocessing as mp
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_spmm_worker, args=(r, world, port, m, q)) for r in range(world)]
+    procs = [ctx.Process(target=_spmm_worker, args=(r, world, port, m, tiled, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
