@@ -295,8 +295,8 @@ def run_c4(args, rank, world, local):
     from diaglib_b200 import dist as DD, kernels as K, partition
 
     torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -446,6 +446,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--nx", type=int, default=256, help="grid edge (n = nx^3); 256 is the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--natural-order", action="store_true", help="c3: rows of the built-in matvec in natural order (no tiles)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4"],
                     help="c3 = the headline LOBPCG workload (default); c4 = FCI-like Davidson run (BASELINE.json configs[3])")
     ap.add_argument("--bits", type=int, default=26, help="c4: n = 2^bits rows (26 = the specified 64M; 22 has an oracle fixture)")
@@ -468,8 +469,8 @@ def main():
     from diaglib_b200 import dist as DD, kernels as K, partition
 
     torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")  # these levels print a version banner on stdout; keep it to the single JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -489,6 +490,12 @@ def main():
     r0, r1 = DD.install_partitioned(rows, n, rank, world, dist if world > 1 else None)
     csr_nnz = csr_nnz[0]
     n_loc = r1 - r0
+    # processing order of the rows in the built-in matvec: 64x2x2 grid tiles along a z-order curve
+    # inside this rank's slab of planes (a locality hint; the product is bit-identical for any order)
+    row_order = None
+    if not args.natural_order and r0 % (nx * nx) == 0 and r1 % (nx * nx) == 0:
+        row_order = "tile 64x2x2, z-order curve"
+        D.set_csr_row_order(P.tile_order_3d(nx, nx, nx, tile=(64, 2, 2), z0=r0 // (nx * nx), z1=r1 // (nx * nx)))
     guess = make_guess(global_diag(nx, nx, nx), n, n_max, r0, r1)
     blk_bytes = guess.nbytes
 
@@ -645,26 +652,29 @@ def main():
         import ctypes as C
         i32 = lambda v_: C.byref(C.c_int32(int(v_)))  # noqa: E731
         nnz_loc = int(csr_nnz)
-        for _ in range(2):
-            lib.diaglib_b200_csr_matvec(i32(n_loc), i32(q), C.c_void_p(v.ptr), C.c_void_p(y.ptr))
-        lib.diaglib_b200_sync()
-        K.timer_start()
-        for _ in range(reps):
-            lib.diaglib_b200_csr_matvec(i32(n_loc), i32(q), C.c_void_p(v.ptr), C.c_void_p(y.ptr))
-        sp_ms = K.timer_stop_ms() / reps
+
+        def time_spmm(mm):
+            for _ in range(2):
+                lib.diaglib_b200_csr_matvec(i32(n_loc), i32(mm), C.c_void_p(v.ptr), C.c_void_p(y.ptr))
+            lib.diaglib_b200_sync()
+            K.timer_start()
+            for _ in range(reps):
+                lib.diaglib_b200_csr_matvec(i32(n_loc), i32(mm), C.c_void_p(v.ptr), C.c_void_p(y.ptr))
+            return K.timer_stop_ms() / reps
+
+        sp_ms = time_spmm(q)
         sbytes = 12.0 * nnz_loc + 8.0 * (n_loc + 1) + 16.0 * n_loc * q
-        spmm_traffic = None
-        try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_spmm_short_r01.json")))
-            spmm_traffic = cap["chunked_m37"]["traffic_bytes"] * (n_loc / 16777216.0) if q == 37 else None
-        except Exception:
-            pass
+        sp32_ms = time_spmm(32)
+        sbytes32 = 12.0 * nnz_loc + 8.0 * (n_loc + 1) + 16.0 * n_loc * 32
         roof["spmm"] = {"kernel": f"spmm_csr_short_kernel m={q}, n={n_loc}, nnz={nnz_loc}", "bound": "hbm", "ms_per_launch": sp_ms,
                         "achieved_gbs": sbytes / (sp_ms * 1e-3) / 1e9, "frac_hbm": sbytes / (sp_ms * 1e-3) / 1e9 / hbm_peak,
-                        "algorithmic_bytes": sbytes,
-                        "traffic": spmm_traffic,
-                        "note": "two launches (24 + 13 columns) keep x in L2; DRAM 13.3 GB for 11.5 GB algorithmic, L2->SM fill "
-                                "29.6 GB at ~10.6 TB/s: profiles/ncu_spmm_short_r01.json"}
+                        "algorithmic_bytes": sbytes, "row_order": row_order or "natural",
+                        "m32": {"ms_per_launch": sp32_ms, "achieved_gbs": sbytes32 / (sp32_ms * 1e-3) / 1e9,
+                                "frac_hbm": sbytes32 / (sp32_ms * 1e-3) / 1e9 / hbm_peak},
+                        "traffic": None,
+                        "note": "includes the halo exchange for N > 1 (own stream, overlapped with the rows that need no halo); "
+                                "m = 37 = 4 register blocks of 8 columns + 5 columns through the generic row loop, m = 32 "
+                                "has no remainder; ncu traffic: profiles/ (round 1: 13.3 GB for 11.5 GB algorithmic in natural order)"}
         for a in (v, y, cd, w, cg):
             a.free()
 
@@ -697,6 +707,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": bench_config(nx, n_loc, world), "rows_per_gpu": n_loc, "parallelism": f"row-partition x{world}",
+            "stats": D.last_stats(),
             "parity": parity,
             "time_to_converge_s": ms_per_step * 1e-3, "iterations": tot_its / args.steps, "converged": True,
             "final_rms_residual_max": res_max, "eig_lowest": [float(x) for x in eig[:4]],

@@ -144,17 +144,21 @@ def tile_order_3d(nx: int, ny: int, nz: int, tile=(32, 4, 2), z0: int = 0, z1: i
     z1 = nz if z1 is None else z1
     tx, ty, tz = tile
     lz = z1 - z0
-    x, y, z = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(lz), indexing="ij")
-    x, y, z = x.ravel(), y.ravel(), z.ravel()
-    bx, by, bz = x // tx, y // ty, z // tz
-    if curve == "morton":
-        tkey = _morton3(bx, by, bz)
-    else:
-        tkey = (bz * ((ny + ty - 1) // ty) + by) * ((nx + tx - 1) // tx) + bx
-    inner = ((z % tz) * ty + (y % ty)) * tx + (x % tx)
-    order = np.lexsort((inner, tkey))
-    rows = x + nx * (y + ny * z)
-    return rows[order].astype(np.int32)
+    ntx, nty, ntz = -(-nx // tx), -(-ny // ty), -(-lz // tz)
+    bx, by, bz = np.meshgrid(np.arange(ntx), np.arange(nty), np.arange(ntz), indexing="ij")
+    bx, by, bz = bx.ravel(), by.ravel(), bz.ravel()
+    tkey = _morton3(bx, by, bz) if curve == "morton" else (bz * nty + by) * ntx + bx
+    t = np.argsort(tkey, kind="stable")
+    bx, by, bz = bx[t], by[t], bz[t]
+    # rows of every tile, x fastest, then y, then z: shape (tiles, tz, ty, tx)
+    x = (bx * tx)[:, None, None, None] + np.arange(tx)[None, None, None, :]
+    y = (by * ty)[:, None, None, None] + np.arange(ty)[None, None, :, None]
+    z = (bz * tz)[:, None, None, None] + np.arange(tz)[None, :, None, None]
+    rows = (x + nx * (y + ny * z)).reshape(-1)
+    if nx % tx or ny % ty or lz % tz:
+        ok = ((x < nx) & (y < ny) & (z < lz)).reshape(-1)
+        rows = rows[ok]
+    return rows.astype(np.int32)
 
 
 def fci_strides(n_strides: int = 50, bandwidth: int = 1 << 20, seed: int = 1):
