@@ -17,6 +17,13 @@
       (16.7 M rows, about 8 minutes of host time on the GPU box) and backs bench.py's parity block
       when no fresh run is present.  The thread count of the generating run is recorded inside.
 
+  c3_oracle_acc_nx{64,128,256}.json : the same solves by the oracle in its DIAGNOSTIC mode (reduced
+      eigenproblems through dpotrf + dgesvj instead of dsyev): `python tools/oracle_spread.py NX T 0 OUT 1`.
+      They quantify how much of an iteration-count difference is dsyev's accuracy (bench.parity_block).
+  c4_oracle_n22.json : the oracle's Davidson-Liu solve of C4's matrix at n = 2^22 (tools/c4_oracle.py).
+  c5_oracle_n18.json : the oracle's Davidson-Liu and LOBPCG solves of C5's problem at n = 2^18
+      (128 roots of 133, lda = 1330; tools/c5_oracle.py).
+
 Run from the repo root:  python tests/golden/make_golden.py   (the first two files)
                          python bench.py --impl reference --nx 32 && cp gpurun_out/oracle_c3_nx32.json tests/golden/c3_oracle_nx32.json
 """

@@ -782,3 +782,32 @@ def test_gen_david_reference_restart_switch(gpu_lib, oracle):
     # same (wrong) answer as the literal oracle, same iteration count within 1
     assert np.abs(eig[:n_targ] - lit["eig"][:n_targ]).max() / np.abs(lit["eig"][:n_targ]).max() < 1e-6
     assert abs(len(hg["it"]) - len(lit["it"])) <= 1
+
+
+@pytest.mark.parametrize("driver", ["davidson", "lobpcg"])
+def test_c5_many_roots_n18_vs_oracle_fixture(gpu_lib, driver):
+    """C5 at n = 2^18: toy_sparse, 128 roots of 133, Davidson-Liu with max_dav = 10
+    (lda = 1330: ortho_cd at m = 133, reduced eigenproblems up to 1330 x 1330) and LOBPCG (len_a = 399),
+    against the oracle's complete solves (tests/golden/c5_oracle_n18.json, tools/c5_oracle.py; minutes of
+    CPU, hence a fixture).  diaglib.f90:1676-1828, 389-533."""
+    gold = json.load(open(os.path.join(GOLD, "c5_oracle_n18.json")))
+    n, n_targ, n_max, tol = gold["n"], gold["n_targ"], gold["n_max"], gold["tol"]
+    csr = P.toy_sparse(n)
+    gpu_lib.set_csr(*csr)
+    g = np.asfortranarray(P.guess_lowest_diag(csr[3], n_max) + P.guess(n, n_max) * (gold["noise"] / np.sqrt(n / 12.0)))
+    eig = np.zeros(n_max)
+    if driver == "davidson":
+        ok = gpu_lib.davidson_driver(False, n, n_targ, n_max, 100, tol, gold["max_dav"], 0.0, None, None, eig, g)
+    else:
+        ok = gpu_lib.lobpcg_driver(False, False, n, n_targ, n_max, 100, tol, 0.0, None, None, None, eig, g)
+    hg = gpu_lib.last_history(n_max)
+    ref = gold[driver]
+    eo = np.array(ref["eig"][:n_targ])
+    rel = np.abs(eig[:n_targ] - eo).max() / np.abs(eo).max()
+    print(f"C5 n=2^18 {driver}: iterations gpu {len(hg['it'])} oracle {ref['iterations']}, max rel eig err {rel:.2e}, "
+          f"timers {gpu_lib.last_timers()}")
+    assert ok and ref["ok"]
+    assert rel < REL
+    assert abs(len(hg["it"]) - ref["iterations"]) <= 1
+    check_solution(csr, eig, g, n_targ, tol)
+    gpu_lib.lib().diaglib_b200_release_workspace()
