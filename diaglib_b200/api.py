@@ -81,6 +81,9 @@ def lib():
         L.diaglib_b200_k_set_eig_mode.argtypes = [C.c_int32, C.c_int32]
         L.diaglib_b200_k_sym_eig_time_ms.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.diaglib_b200_k_sym_eig_time_ms.restype = C.c_double
+        L.diaglib_b200_k_set_tuning.argtypes = [C.c_char_p, C.c_int32]
+        L.diaglib_b200_k_time_small.argtypes = [C.c_int32] * 5
+        L.diaglib_b200_k_time_small.restype = C.c_double
         L.diaglib_b200_k_chol_inv.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.diaglib_b200_k_get_coeffs.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 3
         L.diaglib_b200_comm_init.argtypes = [C.c_int32, C.c_int32, C.c_void_p]
@@ -319,4 +322,5 @@ def last_stats():
     s = np.zeros(8, np.int64)
     lib().diaglib_b200_stats(_ptr(s))
     return dict(ortho_cd_passes=int(s[0]), ortho_vs_x_sweeps=int(s[1]), qr_fallbacks=int(s[2]), chol_shifts=int(s[3]),
-                launches=int(s[4]), launches_total=int(s[5]), host_syncs=int(s[6]))
+                launches=int(s[4]), launches_total=int(s[5]), host_syncs=int(s[6]),
+                eig_calls=int(s[7] & 0xffff), eig_sweeps=int((s[7] >> 16) & 0xffffff), eig_two_sided_fallbacks=int(s[7] >> 40))

@@ -112,6 +112,7 @@ struct Engine {
   cudaStream_t st_halo = nullptr;
   cudaEvent_t ev_x = nullptr, ev_halo = nullptr;
   int64_t st_syncs = 0;   // host <- device synchronisations of the last driver call
+  int64_t st_eig_calls = 0, st_eig_sweeps = 0, st_eig_fallbacks = 0;   // reduced eigensolves of the last driver call
 
   DevBuf partial, smallws, resid_scratch, scal;
   // driver workspaces, cached across calls (the reference allocates per call, 251-276 / 1600-1618;
@@ -549,6 +550,7 @@ struct Engine {
     hist.clear(n_max);
     st_cd_passes = st_sweeps = st_qr = st_shifts = 0;
     st_syncs = 0;
+    st_eig_calls = st_eig_sweeps = st_eig_fallbacks = 0;
     st_launch0 = g_launches;
     for (double& t : t_acc) t = 0;
   }
@@ -815,6 +817,7 @@ void Engine::lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, in
       EigStatus es;
       DLB_CUDA_CHECK(cudaMemcpyAsync(&es, d_eigst, sizeof es, cudaMemcpyDeviceToHost, st));
       read_back(h_eig.data(), e_red, n_max * sizeof(double));                          // 416
+      ++st_eig_calls; st_eig_sweeps += es.sweeps; st_eig_fallbacks += es.path == 2 ? 1 : 0;
       if (!es.converged) {                                                             // 412-415
         fail(DIAGLIB_B200_EDSYEV, "dsyev failed. info = %6d", es.sweeps);
         break;
@@ -1046,6 +1049,7 @@ void Engine::davidson(bool verbose, bool gen, int n, int n_targ, int n_max, int 
       EigStatus es;
       DLB_CUDA_CHECK(cudaMemcpyAsync(&es, d_eigst, sizeof es, cudaMemcpyDeviceToHost, st));
       read_back(h_eig.data(), e_red, n_max * sizeof(double));                           // 1715
+      ++st_eig_calls; st_eig_sweeps += es.sweeps; st_eig_fallbacks += es.path == 2 ? 1 : 0;
       if (!es.converged) {
         fail(DIAGLIB_B200_EDSYEV, "dsyev failed. info = %6d", es.sweeps);
         break;
@@ -1995,7 +1999,8 @@ void diaglib_b200_timers(double* out12) { for (int i = 0; i < 12; ++i) out12[i] 
 void diaglib_b200_set_profile(int32_t on) { g.profile = on != 0; }
 void diaglib_b200_stats(int64_t* out8) {
   out8[0] = g.st_cd_passes; out8[1] = g.st_sweeps; out8[2] = g.st_qr; out8[3] = g.st_shifts; out8[4] = g.st_launches;
-  out8[5] = g_launches; out8[6] = g.st_syncs; out8[7] = 0;
+  out8[5] = g_launches; out8[6] = g.st_syncs;
+  out8[7] = g.st_eig_calls + (g.st_eig_sweeps << 16) + (g.st_eig_fallbacks << 40);   // packed: calls | sweeps << 16 | two-sided fallbacks << 40
 }
 
 // ---- kernel-level entry points (include/diaglib_b200_kernels.h) ---------------------------
@@ -2224,6 +2229,63 @@ int32_t diaglib_b200_k_true_residual(int32_t n_loc, int32_t m, const double* x_d
   return g.status;
 }
 
+int32_t diaglib_b200_k_set_tuning(const char* name, int32_t value) {
+  const std::string nm(name ? name : "");
+  int* slot = nullptr;
+  if (nm == "coeffs_threads") slot = &g_coeffs_threads;
+  else if (nm == "spmm_tail") slot = &g_spmm_tail;
+  else if (nm == "spmm_minb") slot = &g_spmm_minb;
+  else if (nm == "spmm_chunk") slot = &g_spmm_chunk;
+  else if (nm == "eig_block") slot = &g_eig_block;
+  else if (nm == "eig_mode") slot = &g_eig_mode;
+  if (!slot) return -1;
+  const int prev = *slot;
+  *slot = value;
+  return prev;
+}
+double diaglib_b200_k_time_small(int32_t which, int32_t a, int32_t b, int32_t c, int32_t reps) {
+  // which = 0: chol_inv on an a x a metric; 1: get_coeffs(len_u = a, n_max = b, n_act = c).  Random but
+  // well-posed inputs generated here; returns milliseconds per call (CUDA events, back-to-back launches).
+  if (!require_init()) return -1.0;
+  std::vector<double> h;
+  DevBuf buf;
+  if (which == 0) {
+    const int m = a;
+    g.ensure_small(m, m);
+    h.assign((size_t)m * m, 0.0);
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j) h[i + (size_t)j * m] = (i == j ? 2.0 : 0.0) + 0.3 / (1.0 + std::abs(i - j));
+    DLB_CUDA_CHECK(cudaMemcpyAsync(g.d_metric, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, g.st));
+    chol_inv(g.st, m, g.d_metric, m, g.d_T, g.d_cholwork, g.d_cholst);
+    DLB_CUDA_CHECK(cudaEventRecord(g.sw0, g.st));
+    for (int r = 0; r < reps; ++r) chol_inv(g.st, m, g.d_metric, m, g.d_T, g.d_cholwork, g.d_cholst);
+  } else {
+    const int len_u = a, n_max = b, n_act = c;
+    const size_t cw = coeffs_work_doubles(len_u, n_max, n_act), ew = eig_work_doubles(len_u);
+    if (!buf.ensure(((size_t)len_u * len_u + len_u + (size_t)len_u * n_act + cw + ew + 32) * sizeof(double))) return -1.0;
+    double* ar = buf.as<double>();
+    double* w = ar + (size_t)len_u * len_u;
+    double* up = w + len_u;
+    double* work = up + (size_t)len_u * n_act;
+    double* ework = work + cw;
+    EigStatus* es = reinterpret_cast<EigStatus*>(ework + ew);
+    CoeffStatus* cs = reinterpret_cast<CoeffStatus*>(ework + ew + 8);
+    h.assign((size_t)len_u * len_u, 0.0);
+    for (int i = 0; i < len_u; ++i)
+      for (int j = 0; j < len_u; ++j) h[i + (size_t)j * len_u] = (i == j ? 1.0 + i : 0.0) + 0.02 / (1.0 + std::abs(i - j));
+    DLB_CUDA_CHECK(cudaMemcpyAsync(ar, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, g.st));
+    sym_eig(g.st, len_u, ar, len_u, false, w, ework, es);      // eigenvectors in place, as in the drivers
+    get_coeffs(g.st, len_u, len_u, n_max, n_act, ar, up, work, cs);
+    DLB_CUDA_CHECK(cudaEventRecord(g.sw0, g.st));
+    for (int r = 0; r < reps; ++r) get_coeffs(g.st, len_u, len_u, n_max, n_act, ar, up, work, cs);
+  }
+  DLB_CUDA_CHECK(cudaEventRecord(g.sw1, g.st));
+  DLB_CUDA_CHECK(cudaEventSynchronize(g.sw1));
+  float ms = 0.f;
+  DLB_CUDA_CHECK(cudaEventElapsedTime(&ms, g.sw0, g.sw1));
+  buf.release();
+  return (double)ms / reps;
+}
 int32_t diaglib_b200_k_set_reference_restart(int32_t on) {
   const int prev = g.reference_restart ? 1 : 0;
   g.reference_restart = on != 0;

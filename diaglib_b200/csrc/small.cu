@@ -1089,9 +1089,11 @@ size_t coeffs_work_doubles(int len_u, int n_max, int n_act) {
   return 4 * (size_t)n_act * n_act + (size_t)n_max * n_act + (size_t)len_u * n_act + 8;
 }
 
+int g_coeffs_threads = 0;   // 0: 1024 threads; experiment switch (diaglib_b200_k_set_tuning "coeffs_threads")
 void get_coeffs(cudaStream_t st, int len_a, int len_u, int n_max, int n_act, const double* a_red, double* u_p,
                 double* work, CoeffStatus* status_dev) {
-  get_coeffs_kernel<<<1, SM_THREADS, 0, st>>>(len_a, len_u, n_max, n_act, a_red, u_p, work, status_dev);
+  const int threads = g_coeffs_threads > 0 ? g_coeffs_threads : SM_THREADS;
+  get_coeffs_kernel<<<1, threads, 0, st>>>(len_a, len_u, n_max, n_act, a_red, u_p, work, status_dev);
   ++g_launches;
   DLB_CUDA_CHECK(cudaGetLastError());
 }

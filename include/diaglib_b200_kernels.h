@@ -69,6 +69,12 @@ int32_t diaglib_b200_k_sym_eig(int32_t k, double* a_host, int32_t lda, int32_t u
  * (default), 1 = two-sided only; block = columns per block of the one-sided solver (0 = automatic,
  * else 4 or 8).  Returns the previous mode. */
 int32_t diaglib_b200_k_set_eig_mode(int32_t mode, int32_t block);
+/* experiment switches by name (coeffs_threads, spmm_tail, spmm_minb, spmm_chunk, eig_block, eig_mode);
+ * returns the previous value, -1 for an unknown name */
+int32_t diaglib_b200_k_set_tuning(const char* name, int32_t value);
+/* device time of the small replicated kernels, milliseconds per call over `reps` back-to-back
+ * launches: which = 0 chol_inv on an a x a metric; which = 1 get_coeffs(len_u = a, n_max = b, n_act = c) */
+double diaglib_b200_k_time_small(int32_t which, int32_t a, int32_t b, int32_t c, int32_t reps);
 /* gen_david_driver restart: 0 (default) keeps B times the restart vectors in bspace, 1 executes the
  * reference's literal `bspace = zero` (diaglib.f90:2200; also DIAGLIB_B200_REFERENCE_RESTART=1).
  * Returns the previous setting. */

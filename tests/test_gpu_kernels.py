@@ -298,6 +298,23 @@ def test_sym_eig_not_positive_definite_falls_back(K):
     assert K.sym_eig.last_path == 2 and np.abs(w).max() == 0.0
 
 
+def test_small_kernel_timing_table(K, gpu_lib):
+    """not a pass/fail test of speed: device time of the replicated single-CTA kernels (pytest -s)"""
+    L = gpu_lib.lib()
+    for m in (13, 21, 37, 74, 133):
+        print(f"chol_inv m={m}: {1e3 * L.diaglib_b200_k_time_small(0, m, 0, 0, 50):.1f} us")
+    for len_u, n_max, n_act in ((111, 37, 37), (111, 37, 20), (74, 37, 37), (63, 21, 21), (399, 133, 133)):
+        row = []
+        for threads in (1024, 512, 256):
+            prev = L.diaglib_b200_k_set_tuning(b"coeffs_threads", threads)
+            try:
+                row.append(1e3 * L.diaglib_b200_k_time_small(1, len_u, n_max, n_act, 20))
+            finally:
+                L.diaglib_b200_k_set_tuning(b"coeffs_threads", prev)
+        print(f"get_coeffs len_u={len_u} n_max={n_max} n_act={n_act}: {row[0]:.1f} us (1024 threads), {row[1]:.1f} (512), {row[2]:.1f} (256)")
+        assert row[0] > 0
+
+
 def test_sym_eig_timing_table(K):
     """not a pass/fail test of speed: prints the per-solve time of both solvers (pytest -s)"""
     a = graded_lobpcg_like()
