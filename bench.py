@@ -648,6 +648,51 @@ def main():
         roof["gram"] = {"kernel": f"gram_tma_kernel sym {p}x{p}, n={n_loc}", "ms_per_launch": gr_ms,
                         "achieved_tflops": gflops / (gr_ms * 1e-3) / 1e12, "achieved_gbs": gbytes / (gr_ms * 1e-3) / 1e9,
                         "frac_tensor": gflops / (gr_ms * 1e-3) / 1e12 / f64_peak, "frac_hbm": gbytes / (gr_ms * 1e-3) / 1e9 / hbm_peak}
+        # the narrow kernels of ortho_cd / ortho_vs_x (50 % of a solve): useful flops, flops the tensor pipe
+        # actually executes on its 8 x 8 x 4 tiles (padding included), and both rooflines
+        def executed_gram(pp, qq, sym):
+            ntp, ntq = -(-pp // 8), -(-qq // 8)
+            return 128.0 * (ntp * (ntp + 1) // 2 if sym else ntp * ntq)       # flops per row
+
+        def executed_bmul(pp, qq, tri):
+            kp, ntq = -(-pp // 16) * 16, -(-qq // 8)
+            if not tri:
+                return 2.0 * kp * ntq * 8
+            return 64.0 * sum(max(0, ntq - (4 * t) // 8) for t in range(kp // 4))
+
+        def one(name, fn, useful, executed, nbytes):
+            for _ in range(2):
+                fn()
+            lib.diaglib_b200_sync()
+            K.timer_start()
+            for _ in range(reps):
+                fn()
+            ms_ = K.timer_stop_ms() / reps
+            return {"kernel": name, "ms_per_launch": ms_, "useful_tflops": useful * n_loc / ms_ / 1e9,
+                    "executed_tflops": executed * n_loc / ms_ / 1e9, "gbs": nbytes / ms_ / 1e6,
+                    "frac_tensor_executed": executed * n_loc / ms_ / 1e9 / f64_peak, "frac_hbm": nbytes / ms_ / 1e6 / hbm_peak}
+
+        tm = np.asfortranarray(np.triu(np.random.default_rng(1).standard_normal((q, q)) * 0.1 + np.eye(q)))
+        td = K.DeviceArray.from_numpy(tm)
+        xu = K.DeviceArray.from_numpy(np.asfortranarray(np.random.default_rng(2).standard_normal((2 * q, q)) * 1e-3))
+        g37 = K.DeviceArray((q, q))
+        g74 = K.DeviceArray((2 * q, q))
+        roof["narrow"] = [
+            one(f"gram sym {q}x{q} (ortho_cd metric, 3256)",
+                lambda: lib.diaglib_b200_k_gram(n_loc, y.ptr, n_loc, q, y.ptr, n_loc, q, g37.ptr, q, 1),
+                q * (q + 1.0), executed_gram(q, q, True), 8.0 * n_loc * q),
+            one(f"trmm {q} in place, upper triangular (3327)",
+                lambda: lib.diaglib_b200_k_trmm(n_loc, y.ptr, n_loc, q, td.ptr),
+                q * (q + 1.0), executed_bmul(q, q, True), 16.0 * n_loc * q),
+            one(f"gram {2 * q}x{q} (x^T u, 3543)",
+                lambda: lib.diaglib_b200_k_gram(n_loc, v.ptr, n_loc, 2 * q, y.ptr, n_loc, q, g74.ptr, 2 * q, 0),
+                2.0 * 2 * q * q, executed_gram(2 * q, q, False), 8.0 * n_loc * 3 * q),
+            one(f"block_mul {2 * q}->{q}, u -= x xu (3544)",
+                lambda: lib.diaglib_b200_k_block_mul(n_loc, v.ptr, n_loc, 2 * q, xu.ptr, 2 * q, q, -1.0, 1.0, y.ptr, n_loc),
+                2.0 * 2 * q * q, executed_bmul(2 * q, q, False), 8.0 * n_loc * 4 * q),
+        ]
+        for a_ in (td, xu, g37, g74):
+            a_.free()
         # third family: the built-in CSR block matvec at m = n_max (includes the halo exchange for N > 1)
         import ctypes as C
         i32 = lambda v_: C.byref(C.c_int32(int(v_)))  # noqa: E731
@@ -671,7 +716,9 @@ def main():
                         "algorithmic_bytes": sbytes, "row_order": row_order or "natural",
                         "m32": {"ms_per_launch": sp32_ms, "achieved_gbs": sbytes32 / (sp32_ms * 1e-3) / 1e9,
                                 "frac_hbm": sbytes32 / (sp32_ms * 1e-3) / 1e9 / hbm_peak},
-                        "traffic": None,
+                        "traffic": (12.419e9 * n_loc / 16777216.0) if (q == 37 and row_order) else None,
+                        "traffic_source": "profiles/ncu_spmm_r02.json (ncu --set full, n = 2^24, tiled order, m = 37: 7.48 GB read + "
+                                          "4.94 GB written), scaled by rows",
                         "note": "includes the halo exchange for N > 1 (own stream, overlapped with the rows that need no halo); "
                                 "m = 37 = 4 register blocks of 8 columns + 5 columns through the generic row loop, m = 32 "
                                 "has no remainder; ncu traffic: profiles/ (round 1: 13.3 GB for 11.5 GB algorithmic in natural order)"}

@@ -2068,6 +2068,11 @@ int32_t diaglib_b200_k_block_mul(int64_t n, const double* v, int64_t ldv, int32_
   block_mul(g.st, n, v, ldv, p, c, ldc, q, alpha, beta, y, ldy);
   return 0;
 }
+int32_t diaglib_b200_k_trmm(int64_t n, double* u, int64_t ldu, int32_t m, const double* t_dev) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  block_trmm_inplace(g.st, n, u, ldu, m, t_dev);
+  return 0;
+}
 int32_t diaglib_b200_k_block_mul_gram(int64_t n, const double* v, int64_t ldv, int32_t p, const double* c, int32_t ldc,
                                       int32_t q, double alpha, double beta, double* y, int64_t ldy, int32_t upper_tri,
                                       double* g_out, int32_t ldg) {
@@ -2233,6 +2238,7 @@ int32_t diaglib_b200_k_set_tuning(const char* name, int32_t value) {
   const std::string nm(name ? name : "");
   int* slot = nullptr;
   if (nm == "coeffs_threads") slot = &g_coeffs_threads;
+  else if (nm == "coeffs_smem") slot = &g_coeffs_smem;
   else if (nm == "spmm_tail") slot = &g_spmm_tail;
   else if (nm == "spmm_minb") slot = &g_spmm_minb;
   else if (nm == "spmm_chunk") slot = &g_spmm_chunk;

@@ -18,6 +18,7 @@ extern bool g_eig_two_sided;
 extern int g_eig_coop_min_k;
 extern int g_eig_mode;
 extern int g_coeffs_threads;
+extern int g_coeffs_smem;
 extern int g_eig_block;
 // Predicate of the dense kernels (gram_tn, block_mul, block_trmm_inplace, block_mul_gram): while it
 // points to a device int, every kernel these wrappers launch returns at once when that int is 0.

@@ -21,6 +21,7 @@ namespace {
 constexpr int SM_THREADS = 1024;
 constexpr double EPS = DBL_EPSILON;       // epsilon(one)
 constexpr double TOL_ORTHO = 2.0 * EPS;   // diaglib.f90:151
+constexpr size_t CHOL_SMEM_MAX = 200 * 1024;   // factors of chol_inv stay in shared memory up to m = 112
 
 __device__ double cta_sum(double v, double* s_red) {
   v = warp_sum(v);
@@ -100,6 +101,114 @@ __device__ void cta_trtri_lower(int m, const double* L, int ldl, double* Li, int
 //   T (m x m, ld m): output L^-T, upper triangular with explicit zeros
 // unorm_sq = ||U||_F^2; the reference calls dnrm2(n*m,u,1) (3268), which equals
 // sqrt(trace(G)) up to rounding, and the trace is already here.
+// Lower Cholesky factor AND its inverse in one elimination: the row operations that reduce
+// [L | I] to [I | L^-1] are applied while the columns of L are produced, so there is no separate
+// (serial) triangular inversion and no per-element index division.  L, X: m x m in SHARED memory
+// (ld m), on entry L = the matrix (lower triangle used), on exit L = factor, X = L^-1 (lower, zeros
+// above).  buf: 2 m doubles of shared memory.  Returns dpotrf-style info (uniform).  Two CTA
+// barriers per column; threads are arranged as (row = tid mod RS, column group = tid / RS) with RS
+// the power of two >= m, so that the trailing updates need only shifts.
+__device__ int cta_potrf_inv_smem(int m, double* L, double* X, double* buf) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  int rs_log = 5;
+  while ((1 << rs_log) < m) ++rs_log;
+  const int RS = 1 << rs_log, CG = nt >> rs_log;   // nt >= RS is guaranteed by the callers
+  const int row = tid & (RS - 1), kq = tid >> rs_log;
+  double* colbuf = buf;       // column j of the factor
+  double* rowbuf = buf + m;   // row j of the inverse
+  for (int e = tid; e < m * m; e += nt) X[e] = 0.0;
+  __syncthreads();
+  for (int i = tid; i < m; i += nt) X[i + (size_t)i * m] = 1.0;
+  __syncthreads();
+  for (int j = 0; j < m; ++j) {
+    const double piv = L[j + (size_t)j * m];
+    if (!(piv > 0.0)) return j + 1;   // uniform; also catches NaN like dpotrf's disnan test
+    const double sq = sqrt(piv);
+    for (int i = j + tid; i < m; i += nt) {
+      const double v = (i == j) ? sq : L[i + (size_t)j * m] / sq;
+      colbuf[i] = v;
+      L[i + (size_t)j * m] = v;
+    }
+    for (int c = tid; c <= j; c += nt) {
+      const double v = X[j + (size_t)c * m] / sq;
+      rowbuf[c] = v;
+      X[j + (size_t)c * m] = v;
+    }
+    __syncthreads();
+    if (row > j && row < m && kq < CG) {
+      const double li = colbuf[row];
+      for (int k = j + 1 + kq; k <= row; k += CG) L[row + (size_t)k * m] = fma(-li, colbuf[k], L[row + (size_t)k * m]);
+      for (int c = kq; c <= j; c += CG) X[row + (size_t)c * m] = fma(-li, rowbuf[c], X[row + (size_t)c * m]);
+    }
+    __syncthreads();
+  }
+  return 0;
+}
+
+// norm_est of a lower triangular matrix in shared memory without index divisions
+__device__ double cta_norm_est_lower(int m, const double* a, double* s_red) {
+  double dmax = 0.0, od = 0.0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < m; j += nw) {
+    for (int i = j + lane; i < m; i += 32) {
+      const double v = a[i + (size_t)j * m];
+      if (i == j) dmax = fmax(dmax, fabs(v));
+      else od = fma(v, v, od);
+    }
+  }
+  const double d = cta_max(dmax, s_red);
+  const double o = cta_sum(od, s_red);
+  return d + sqrt(o);
+}
+
+// cta_chol_inv with the factors in shared memory (m x m each) and `buf` = 2 m doubles of shared memory
+__device__ void cta_chol_inv_smem(int m, const double* G, int ldg, double* L, double* Li, double* buf, double* T,
+                                  CholStatus* st, double* s_red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  double tr = 0.0;
+  for (int j = warp; j < m; j += nw)
+    for (int i = lane; i < m; i += 32) {
+      const double v = G[i + (size_t)j * ldg];
+      L[i + (size_t)j * m] = v;
+      if (i == j) tr += v;
+    }
+  const double unorm = sqrt(fmax(cta_sum(tr, s_red), 0.0));
+  int info = cta_potrf_inv_smem(m, L, Li, buf);
+  const int info_first = info;
+  int n_shifts = 0, hard_fail = 0;
+  double shift = 0.0, alpha = 100.0;
+  while (info != 0) {
+    if (n_shifts >= 10) { hard_fail = 1; break; }  // 3276-3284
+    ++n_shifts;
+    shift = fmax(EPS * alpha * unorm, TOL_ORTHO);   // 3287
+    __syncthreads();
+    for (int j = warp; j < m; j += nw)
+      for (int i = lane; i < m; i += 32) L[i + (size_t)j * m] = G[i + (size_t)j * ldg] + (i == j ? shift : 0.0);
+    __syncthreads();
+    info = cta_potrf_inv_smem(m, L, Li, buf);
+    alpha *= 10.0;
+  }
+  double l_norm = 0.0, linv_norm = 0.0;
+  if (!hard_fail) {
+    l_norm = cta_norm_est_lower(m, L, s_red);
+    linv_norm = cta_norm_est_lower(m, Li, s_red);
+    for (int j = warp; j < m; j += nw)
+      for (int i = lane; i < m; i += 32) T[i + (size_t)j * m] = (i <= j) ? Li[j + (size_t)i * m] : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->l_norm = l_norm;
+    st->linv_norm = linv_norm;
+    st->shift_used = shift;
+    st->unorm = unorm;
+    st->info_first = info_first;
+    st->n_shifts = n_shifts;
+    st->hard_fail = hard_fail;
+    st->pad = 0;
+  }
+  __syncthreads();
+}
+
 __device__ void cta_chol_inv(int m, const double* G, int ldg, double* L, double* Li, double* T, CholStatus* st,
                              double* s_red) {
   double tr = 0.0;
@@ -159,13 +268,12 @@ chol_inv_kernel(int m, const double* G, int ldg, double* T, double* work, CholSt
   extern __shared__ __align__(16) double dyn[];
   OrthoCtl* ctl = link.ctl;
   if (ctl && ctl->live[link.self] == 0) return;   // this pass was not decided (uniform)
-  double* L = work;
-  double* Li = work + (size_t)m * m;
-  if (2 * m * m * (int)sizeof(double) <= 96 * 1024) {  // keep the factors on chip when small
-    L = dyn;
-    Li = dyn + (size_t)m * m;
+  if ((2 * (size_t)m * m + 2 * m) * sizeof(double) <= CHOL_SMEM_MAX && (int)blockDim.x >= m) {
+    // factors on chip: factor and inverse in one elimination
+    cta_chol_inv_smem(m, G, ldg, dyn, dyn + (size_t)m * m, dyn + 2 * (size_t)m * m, T, st, s_red);
+  } else {
+    cta_chol_inv(m, G, ldg, work, work + (size_t)m * m, T, st, s_red);
   }
-  cta_chol_inv(m, G, ldg, L, Li, T, st, s_red);
   if (ctl && threadIdx.x == 0) {
     // the reference's control flow of ortho_cd / ortho_vs_x, decided here instead of on the host
     ctl->passes += 1;
@@ -841,14 +949,16 @@ __device__ void cta_gram(int n, int m, const double* U, int ldu, double* G) {
 }
 
 // returns ok (uniform); growth accumulated as in 3323
+// (buf != null: G, L, Li, T live in shared memory and buf is the 2 m scratch of cta_chol_inv_smem)
 __device__ bool cta_ortho_cd(int n, int m, double* U, int ldu, double* G, double* L, double* Li, double* T,
-                             double* tmp, CholStatus* st, double* s_red, double& growth, int* passes) {
+                             double* tmp, CholStatus* st, double* s_red, double& growth, int* passes, double* buf) {
   growth = 1.0;
   for (int it = 1;; ++it) {
     if (it > 10) return false;  // 3248-3254
     if (threadIdx.x == 0) ++(*passes);
     cta_gram(n, m, U, ldu, G);
-    cta_chol_inv(m, G, m, L, Li, T, st, s_red);
+    if (buf) cta_chol_inv_smem(m, G, m, L, Li, buf, T, st, s_red);
+    else cta_chol_inv(m, G, m, L, Li, T, st, s_red);
     if (st->hard_fail) return false;
     const double l_norm = st->l_norm, linv_norm = st->linv_norm;
     const double rcond = l_norm * linv_norm;
@@ -890,19 +1000,26 @@ __device__ void cta_mgs2(int n, int m, double* U, int ldu, double* s_red) {
 }
 
 __global__ void __launch_bounds__(SM_THREADS)
-get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_red, double* u_p, double* work,
-                  CoeffStatus* cst) {
+get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_red, double* u_p_out, double* work,
+                  int in_smem, CoeffStatus* cst) {
   __shared__ double s_red[32];
   __shared__ CholStatus s_chol;
   __shared__ int s_passes;
+  extern __shared__ __align__(16) double dyn[];
   const int off_x = n_max - n_act;
   const double* u_x = a_red;  // len_u x n_max, ld len_a (eigenvectors left there by sym_eig)
-  double* G = work;                                 // n_act^2
+  // working set: in shared memory when it fits (the factorisations are chains of dependent steps:
+  // from global memory every step pays an L2 round trip, 0.98 ms per call at 111 x 37 against
+  // ~0.1 ms on chip), else in `work`
+  double* base = in_smem ? dyn : work;
+  double* G = base;                                 // n_act^2
   double* L = G + (size_t)n_act * n_act;            // n_act^2
   double* Li = L + (size_t)n_act * n_act;           // n_act^2
   double* T = Li + (size_t)n_act * n_act;           // n_act^2
   double* xu = T + (size_t)n_act * n_act;           // n_max x n_act
   double* tmp = xu + (size_t)n_max * n_act;         // len_u x n_act
+  double* u_p = in_smem ? tmp + (size_t)len_u * n_act : u_p_out;   // len_u x n_act (copied out at the end)
+  double* buf = in_smem ? u_p + (size_t)len_u * n_act : nullptr;   // 2 n_act
   if (threadIdx.x == 0) s_passes = 0;
   // u_p = u_x(:,ind_x:n_max) with 1 removed from the x coefficient (3716-3722)
   for (int e = threadIdx.x; e < len_u * n_act; e += blockDim.x) {
@@ -915,7 +1032,7 @@ get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_re
   // ortho_vs_x(len_u, n_max, n_act, u_x, u_p)
   double growth = 1.0;
   int sweeps = 0, fail = 0, qr = 0;
-  bool ok = cta_ortho_cd(len_u, n_act, u_p, len_u, G, L, Li, T, tmp, &s_chol, s_red, growth, &s_passes);
+  bool ok = cta_ortho_cd(len_u, n_act, u_p, len_u, G, L, Li, T, tmp, &s_chol, s_red, growth, &s_passes, buf);
   if (!ok) { cta_mgs2(len_u, n_act, u_p, len_u, s_red); ++qr; }
   bool done = false;
   while (!done) {
@@ -939,7 +1056,7 @@ get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_re
     __syncthreads();
     for (int e = threadIdx.x; e < len_u * n_act; e += blockDim.x) u_p[e] = tmp[e];
     __syncthreads();
-    ok = cta_ortho_cd(len_u, n_act, u_p, len_u, G, L, Li, T, tmp, &s_chol, s_red, growth, &s_passes);
+    ok = cta_ortho_cd(len_u, n_act, u_p, len_u, G, L, Li, T, tmp, &s_chol, s_red, growth, &s_passes, buf);
     double xu_norm;
     if (!ok) {
       cta_mgs2(len_u, n_act, u_p, len_u, s_red);
@@ -961,6 +1078,8 @@ get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_re
     if (sweeps > 10 && !done) { fail = 1; break; }  // 3568
   }
   __syncthreads();
+  if (in_smem)
+    for (int e = threadIdx.x; e < len_u * n_act; e += blockDim.x) u_p_out[e] = u_p[e];
   if (threadIdx.x == 0) { cst->sweeps = sweeps; cst->cd_passes = s_passes; cst->fail = fail; cst->qr = qr; }
 }
 
@@ -970,12 +1089,12 @@ void chol_inv(cudaStream_t st, int m, const double* metric, int ldm, double* T, 
               const CholLink& link) {
   static bool attr_set = false;
   if (!attr_set) {
-    DLB_CUDA_CHECK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM_MAX));
     attr_set = true;
   }
-  const size_t need = 2 * (size_t)m * m * sizeof(double);
-  const size_t smem = need <= 96 * 1024 ? need : 0;
-  const int threads = m <= 48 ? 256 : SM_THREADS;
+  const size_t need = (2 * (size_t)m * m + 2 * m) * sizeof(double);
+  const size_t smem = need <= CHOL_SMEM_MAX ? need : 0;
+  const int threads = m <= 32 ? 256 : (m <= 64 ? 512 : SM_THREADS);
   chol_inv_kernel<<<1, threads, smem, st>>>(m, metric, ldm, T, work, status_dev, link);
   ++g_launches;
   DLB_CUDA_CHECK(cudaGetLastError());
@@ -1090,10 +1209,22 @@ size_t coeffs_work_doubles(int len_u, int n_max, int n_act) {
 }
 
 int g_coeffs_threads = 0;   // 0: 1024 threads; experiment switch (diaglib_b200_k_set_tuning "coeffs_threads")
+int g_coeffs_smem = 1;      // 0: working set of get_coeffs in global memory (round-1 behaviour)
 void get_coeffs(cudaStream_t st, int len_a, int len_u, int n_max, int n_act, const double* a_red, double* u_p,
                 double* work, CoeffStatus* status_dev) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(get_coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
   const int threads = g_coeffs_threads > 0 ? g_coeffs_threads : SM_THREADS;
-  get_coeffs_kernel<<<1, threads, 0, st>>>(len_a, len_u, n_max, n_act, a_red, u_p, work, status_dev);
+  // G, L, Li, T, xu, tmp, u_p, buf in shared memory when they fit (and the block is wide enough for
+  // the in-shared-memory factorisation: threads >= the power of two above n_act)
+  const size_t need = (4 * (size_t)n_act * n_act + (size_t)n_max * n_act + 2 * (size_t)len_u * n_act + 2 * (size_t)n_act) * sizeof(double);
+  int rs = 32;
+  while (rs < n_act) rs <<= 1;
+  const int in_smem = (need <= 200 * 1024 && threads >= rs && g_coeffs_smem) ? 1 : 0;
+  get_coeffs_kernel<<<1, threads, in_smem ? need : 0, st>>>(len_a, len_u, n_max, n_act, a_red, u_p, work, in_smem, status_dev);
   ++g_launches;
   DLB_CUDA_CHECK(cudaGetLastError());
 }

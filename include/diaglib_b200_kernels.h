@@ -46,6 +46,9 @@ int32_t diaglib_b200_k_block_mul_gram(int64_t n, const double* v_dev, int64_t ld
 int32_t diaglib_b200_k_residual(int64_t n, int32_t m, const double* ax_dev, int64_t ldax, const double* x_dev,
                                 int64_t ldx, const double* theta_host, const int32_t* active_host, double* r_dev,
                                 int64_t ldr, double* norms_host);
+/* U (n x m, device) <- U * T in place, T (m x m, ld m, device) upper triangular with explicit zeros below
+ * the diagonal: the dtrmm('r','l','t','n') of ortho_cd (diaglib.f90:3327) */
+int32_t diaglib_b200_k_trmm(int64_t n, double* u, int64_t ldu, int32_t m, const double* t_dev);
 /* synthetic FCI-like matrix of config C4 (same arithmetic as diaglib_b200/problems.py
  * fci_like): fills col/val/diag (device arrays) for the global rows [r0, r1) of the n-row matrix
  * from the row pointers (device, r1 - r0 + 1 entries, starting at 0).  strides: n_strides sorted

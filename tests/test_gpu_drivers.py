@@ -779,8 +779,10 @@ def test_gen_david_reference_restart_switch(gpu_lib, oracle):
         hg = gpu_lib.last_history(n_max)
     finally:
         K.set_reference_restart(prev)
-    # same (wrong) answer as the literal oracle, same iteration count within 1
-    assert np.abs(eig[:n_targ] - lit["eig"][:n_targ]).max() / np.abs(lit["eig"][:n_targ]).max() < 1e-6
+    # same (wrong) answer as the literal oracle - both collapse to ~0 here, far from the true eigenvalues -
+    # and the same iteration count within 1
+    assert np.abs(eig[:n_targ] - lit["eig"][:n_targ]).max() < 1e-8
+    assert np.abs(eig[:n_targ] - good["eig"][:n_targ]).max() > 1e-3
     assert abs(len(hg["it"]) - len(lit["it"])) <= 1
 
 

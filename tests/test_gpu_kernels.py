@@ -311,7 +311,13 @@ def test_small_kernel_timing_table(K, gpu_lib):
                 row.append(1e3 * L.diaglib_b200_k_time_small(1, len_u, n_max, n_act, 20))
             finally:
                 L.diaglib_b200_k_set_tuning(b"coeffs_threads", prev)
-        print(f"get_coeffs len_u={len_u} n_max={n_max} n_act={n_act}: {row[0]:.1f} us (1024 threads), {row[1]:.1f} (512), {row[2]:.1f} (256)")
+        prev = L.diaglib_b200_k_set_tuning(b"coeffs_smem", 0)
+        try:
+            glob = 1e3 * L.diaglib_b200_k_time_small(1, len_u, n_max, n_act, 20)
+        finally:
+            L.diaglib_b200_k_set_tuning(b"coeffs_smem", prev)
+        print(f"get_coeffs len_u={len_u} n_max={n_max} n_act={n_act}: {row[0]:.1f} us (1024 threads), {row[1]:.1f} (512), "
+              f"{row[2]:.1f} (256); working set in global memory (round 1): {glob:.1f} us")
         assert row[0] > 0
 
 
