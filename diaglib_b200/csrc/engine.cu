@@ -1574,8 +1574,6 @@ int32_t diaglib_b200_init(int32_t device) {
   if (const char* ev = std::getenv("DIAGLIB_B200_EIG_BLOCK")) g_eig_block = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_SHORT")) g_spmm_short = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_CHUNK")) g_spmm_chunk = std::atoi(ev);
-  if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_TAIL")) g_spmm_tail = std::atoi(ev);
-  if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_MINB")) g_spmm_minb = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_CHUNK_TILED")) g_spmm_chunk_tiled = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_BMUL_RT256")) g_bmul_small_tiles = ev[0] != '1';
   g.inited = true;
@@ -2239,8 +2237,6 @@ int32_t diaglib_b200_k_set_tuning(const char* name, int32_t value) {
   int* slot = nullptr;
   if (nm == "coeffs_threads") slot = &g_coeffs_threads;
   else if (nm == "coeffs_smem") slot = &g_coeffs_smem;
-  else if (nm == "spmm_tail") slot = &g_spmm_tail;
-  else if (nm == "spmm_minb") slot = &g_spmm_minb;
   else if (nm == "spmm_chunk") slot = &g_spmm_chunk;
   else if (nm == "eig_block") slot = &g_eig_block;
   else if (nm == "eig_mode") slot = &g_eig_mode;

@@ -27,8 +27,6 @@ extern int g_eig_block;
 extern const int* g_live;
 extern int g_spmm_short;
 extern int g_spmm_chunk;
-extern int g_spmm_tail;
-extern int g_spmm_minb;
 extern int g_spmm_chunk_tiled;
 
 // ---- dense.cu -------------------------------------------------------------------------

@@ -23,6 +23,24 @@ constexpr double EPS = DBL_EPSILON;       // epsilon(one)
 constexpr double TOL_ORTHO = 2.0 * EPS;   // diaglib.f90:151
 constexpr size_t CHOL_SMEM_MAX = 200 * 1024;   // factors of chol_inv stay in shared memory up to m = 112
 
+// 1/sqrt(x) for x inside the float range: FP32 hardware seed + 3 Newton steps in FP64
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y = (double)rsqrtf((float)x);
+  const double hx = 0.5 * x;
+  y = y * (1.5 - hx * y * y);
+  y = y * (1.5 - hx * y * y);
+  y = y * (1.5 - hx * y * y);
+  return y;
+}
+// 1/x for |x| inside the float range: FP32 seed + 3 Newton steps
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y = (double)__frcp_rn((float)x);
+  y = y * (2.0 - x * y);
+  y = y * (2.0 - x * y);
+  y = y * (2.0 - x * y);
+  return y;
+}
+
 __device__ double cta_sum(double v, double* s_red) {
   v = warp_sum(v);
   __syncthreads();
@@ -123,22 +141,34 @@ __device__ int cta_potrf_inv_smem(int m, double* L, double* X, double* buf) {
   for (int j = 0; j < m; ++j) {
     const double piv = L[j + (size_t)j * m];
     if (!(piv > 0.0)) return j + 1;   // uniform; also catches NaN like dpotrf's disnan test
-    const double sq = sqrt(piv);
+    // 1/sqrt(piv): every thread needs it, so it is a multiplication per element instead of a
+    // division (the factor then differs from dpotrf's by an ulp here and there; parity is 1e-10)
+    const double rs = (piv > 1e-30 && piv < 1e30) ? fast_rsqrt(piv) : 1.0 / sqrt(piv);
     for (int i = j + tid; i < m; i += nt) {
-      const double v = (i == j) ? sq : L[i + (size_t)j * m] / sq;
+      const double v = (i == j) ? piv * rs : L[i + (size_t)j * m] * rs;
       colbuf[i] = v;
       L[i + (size_t)j * m] = v;
     }
     for (int c = tid; c <= j; c += nt) {
-      const double v = X[j + (size_t)c * m] / sq;
+      const double v = X[j + (size_t)c * m] * rs;
       rowbuf[c] = v;
       X[j + (size_t)c * m] = v;
     }
     __syncthreads();
     if (row > j && row < m && kq < CG) {
+      // row `row` has (row - j) entries of L and (j + 1) entries of X to update: row + 1 items
+      // whatever j is, dealt round-robin to the column groups
       const double li = colbuf[row];
-      for (int k = j + 1 + kq; k <= row; k += CG) L[row + (size_t)k * m] = fma(-li, colbuf[k], L[row + (size_t)k * m]);
-      for (int c = kq; c <= j; c += CG) X[row + (size_t)c * m] = fma(-li, rowbuf[c], X[row + (size_t)c * m]);
+      const int nl = row - j;
+      for (int t = kq; t <= row; t += CG) {
+        if (t < nl) {
+          const int k = j + 1 + t;
+          L[row + (size_t)k * m] = fma(-li, colbuf[k], L[row + (size_t)k * m]);
+        } else {
+          const int c = t - nl;
+          X[row + (size_t)c * m] = fma(-li, rowbuf[c], X[row + (size_t)c * m]);
+        }
+      }
     }
     __syncthreads();
   }
@@ -311,24 +341,6 @@ chol_inv_kernel(int m, const double* G, int ldg, double* T, double* work, CholSt
 // to be orthogonal to working precision, c^2 + s^2 = 1, its angle may be approximate).
 // Eigenvalues ascending, eigenvectors with their largest component positive.
 // ---------------------------------------------------------------------------------------
-// 1/sqrt(x) for x inside the float range: FP32 hardware seed + 3 Newton steps in FP64
-__device__ __forceinline__ double fast_rsqrt(double x) {
-  double y = (double)rsqrtf((float)x);
-  const double hx = 0.5 * x;
-  y = y * (1.5 - hx * y * y);
-  y = y * (1.5 - hx * y * y);
-  y = y * (1.5 - hx * y * y);
-  return y;
-}
-// 1/x for |x| inside the float range: FP32 seed + 3 Newton steps
-__device__ __forceinline__ double fast_rcp(double x) {
-  double y = (double)__frcp_rn((float)x);
-  y = y * (2.0 - x * y);
-  y = y * (2.0 - x * y);
-  y = y * (2.0 - x * y);
-  return y;
-}
-
 __device__ __forceinline__ void rr_pair(int r, int idx, int kp, int& p, int& q) {
   // round-robin tournament: round r (0..kp-2), pair idx (0..kp/2-1)
   // (0 <= r, idx < kp - 1, so one conditional subtraction replaces each modulo)

@@ -8,8 +8,6 @@
 namespace dlb {
 int g_spmm_short = 1;
 int g_spmm_chunk = 24;
-int g_spmm_tail = 0;     // DIAGLIB_B200_SPMM_TAIL: m mod 8 remainder: 0 generic row loop, 1 inlined tail block (slow), 2 tail function
-int g_spmm_minb = 4;     // DIAGLIB_B200_SPMM_MINB=3: three instead of four CTAs per SM (85 registers)
 int g_spmm_chunk_tiled = 0;   // DIAGLIB_B200_SPMM_CHUNK_TILED=1: column chunks also with a caller-given row order
 namespace {
 
@@ -104,42 +102,13 @@ __device__ __forceinline__ int32_t ld_nc_s32(const int32_t* p) {
   return v;
 }
 
-// The m mod JB remainder of the short-row kernel as a separate, NOT inlined function: the same
-// register-resident scheme for JT < JB columns, but compiled on its own so that it cannot disturb
-// the register allocation / load scheduling of the main loop (an inlined tail block made the whole
-// kernel 20-60 % slower: profiles/spmm_variants_r02.json).  Re-reads the row's column indices.
-template <int JT, int KMAX>
-__device__ __noinline__ void spmm_short_tail(int64_t row, int64_t b, int len, bool valid, const int32_t* __restrict__ col,
-                                             const double* __restrict__ val, const double* __restrict__ xb, int64_t ldx,
-                                             double* __restrict__ axb, int64_t ldax, double shift) {
-  double acc[JT];
-#pragma unroll
-  for (int jj = 0; jj < JT; ++jj) acc[jj] = 0.0;
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    const int kk = len > 0 ? (k < len ? k : len - 1) : 0;
-    const int32_t c = len > 0 ? ld_nc_s32(col + b + kk) : (int32_t)row;
-    double v = len > 0 ? ld_nc_f64(val + b + kk) : 0.0;
-    v = k < len ? v : 0.0;
-    const double* xp = xb + c;
-#pragma unroll
-    for (int jj = 0; jj < JT; ++jj) acc[jj] = fma(v, ld_nc_f64(xp + (int64_t)jj * ldx), acc[jj]);
-  }
-  if (valid) {
-#pragma unroll
-    for (int jj = 0; jj < JT; ++jj) {
-      double s = acc[jj];
-      if (shift != 0.0) s = fma(shift, xb[row + (int64_t)jj * ldx], s);
-      axb[row + (int64_t)jj * ldax] = s;
-    }
-  }
-}
-
-// TAIL (0..JB-1) = m mod JB, known at compile time: the last, narrower column block runs through
-// the same register-resident loop as the full blocks (a generic tail loop for 5 of 37 columns
-// used to cost as much as a full block of 8).
-template <int JB, int KMAX, int TAIL, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+// The m mod JB remainder goes through the generic row loop.  Three ways to give it the register-resident
+// scheme were measured and removed again (profiles/spmm_variants_r02.json, n = 2^24, m = 37, tiled
+// order): a second inlined block 4.52 ms, the same at 3 CTAs per SM 2.69 ms, a not-inlined tail
+// function 2.85 ms, against 2.57 ms with the generic tail - the extra code changes ptxas' schedule
+// of the main loop (fewer gathers in flight under the 64-register cap).
+template <int JB, int KMAX>
+__global__ void __launch_bounds__(256, 4)
 spmm_csr_short_kernel(int64_t n, int64_t n_halo, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                       const double* __restrict__ val, int m, const double* __restrict__ x, int64_t ldx,
                       const double* __restrict__ xh, double* __restrict__ ax, int64_t ldax, double shift,
@@ -190,37 +159,8 @@ spmm_csr_short_kernel(int64_t n, int64_t n_halo, const int64_t* __restrict__ row
       }
     }
   }
-  if (TAIL == 0 && valid && j0 < m)   // (only when the tail instantiations are switched off)
+  if (valid && j0 < m)
     spmm_row_generic<JB>(row, b, b + len, j0, n, n_halo, col, val, m, x, ldx, xh, ax, ldax, shift);
-  if (TAIL > JB) {   // TAIL = JB + t: the t remaining columns through the not-inlined function
-    spmm_short_tail<(TAIL > JB ? TAIL - JB : 1), KMAX>(row, b, len, valid, col, val, x + (int64_t)j0 * ldx, ldx,
-                                                       ax + (int64_t)j0 * ldax, ldax, shift);
-    return;
-  }
-  if (TAIL > 0) {   // m - j0 == TAIL by construction (the launcher picks the instantiation)
-    constexpr int JT = TAIL > 0 ? TAIL : 1;
-    double acc[JT];
-#pragma unroll
-    for (int jj = 0; jj < JT; ++jj) acc[jj] = 0.0;
-    const double* xb = x + (int64_t)j0 * ldx;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int kk = len > 0 ? (k < len ? k : len - 1) : 0;
-      double v = len > 0 ? ld_nc_f64(val + b + kk) : 0.0;
-      v = k < len ? v : 0.0;
-      const double* xp = xb + c[k];
-#pragma unroll
-      for (int jj = 0; jj < JT; ++jj) acc[jj] = fma(v, ld_nc_f64(xp + (int64_t)jj * ldx), acc[jj]);
-    }
-    if (valid) {
-#pragma unroll
-      for (int jj = 0; jj < JT; ++jj) {
-        double s = acc[jj];
-        if (shift != 0.0) s = fma(shift, xb[row + (int64_t)jj * ldx], s);
-        ax[row + (int64_t)(j0 + jj) * ldax] = s;
-      }
-    }
-  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -384,21 +324,8 @@ void spmm_csr(cudaStream_t st, const CsrDevice& A, int m, const double* x, int64
       const double* xc = x + (int64_t)j0 * ldx;
       const double* hc = x_halo ? x_halo + (int64_t)j0 * A.n_halo : nullptr;
       double* axc = ax + (int64_t)j0 * ldax;
-#define DLB_SHORT(T)                                                                                                      \
-  case T:                                                                                                                 \
-    if (g_spmm_minb == 3)                                                                                                 \
-      spmm_csr_short_kernel<8, 7, T, 3><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, mc, xc, ldx, hc, axc, ldax, \
-                                                              shift, A.order, first, count);                             \
-    else                                                                                                                  \
-      spmm_csr_short_kernel<8, 7, T, 4><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, mc, xc, ldx, hc, axc, ldax, \
-                                                              shift, A.order, first, count);                             \
-    break;
-      // g_spmm_tail: 0 = remainder through the generic row loop, 1 = inlined tail block, 2 = not-inlined tail function
-      switch (g_spmm_tail == 0 || mc % 8 == 0 ? 0 : (g_spmm_tail == 2 ? 8 + mc % 8 : mc % 8)) {
-        DLB_SHORT(0) DLB_SHORT(1) DLB_SHORT(2) DLB_SHORT(3) DLB_SHORT(4) DLB_SHORT(5) DLB_SHORT(6) DLB_SHORT(7)
-        DLB_SHORT(9) DLB_SHORT(10) DLB_SHORT(11) DLB_SHORT(12) DLB_SHORT(13) DLB_SHORT(14) DLB_SHORT(15)
-      }
-#undef DLB_SHORT
+      spmm_csr_short_kernel<8, 7><<<grid, 256, 0, st>>>(A.n, A.n_halo, A.rowptr, A.col, A.val, mc, xc, ldx, hc, axc, ldax, shift,
+                                                        A.order, first, count);
       ++g_launches;
     }
   } else {
