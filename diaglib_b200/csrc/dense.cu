@@ -1067,7 +1067,18 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
           for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * SV + a_off + r * 8];
 #pragma unroll
           for (int cc = 0; cc < NQT; ++cc) b[cc] = sCk[cc * 8 * PS + k4 * 4];
-          if (!tri) {
+          if (tri >= 2 && kc * BM_KC + k4 * 4 >= tri - 2) {
+            // rows >= tri - 2 of C are an identity block (Y = V1 C1 + V2): these four rows only touch
+            // the column tiles that hold their diagonal entries
+            const int d0 = kc * BM_KC + k4 * 4 - (tri - 2);
+            const int c0 = d0 >> 3, c1 = (d0 + 3) >> 3;
+#pragma unroll
+            for (int cc = 0; cc < NQT; ++cc)
+              if (cc == c0 || cc == c1) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
+              }
+          } else if (tri != 1) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -1163,7 +1174,8 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
 
 template <int NQT>
 void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc,
-                     int q, double alpha, double beta, double* Y, int64_t ldy, bool tri) {
+                     int q, double alpha, double beta, double* Y, int64_t ldy, int mode) {
+  const bool tri = mode == 1;   // the barrier-pipelined fallbacks know the triangular case only (an identity block is just data)
   constexpr int QB = NQT * 8;
   constexpr size_t smem = (size_t)BM_STAGES * (BM_KC * BM_SV + QB * BM_SC) * sizeof(double);
   static bool attr_set = false;
@@ -1198,7 +1210,7 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
     if (NQT == 5 && smem16 <= 220 * 1024 && n >= 256 * 2 && !g_bmul_small_tiles) {
       const int64_t nt16 = (n + 255) / 256;
       const unsigned grid = (unsigned)std::min<int64_t>(nt16, (int64_t)num_sms);
-      blockmul_ws_kernel<5, 16, false><<<grid, 17 * 32, smem16, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr, g_live);
+      blockmul_ws_kernel<5, 16, false><<<grid, 17 * 32, smem16, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, mode, nullptr, g_live);
       ++g_launches;
       return;
     }
@@ -1206,7 +1218,7 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
       // two CTAs per SM while C (p x q) is small enough to be resident twice, one beyond (Davidson:
       // p = ldu up to ~400 with q <= 40)
       const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * (smem8 <= 110 * 1024 ? 2 : 1));
-      blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, tri ? 1 : 0, nullptr, g_live);
+      blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, mode, nullptr, g_live);
       ++g_launches;
       return;
     }
@@ -1237,7 +1249,7 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
 }  // namespace
 
 void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc, int q,
-               double alpha, double beta, double* Y, int64_t ldy, bool upper_tri) {
+               double alpha, double beta, double* Y, int64_t ldy, bool upper_tri, int ident_from) {
   if (n <= 0 || q <= 0) return;
   if (q > 128) {
     // column blocks of Y are produced one launch at a time: Y must not overlap the columns of V
@@ -1254,12 +1266,15 @@ void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, 
     const int qb = std::min(128, q - q0);
     const double* Cb = C + (size_t)q0 * ldc;
     double* Yb = Y + (int64_t)q0 * ldy;
+    // 1: C upper triangular (first column block only); >= 2: rows >= mode - 2 of C are an identity block
+    // (single column block only: the diagonal of the identity must start at column 0)
+    const int mode = (upper_tri && q0 == 0) ? 1 : ((ident_from >= 0 && q <= 128) ? 2 + ident_from : 0);
     if (qb <= 40)
-      launch_blockmul<5>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy, upper_tri && q0 == 0);
+      launch_blockmul<5>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy, mode);
     else if (qb <= 80)
-      launch_blockmul<10>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy, upper_tri && q0 == 0);
+      launch_blockmul<10>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy, mode);
     else
-      launch_blockmul<16>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy, upper_tri && q0 == 0);
+      launch_blockmul<16>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy, mode);
   }
   DLB_CUDA_CHECK(cudaGetLastError());
 }

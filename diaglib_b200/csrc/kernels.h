@@ -42,8 +42,10 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
 // product is row-local (q <= 128).  Replaces dgemm('n','n',n,q,p,...) at
 // diaglib.f90:322,324,420,421,495,497,1717,1721,3544 and dtrmm('r','l','t','n') at 3327
 // (with C = L^-T stored as a full matrix with an explicit zero triangle).
+// ident_from >= 0 is a hint: rows [ident_from, p) of C are the q x q identity (Y = V1 C1 + V2 with
+// V2 the last q columns of V), so the tensor pipe only visits the tiles on that diagonal.
 void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc, int q,
-               double alpha, double beta, double* Y, int64_t ldy, bool upper_tri = false);
+               double alpha, double beta, double* Y, int64_t ldy, bool upper_tri = false, int ident_from = -1);
 
 // U <- U * T, T upper triangular m x m (ld m), in place (dtrmm at diaglib.f90:3327).
 void block_trmm_inplace(cudaStream_t st, int64_t n, double* U, int64_t ldu, int m, const double* T);
@@ -156,6 +158,10 @@ struct CoeffStatus { int sweeps; int cd_passes; int fail; int qr; };
 size_t coeffs_work_doubles(int len_u, int n_max, int n_act);
 void get_coeffs(cudaStream_t st, int len_a, int len_u, int n_max, int n_act, const double* a_red, double* u_p,
                 double* work, CoeffStatus* status_dev);
+
+// cp ((m + k) x k, ldc) = [-xu (m x k, ldx); I_k]: coefficients that turn u <- u - x xu (3544) into one
+// product over the adjacent blocks [x u]
+void proj_coeff(cudaStream_t st, int m, int k, const double* xu, int ldx, double* cp, int ldc);
 
 // reduced problem of caslr_eff_driver: c = a^T a (1303); eig(i) = sqrt(e(k-1-i)), up(:,i) = z(:,k-1-i),
 // um(:,i) = sred up(:,i) / eig(i) (1314-1324)

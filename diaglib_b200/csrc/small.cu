@@ -141,34 +141,26 @@ __device__ int cta_potrf_inv_smem(int m, double* L, double* X, double* buf) {
   for (int j = 0; j < m; ++j) {
     const double piv = L[j + (size_t)j * m];
     if (!(piv > 0.0)) return j + 1;   // uniform; also catches NaN like dpotrf's disnan test
-    // 1/sqrt(piv): every thread needs it, so it is a multiplication per element instead of a
-    // division (the factor then differs from dpotrf's by an ulp here and there; parity is 1e-10)
-    const double rs = (piv > 1e-30 && piv < 1e30) ? fast_rsqrt(piv) : 1.0 / sqrt(piv);
+    // (measured: multiplying by a Newton-refined reciprocal square root instead of dividing, and one
+    // merged update loop instead of two, changed nothing at m = 37 (34.9 vs 33.8 us) and lost at
+    // m = 74 (135 vs 97 us: the merged loop diverges inside a warp) - the step is bound by its two
+    // barriers and the shared-memory round trips between them, not by the arithmetic)
+    const double sq = sqrt(piv);
     for (int i = j + tid; i < m; i += nt) {
-      const double v = (i == j) ? piv * rs : L[i + (size_t)j * m] * rs;
+      const double v = (i == j) ? sq : L[i + (size_t)j * m] / sq;
       colbuf[i] = v;
       L[i + (size_t)j * m] = v;
     }
     for (int c = tid; c <= j; c += nt) {
-      const double v = X[j + (size_t)c * m] * rs;
+      const double v = X[j + (size_t)c * m] / sq;
       rowbuf[c] = v;
       X[j + (size_t)c * m] = v;
     }
     __syncthreads();
     if (row > j && row < m && kq < CG) {
-      // row `row` has (row - j) entries of L and (j + 1) entries of X to update: row + 1 items
-      // whatever j is, dealt round-robin to the column groups
       const double li = colbuf[row];
-      const int nl = row - j;
-      for (int t = kq; t <= row; t += CG) {
-        if (t < nl) {
-          const int k = j + 1 + t;
-          L[row + (size_t)k * m] = fma(-li, colbuf[k], L[row + (size_t)k * m]);
-        } else {
-          const int c = t - nl;
-          X[row + (size_t)c * m] = fma(-li, rowbuf[c], X[row + (size_t)c * m]);
-        }
-      }
+      for (int k = j + 1 + kq; k <= row; k += CG) L[row + (size_t)k * m] = fma(-li, colbuf[k], L[row + (size_t)k * m]);
+      for (int c = kq; c <= j; c += CG) X[row + (size_t)c * m] = fma(-li, rowbuf[c], X[row + (size_t)c * m]);
     }
     __syncthreads();
   }
@@ -1270,6 +1262,20 @@ __global__ void lr_um_kernel(int k_, int n_max, const double* __restrict__ sred,
   um[r + (size_t)i * ldum] = s / sqrt(e[k_ - 1 - i]);
 }
 }  // namespace
+
+namespace {
+// cp ((m + k) x k, ldc) = [-xu (m x k, ldx); I_k]
+__global__ void proj_coeff_kernel(int m, int k, const double* __restrict__ xu, int ldx, double* __restrict__ cp, int ldc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= m + k || j >= k) return;
+  cp[i + (size_t)j * ldc] = i < m ? -xu[i + (size_t)j * ldx] : (i - m == j ? 1.0 : 0.0);
+}
+}  // namespace
+void proj_coeff(cudaStream_t st, int m, int k, const double* xu, int ldx, double* cp, int ldc) {
+  if (k <= 0) return;
+  proj_coeff_kernel<<<dim3((m + k + 127) / 128, k), 128, 0, st>>>(m, k, xu, ldx, cp, ldc);
+  ++g_launches;
+}
 
 void small_ata(cudaStream_t st, int k, const double* a, int lda, double* c, int ldc) {
   if (k <= 0) return;

@@ -78,7 +78,11 @@ def assert_history(ro, hg, n_targ, upto=None):
     L = min(len(hg["it"]), len(ro["it"])) if upto is None else upto
     a, b = hg["eig"][:L, :n_targ], ro["hist_eig"][:L, :n_targ]
     assert (np.abs(a - b) / np.abs(b)).max() < 1e-4
-    assert (np.abs(a[:3] - b[:3]) / np.abs(b[:3])).max() < 1e-6  # the first iterations are still in lock-step
+    # the first iterations are still in lock-step: rounding-level differences (summation order of the
+    # Gram kernels, the Cholesky's division order) grow ~10x per iteration from a random start and
+    # sit at 0.3-1.3e-6 after three iterations across builds of this library
+    assert (np.abs(a[:3] - b[:3]) / np.abs(b[:3])).max() < 1e-5
+    assert (np.abs(a[:1] - b[:1]) / np.abs(b[:1])).max() < 1e-8
 
 
 @pytest.mark.parametrize("driver", ["lobpcg", "davidson"])
