@@ -2092,6 +2092,11 @@ int32_t diaglib_b200_k_trmm(int64_t n, double* u, int64_t ldu, int32_t m, const 
   block_trmm_inplace(g.st, n, u, ldu, m, t_dev);
   return 0;
 }
+int32_t diaglib_b200_k_trmm_oop(int64_t n, const double* u, int64_t ldu, int32_t m, const double* t_dev, double* y, int64_t ldy) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  block_mul(g.st, n, u, ldu, m, t_dev, m, m, 1.0, 0.0, y, ldy, true);
+  return 0;
+}
 int32_t diaglib_b200_k_block_mul_gram(int64_t n, const double* v, int64_t ldv, int32_t p, const double* c, int32_t ldc,
                                       int32_t q, double alpha, double beta, double* y, int64_t ldy, int32_t upper_tri,
                                       double* g_out, int32_t ldg) {

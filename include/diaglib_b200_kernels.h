@@ -49,6 +49,8 @@ int32_t diaglib_b200_k_residual(int64_t n, int32_t m, const double* ax_dev, int6
 /* U (n x m, device) <- U * T in place, T (m x m, ld m, device) upper triangular with explicit zeros below
  * the diagonal: the dtrmm('r','l','t','n') of ortho_cd (diaglib.f90:3327) */
 int32_t diaglib_b200_k_trmm(int64_t n, double* u, int64_t ldu, int32_t m, const double* t_dev);
+/* the same product written to another block, Y (n x m, ldy) = U * T (measurement of in-place vs out-of-place) */
+int32_t diaglib_b200_k_trmm_oop(int64_t n, const double* u, int64_t ldu, int32_t m, const double* t_dev, double* y, int64_t ldy);
 /* synthetic FCI-like matrix of config C4 (same arithmetic as diaglib_b200/problems.py
  * fci_like): fills col/val/diag (device arrays) for the global rows [r0, r1) of the n-row matrix
  * from the row pointers (device, r1 - r0 + 1 entries, starting at 0).  strides: n_strides sorted

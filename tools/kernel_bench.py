@@ -103,6 +103,43 @@ def main():
             ax.free()
         print(json.dumps(dict(n=n, **out)))
         return
+    if only == "trmm":
+        # the in-place triangular multiply of ortho_cd (diaglib.f90:3327) on a 37-column block
+        tm = np.asfortranarray(np.triu(np.random.default_rng(1).standard_normal((37, 37)) * 0.05 + np.eye(37)))
+        td = K.DeviceArray.from_numpy(tm)
+        lib.diaglib_b200_k_trmm(n, v.ptr, n, 37, td.ptr)
+        lib.diaglib_b200_sync()
+        K.timer_start()
+        for _ in range(reps):
+            lib.diaglib_b200_k_trmm(n, v.ptr, n, 37, td.ptr)
+        ms = K.timer_stop_ms() / reps
+        out["trmm_37_in_place"] = dict(ms=round(ms, 4), gbs=round(16.0 * n * 37 / ms / 1e6, 1))
+        tds = {}
+        for m in (37, 24, 16):
+            tm2 = np.asfortranarray(np.triu(np.random.default_rng(1).standard_normal((m, m)) * 0.05 + np.eye(m)))
+            tds[m] = K.DeviceArray.from_numpy(tm2)
+            for mode in ("in_place", "out_of_place"):
+                def go():
+                    if mode == "in_place":
+                        lib.diaglib_b200_k_trmm(n, v.ptr, n, m, tds[m].ptr)
+                    else:
+                        lib.diaglib_b200_k_trmm_oop(n, v.ptr, n, m, tds[m].ptr, w.ptr, n)
+                go()
+                lib.diaglib_b200_sync()
+                K.timer_start()
+                for _ in range(reps):
+                    go()
+                ms = K.timer_stop_ms() / reps
+                out[f"trmm_{m}_{mode}"] = dict(ms=round(ms, 4), gbs=round(16.0 * n * m / ms / 1e6, 1))
+        # a plain device copy of the same block for reference (read + write, different buffers / same buffer region)
+        lib.diaglib_b200_d2d(w.ptr, v.ptr, 8 * n * 37)
+        K.timer_start()
+        for _ in range(reps):
+            lib.diaglib_b200_d2d(w.ptr, v.ptr, 8 * n * 37)
+        ms = K.timer_stop_ms() / reps
+        out["memcpy_d2d_37cols"] = dict(ms=round(ms, 4), gbs=round(16.0 * n * 37 / ms / 1e6, 1))
+        print(json.dumps(dict(n=n, **out)))
+        return
     if only == "gram":
         t_gram(111, 111, 1, v, w, "gram_sym_111")
         t_gram(74, 37, 0, v, w, "gram_74x37")
