@@ -988,6 +988,30 @@ constexpr int BMW_STAGES = 4;
 // the next ortho_cd pass needs (diaglib.f90:3256), so that U is not read again: the finished
 // 16 x 40 accumulator tile of a warp is re-used as DMMA operands through warp shuffles (the
 // C-fragment of lane (row g, columns 2t,2t+1) becomes the A/B fragment of lane (column, row)).
+// one 16-column chunk (index KC, compile time) of Y += V C for an upper triangular C: only the tiles
+// with columns >= the chunk's rows are multiplied, decided at compile time
+template <int NQT, int KC>
+__device__ __forceinline__ void bm_chunk_tri(double (&acc)[2][NQT][2], const double* sV, const double* sCb, int a_off, int SV,
+                                             int PS) {
+  const double* sCk = sCb + KC * BM_KC;
+#pragma unroll
+  for (int k4 = 0; k4 < BM_KC / 4; ++k4) {
+    const int kbase = KC * BM_KC + k4 * 4;
+    if (kbase >= NQT * 8) continue;
+    double a[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * SV + a_off + r * 8];
+#pragma unroll
+    for (int cc = 0; cc < NQT; ++cc) {
+      if (kbase < (cc + 1) * 8) {
+        const double b = sCk[cc * 8 * PS + k4 * 4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b);
+      }
+    }
+  }
+}
+
 template <int NQT, int NCONS, bool GRAM>
 __global__ void __launch_bounds__((NCONS + 1) * 32)
 blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, const double* __restrict__ C, int ldc,
@@ -1056,46 +1080,70 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
     int s = 0;
     uint32_t ph = 0;
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
-      for (int kc = 0; kc < nk; ++kc) {
+      // one k-chunk of the tile: wait for its stage, multiply, release the stage
+      auto stage_wait = [&]() -> const double* {
         mbar_wait(&full[s], ph);
-        const double* sV = ring + (size_t)s * STAGE;
-        const double* sCk = sC + kc * BM_KC + b_off;
-#pragma unroll
-        for (int k4 = 0; k4 < BM_KC / 4; ++k4) {
-          double a[2], b[NQT];
-#pragma unroll
-          for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * SV + a_off + r * 8];
-#pragma unroll
-          for (int cc = 0; cc < NQT; ++cc) b[cc] = sCk[cc * 8 * PS + k4 * 4];
-          if (tri >= 2 && kc * BM_KC + k4 * 4 >= tri - 2) {
-            // rows >= tri - 2 of C are an identity block (Y = V1 C1 + V2): these four rows only touch
-            // the column tiles that hold their diagonal entries
-            const int d0 = kc * BM_KC + k4 * 4 - (tri - 2);
-            const int c0 = d0 >> 3, c1 = (d0 + 3) >> 3;
-#pragma unroll
-            for (int cc = 0; cc < NQT; ++cc)
-              if (cc == c0 || cc == c1) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
-              }
-          } else if (tri != 1) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-              for (int cc = 0; cc < NQT; ++cc) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
-          } else {
-            const int kbase = kc * BM_KC + k4 * 4;
-#pragma unroll
-            for (int cc = 0; cc < NQT; ++cc)
-              if (kbase < (cc + 1) * 8) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
-              }
-          }
-        }
+        return ring + (size_t)s * STAGE;
+      };
+      auto stage_release = [&]() {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         if (++s == BMW_STAGES) { s = 0; ph ^= 1; }
+      };
+      if (tri == 1 && NQT == 5) {
+        // C upper triangular, q <= 40 (the dtrmm of ortho_cd): at most three chunks, written out with the
+        // chunk index as a compile-time constant so that the tiles below the diagonal are not even
+        // issued.  A predicated-off DMMA still occupies its slot of the FP64 pipe (ncu: pipe 71 % busy
+        // with 56 % of the issued DMMAs predicated off, math-pipe-throttle the top stall), which made
+        // the triangular multiply pipe-bound although it needs half the flops.
+        if (0 < nk) { const double* sV = stage_wait(); bm_chunk_tri<NQT, 0>(acc, sV, sC + b_off, a_off, SV, PS); stage_release(); }
+        if (1 < nk) { const double* sV = stage_wait(); bm_chunk_tri<NQT, 1>(acc, sV, sC + b_off, a_off, SV, PS); stage_release(); }
+        if (2 < nk) { const double* sV = stage_wait(); bm_chunk_tri<NQT, 2>(acc, sV, sC + b_off, a_off, SV, PS); stage_release(); }
+      } else {
+        for (int kc = 0; kc < nk; ++kc) {
+          const double* sV = stage_wait();
+          if (tri >= 2 && kc * BM_KC >= tri - 2) {
+            // rows >= tri - 2 of C are an identity block (Y = V1 C1 + V2) and this chunk lies inside it:
+            // its columns of V are ADDED to the accumulators they belong to, no tensor instruction
+            const int shift_k = (tri - 2) - kc * BM_KC;   // chunk column of output column `col` = col + shift_k
+#pragma unroll
+            for (int cc = 0; cc < NQT; ++cc)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int col = cc * 8 + (lane & 3) * 2 + e;
+                const int kk = col + shift_k;
+                if (kk >= 0 && kk < BM_KC && col < q) {
+#pragma unroll
+                  for (int r = 0; r < 2; ++r) acc[r][cc][e] += sV[kk * SV + warp * 16 + r * 8 + (lane >> 2)];
+                }
+              }
+          } else {
+            const double* sCk = sC + kc * BM_KC + b_off;
+#pragma unroll
+            for (int k4 = 0; k4 < BM_KC / 4; ++k4) {
+              double a[2], b[NQT];
+#pragma unroll
+              for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * SV + a_off + r * 8];
+#pragma unroll
+              for (int cc = 0; cc < NQT; ++cc) b[cc] = sCk[cc * 8 * PS + k4 * 4];
+              if (tri != 1) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                  for (int cc = 0; cc < NQT; ++cc) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
+              } else {
+                const int kbase = kc * BM_KC + k4 * 4;   // (wider triangular blocks: predicated)
+#pragma unroll
+                for (int cc = 0; cc < NQT; ++cc)
+                  if (kbase < (cc + 1) * 8) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
+                  }
+              }
+            }
+          }
+          stage_release();
+        }
       }
       const int64_t row0 = (blockIdx.x + ti * gridDim.x) * RT;
 #pragma unroll
