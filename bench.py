@@ -687,8 +687,8 @@ def main():
             one(f"gram {2 * q}x{q} (x^T u, 3543)",
                 lambda: lib.diaglib_b200_k_gram(n_loc, v.ptr, n_loc, 2 * q, y.ptr, n_loc, q, g74.ptr, 2 * q, 0),
                 2.0 * 2 * q * q, executed_gram(2 * q, q, False), 8.0 * n_loc * 3 * q),
-            one(f"block_mul {2 * q}->{q}, u -= x xu (3544)",
-                lambda: lib.diaglib_b200_k_block_mul(n_loc, v.ptr, n_loc, 2 * q, xu.ptr, 2 * q, q, -1.0, 1.0, y.ptr, n_loc),
+            one(f"u -= x xu, x {2 * q} columns, u the {q} columns behind it (3544; one product over [x u])",
+                lambda: lib.diaglib_b200_k_project_out(n_loc, 2 * q, q, v.ptr, n_loc, xu.ptr, v.col_ptr(2 * q), n_loc),
                 2.0 * 2 * q * q, executed_bmul(2 * q, q, False), 8.0 * n_loc * 4 * q),
         ]
         for a_ in (td, xu, g37, g74):

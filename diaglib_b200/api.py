@@ -83,6 +83,7 @@ def lib():
         L.diaglib_b200_k_sym_eig_time_ms.restype = C.c_double
         L.diaglib_b200_k_set_tuning.argtypes = [C.c_char_p, C.c_int32]
         L.diaglib_b200_k_trmm.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+        L.diaglib_b200_k_project_out.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
         L.diaglib_b200_k_trmm_oop.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
         L.diaglib_b200_k_time_small.argtypes = [C.c_int32] * 5
         L.diaglib_b200_k_time_small.restype = C.c_double

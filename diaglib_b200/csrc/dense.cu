@@ -1090,15 +1090,24 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
         if (lane == 0) mbar_arrive(&empty[s]);
         if (++s == BMW_STAGES) { s = 0; ph ^= 1; }
       };
-      if (tri == 1 && NQT == 5) {
-        // C upper triangular, q <= 40 (the dtrmm of ortho_cd): at most three chunks, written out with the
-        // chunk index as a compile-time constant so that the tiles below the diagonal are not even
-        // issued.  A predicated-off DMMA still occupies its slot of the FP64 pipe (ncu: pipe 71 % busy
-        // with 56 % of the issued DMMAs predicated off, math-pipe-throttle the top stall), which made
-        // the triangular multiply pipe-bound although it needs half the flops.
-        if (0 < nk) { const double* sV = stage_wait(); bm_chunk_tri<NQT, 0>(acc, sV, sC + b_off, a_off, SV, PS); stage_release(); }
-        if (1 < nk) { const double* sV = stage_wait(); bm_chunk_tri<NQT, 1>(acc, sV, sC + b_off, a_off, SV, PS); stage_release(); }
-        if (2 < nk) { const double* sV = stage_wait(); bm_chunk_tri<NQT, 2>(acc, sV, sC + b_off, a_off, SV, PS); stage_release(); }
+      if (tri == 1) {
+        // C upper triangular (the dtrmm of ortho_cd, p = q <= 8 NQT): at most NQT / 2 chunks, written out
+        // with the chunk index as a compile-time constant so that the tiles below the diagonal are not
+        // even issued.  A predicated-off DMMA still occupies its slot of the FP64 pipe (ncu on the
+        // round-1 form: pipe 71 % busy with 56 % of the issued DMMAs predicated off, math-pipe-throttle
+        // the top stall), which made the triangular multiply pipe-bound although it needs half the
+        // flops: 2.23 -> 1.68 ms at 37 columns, n = 2^24 (0.68 -> 0.91 of the HBM copy peak).
+#define DLB_TRI_CHUNK(KC)                                                                   \
+  if constexpr (KC * BM_KC < NQT * 8) {                                                     \
+    if (KC < nk) {                                                                          \
+      const double* sV = stage_wait();                                                      \
+      bm_chunk_tri<NQT, KC>(acc, sV, sC + b_off, a_off, SV, PS);                            \
+      stage_release();                                                                      \
+    }                                                                                       \
+  }
+        DLB_TRI_CHUNK(0) DLB_TRI_CHUNK(1) DLB_TRI_CHUNK(2) DLB_TRI_CHUNK(3)
+        DLB_TRI_CHUNK(4) DLB_TRI_CHUNK(5) DLB_TRI_CHUNK(6) DLB_TRI_CHUNK(7)
+#undef DLB_TRI_CHUNK
       } else {
         for (int kc = 0; kc < nk; ++kc) {
           const double* sV = stage_wait();
@@ -1126,20 +1135,10 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
               for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * SV + a_off + r * 8];
 #pragma unroll
               for (int cc = 0; cc < NQT; ++cc) b[cc] = sCk[cc * 8 * PS + k4 * 4];
-              if (tri != 1) {
 #pragma unroll
-                for (int r = 0; r < 2; ++r)
+              for (int r = 0; r < 2; ++r)
 #pragma unroll
-                  for (int cc = 0; cc < NQT; ++cc) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
-              } else {
-                const int kbase = kc * BM_KC + k4 * 4;   // (wider triangular blocks: predicated)
-#pragma unroll
-                for (int cc = 0; cc < NQT; ++cc)
-                  if (kbase < (cc + 1) * 8) {
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
-                  }
-              }
+                for (int cc = 0; cc < NQT; ++cc) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
             }
           }
           stage_release();

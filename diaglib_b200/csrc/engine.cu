@@ -2092,6 +2092,15 @@ int32_t diaglib_b200_k_trmm(int64_t n, double* u, int64_t ldu, int32_t m, const 
   block_trmm_inplace(g.st, n, u, ldu, m, t_dev);
   return 0;
 }
+int32_t diaglib_b200_k_project_out(int64_t n, int32_t m, int32_t k, const double* x, int64_t ldx, const double* xu_dev, double* u,
+                                   int64_t ldu) {
+  if (!require_init()) return DIAGLIB_B200_ENODEVICE;
+  g.ensure_small(k, m);
+  if (g.status) return g.status;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(g.d_xu, xu_dev, (size_t)m * k * sizeof(double), cudaMemcpyDeviceToDevice, g.st));
+  g.project_out(n, m, k, x, ldx, u, ldu);
+  return 0;
+}
 int32_t diaglib_b200_k_trmm_oop(int64_t n, const double* u, int64_t ldu, int32_t m, const double* t_dev, double* y, int64_t ldy) {
   if (!require_init()) return DIAGLIB_B200_ENODEVICE;
   block_mul(g.st, n, u, ldu, m, t_dev, m, m, 1.0, 0.0, y, ldy, true);

@@ -49,6 +49,10 @@ int32_t diaglib_b200_k_residual(int64_t n, int32_t m, const double* ax_dev, int6
 /* U (n x m, device) <- U * T in place, T (m x m, ld m, device) upper triangular with explicit zeros below
  * the diagonal: the dtrmm('r','l','t','n') of ortho_cd (diaglib.f90:3327) */
 int32_t diaglib_b200_k_trmm(int64_t n, double* u, int64_t ldu, int32_t m, const double* t_dev);
+/* u (n x k) <- u - x (n x m) xu (m x k, device, ld m): the projection step of ortho_vs_x (diaglib.f90:3544) the
+ * way the drivers run it (one product over [x u] when u is the block right behind x) */
+int32_t diaglib_b200_k_project_out(int64_t n, int32_t m, int32_t k, const double* x, int64_t ldx, const double* xu_dev, double* u,
+                                   int64_t ldu);
 /* the same product written to another block, Y (n x m, ldy) = U * T (measurement of in-place vs out-of-place) */
 int32_t diaglib_b200_k_trmm_oop(int64_t n, const double* u, int64_t ldu, int32_t m, const double* t_dev, double* y, int64_t ldy);
 /* synthetic FCI-like matrix of config C4 (same arithmetic as diaglib_b200/problems.py
