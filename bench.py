@@ -426,6 +426,7 @@ def run_c4(args, rank, world, local):
             "true_rms_residual_max": true_rms, "true_max_residual": true_max,
             "eig": [float(x) for x in eig[:C4_N_TARG]], "parity": parity, "gpu_launches": int(launches), "clocks": clocks,
             "phases_s": {k: round(float(v), 5) for k, v in timers.items()}, "stats": stats,
+            "allreduce": D.peer_info(),
         }
         print(json.dumps(line), flush=True)
     ok_res = true_rms < 2 * TOL and true_max < 20 * TOL
@@ -755,6 +756,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": bench_config(nx, n_loc, world), "rows_per_gpu": n_loc, "parallelism": f"row-partition x{world}",
             "stats": D.last_stats(),
+            "allreduce": D.peer_info(),
             "parity": parity,
             "time_to_converge_s": ms_per_step * 1e-3, "iterations": tot_its / args.steps, "converged": True,
             "final_rms_residual_max": res_max, "eig_lowest": [float(x) for x in eig[:4]],

@@ -29,6 +29,7 @@ from .api import (  # noqa: F401
     set_halo,
     last_history,
     last_stats,
+    peer_info,
     last_timers,
     set_profile,
 )

@@ -321,6 +321,14 @@ def set_profile(on: bool) -> None:
     lib().diaglib_b200_set_profile(C.c_int32(1 if on else 0))
 
 
+def peer_info():
+    """How the k x k all-reduces travel: ranks sharing the peer window (0 = NCCL), window calls of the last
+    driver call, time-out flag, completed window calls."""
+    s = np.zeros(4, np.int64)
+    lib().diaglib_b200_peer_info(_ptr(s))
+    return dict(window_ranks=int(s[0]), calls=int(s[1]), error=int(s[2]), epoch=int(s[3]))
+
+
 def last_stats():
     s = np.zeros(8, np.int64)
     lib().diaglib_b200_stats(_ptr(s))

@@ -16,6 +16,8 @@
 
 namespace dlb {
 const int* g_live = nullptr;   // see kernels.h
+PeerWin g_peerwin;
+bool g_fuse_allreduce = false;
 
 bool g_disable_ws = false;
 bool g_disable_tma = false;
@@ -549,30 +551,156 @@ bool make_tmap(CUtensorMap* tm, const double* base, int64_t n, int ncols, int64_
   return r == CUDA_SUCCESS;
 }
 
-// deterministic (fixed-order) sum of the per-CTA partials; mirrors the lower triangle if sym
-__global__ void gram_reduce_kernel(const double* __restrict__ partial, int ncta, int PB, int QB, int p, int q,
-                                   int sym, double* __restrict__ C, int ldc, double* __restrict__ Ct,
-                                   const int* __restrict__ live) {
+// deterministic (fixed-order) sum of the per-CTA partials; mirrors the lower triangle if sym.
+// A CTA of GRED_SL warps produces 32 consecutive elements: warp s adds the partials c = s, s + GRED_SL,
+// ... of its 32 elements (coalesced 256-byte reads, all loads of a thread independent), then the
+// GRED_SL slice sums are added in a fixed order through shared memory.  The replicated tail of every
+// Gram call: 22 us with one thread per element walking all ~148-296 partials, ~5 us in this form.
+constexpr int GRED_SL = 8;
+__global__ void __launch_bounds__(GRED_SL * 32)
+gram_reduce_kernel(const double* __restrict__ partial, int ncta, int PB, int QB, int p, int q,
+                   int sym, double* __restrict__ C, int ldc, double* __restrict__ Ct,
+                   const int* __restrict__ live) {
   if (live && *live == 0) return;   // predicated step of a speculative ortho chain (engine.cu)
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p * q) return;
-  const int i = idx % p, j = idx / p;
-  int si = i, sj = j;
-  if (sym && j > i) { si = j; sj = i; }
-  const double* src = partial + si + (size_t)sj * PB;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  const size_t step = (size_t)PB * QB;
-  int c = 0;
-  for (; c + 4 <= ncta; c += 4) {
-    s0 += src[(size_t)c * step];
-    s1 += src[(size_t)(c + 1) * step];
-    s2 += src[(size_t)(c + 2) * step];
-    s3 += src[(size_t)(c + 3) * step];
+  __shared__ double red[GRED_SL][32];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
+  const bool valid = idx < p * q;
+  int i = 0, j = 0;
+  double s0 = 0.0, s1 = 0.0;
+  if (valid) {
+    i = idx % p;
+    j = idx / p;
+    int si = i, sj = j;
+    if (sym && j > i) { si = j; sj = i; }
+    const size_t step = (size_t)PB * QB;
+    const double* src = partial + si + (size_t)sj * PB + (size_t)sl * step;
+    int c = sl;
+#pragma unroll 4
+    for (; c + GRED_SL < ncta; c += 2 * GRED_SL) {
+      s0 += src[0];
+      s1 += src[(size_t)GRED_SL * step];
+      src += (size_t)2 * GRED_SL * step;
+    }
+    if (c < ncta) s0 += src[0];
   }
-  for (; c < ncta; ++c) s0 += src[(size_t)c * step];
-  const double v = (s0 + s1) + (s2 + s3);
-  C[i + (size_t)j * ldc] = v;
-  if (Ct) Ct[j + (size_t)i * ldc] = v;  // mirror of an off-diagonal block of a symmetric product
+  red[sl][lane] = s0 + s1;
+  __syncthreads();
+  if (sl == 0 && valid) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < GRED_SL; ++w) v += red[w][lane];
+    C[i + (size_t)j * ldc] = v;
+    if (Ct) Ct[j + (size_t)i * ldc] = v;  // mirror of an off-diagonal block of a symmetric product
+  }
+}
+
+// The same reduction finished by the all-reduce over the peer windows (kernels.h): phase 1 stores the
+// locally reduced element into this rank's slot of every rank's window and the last CTA to get
+// there publishes the epoch; phase 2 waits for the epochs of all senders in the own window and adds
+// the slots in rank order.  All CTAs of the grid are co-resident (<= 512 CTAs of 256 threads).
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void __launch_bounds__(GRED_SL * 32)
+gram_reduce_peer_kernel(const double* partial, int ncta, int PB, int QB, int p, int q, int sym,
+                        double* C, int ldc, double* Ct, const int* __restrict__ live,
+                        PeerWin w, int max_from) {
+  if (live && *live == 0) return;   // the same on every rank: the decisions are taken on all-reduced data
+  __shared__ double red[GRED_SL][32];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
+  const bool valid = idx < p * q;
+  const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(&w.state->epoch) + 1;
+  const size_t half = (size_t)(e & 1) * w.nranks * PEER_CAP;
+  int i = 0, j = 0;
+  double s0 = 0.0, s1 = 0.0;
+  if (valid) {
+    i = idx % p;
+    j = idx / p;
+    int si = i, sj = j;
+    if (sym && j > i) { si = j; sj = i; }
+    const size_t step = (size_t)PB * QB;
+    const double* src = partial + si + (size_t)sj * PB + (size_t)sl * step;
+    int c = sl;
+#pragma unroll 4
+    for (; c + GRED_SL < ncta; c += 2 * GRED_SL) {
+      s0 += src[0];
+      s1 += src[(size_t)GRED_SL * step];
+      src += (size_t)2 * GRED_SL * step;
+    }
+    if (c < ncta) s0 += src[0];
+  }
+  red[sl][lane] = s0 + s1;
+  __syncthreads();
+  // ---- phase 1: warp r stores the 32 values into this rank's slot of rank r's window
+  if (valid) {
+    double v = 0.0;
+#pragma unroll
+    for (int x = 0; x < GRED_SL; ++x) v += red[x][lane];
+    for (int r = sl; r < w.nranks; r += GRED_SL) w.data[r][half + (size_t)w.rank * PEER_CAP + idx] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&w.state->arrive, 1u);
+    if (t == gridDim.x - 1) {   // every CTA's stores are ordered before its arrival: publish the epoch
+      w.state->arrive = 0;
+      __threadfence_system();
+      for (int r = 0; r < w.nranks; ++r) st_release_sys_u64(&w.flags[r][w.rank], e);
+    }
+    // ---- phase 2: wait for every sender's epoch in the own window (bounded: a lost peer must not hang the GPU)
+    const unsigned long long t0 = global_timer_ns();
+    for (int r = 0; r < w.nranks; ++r) {
+      const unsigned long long* f = &w.flags[w.rank][r];
+      while (ld_acquire_sys_u64(f) < e) {
+        if (global_timer_ns() - t0 > 20000000000ull) { w.state->error = 1; break; }
+      }
+    }
+  }
+  __syncthreads();
+  if (sl == 0 && valid) {
+    const double* slot = w.data[w.rank] + half + idx;
+    double v = __ldcg(slot);
+    if (idx < max_from) {
+      for (int r = 1; r < w.nranks; ++r) v += __ldcg(slot + (size_t)r * PEER_CAP);
+    } else {
+      for (int r = 1; r < w.nranks; ++r) v = fmax(v, __ldcg(slot + (size_t)r * PEER_CAP));
+    }
+    C[i + (size_t)j * ldc] = v;
+    if (Ct) Ct[j + (size_t)i * ldc] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&w.state->depart, 1u);
+    if (t == gridDim.x - 1) {   // nobody reads the epoch any more: the call is complete
+      w.state->depart = 0;
+      w.state->epoch = e;
+    }
+  }
+}
+
+// reduction of the partials of one block: plain, or finished by the peer all-reduce when the engine
+// asked for it (g_fuse_allreduce) and the window exists
+static void launch_gram_reduce(cudaStream_t st, const double* partial, int ncta, int PB, int QB, int pb, int qb, int sym,
+                               double* C, int ldc, double* Ct) {
+  const int tot = pb * qb;
+  if (g_fuse_allreduce && g_peerwin.nranks > 1 && tot <= PEER_CAP)
+    gram_reduce_peer_kernel<<<(tot + 31) / 32, GRED_SL * 32, 0, st>>>(partial, ncta, PB, QB, pb, qb, sym, C, ldc, Ct, g_live,
+                                                                       g_peerwin, 1 << 30);
+  else
+    gram_reduce_kernel<<<(tot + 31) / 32, GRED_SL * 32, 0, st>>>(partial, ncta, PB, QB, pb, qb, sym, C, ldc, Ct, g_live);
+  ++g_launches;
 }
 
 // Build a balanced task schedule for a p x q block (tile counts ntp x ntq).
@@ -713,11 +841,9 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
           const size_t sm = (size_t)GR_STAGES * cols * kt * 8 + 2 * GR_STAGES * sizeof(uint64_t) + 1024;
           gram_tma_kernel<<<g, GR_THREADS, sm, st>>>(n, tmA, tmB, same, kt, sch, partial, PB, QB, g_live);
           ++g_launches;
-          const int tot = pb * qb;
           double* Cblk = C + p0 + (size_t)q0 * ldc;
           double* Cmir = (sym_lower && !diag_blk) ? C + q0 + (size_t)p0 * ldc : nullptr;
-          gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, g, PB, QB, pb, qb, diag_blk ? 1 : 0, Cblk, ldc, Cmir, g_live);
-          ++g_launches;
+          launch_gram_reduce(st, partial, g, PB, QB, pb, qb, diag_blk ? 1 : 0, Cblk, ldc, Cmir);
           launched = true;
         }
       }
@@ -733,13 +859,19 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
       else
         gram_kernel<false><<<grid, GR_THREADS, smem, st>>>(n, Ab, lda, pb, Bb, ldb, qb, same, KT, sched, partial, PB, QB, g_live);
       ++g_launches;
-      const int tot = pb * qb;
       double* Cblk = C + p0 + (size_t)q0 * ldc;
       double* Cmir = (sym_lower && !diag_blk) ? C + q0 + (size_t)p0 * ldc : nullptr;
-      gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, grid, PB, QB, pb, qb, diag_blk ? 1 : 0, Cblk,
-                                                            ldc, Cmir, g_live);
-      ++g_launches;
+      launch_gram_reduce(st, partial, grid, PB, QB, pb, qb, diag_blk ? 1 : 0, Cblk, ldc, Cmir);
     }
+  DLB_CUDA_CHECK(cudaGetLastError());
+}
+
+void peer_allreduce(cudaStream_t st, double* d, int count, int max_from) {
+  if (count <= 0 || g_peerwin.nranks <= 1) return;
+  // the buffer itself is the one "partial": p = count, q = 1
+  gram_reduce_peer_kernel<<<(count + 31) / 32, GRED_SL * 32, 0, st>>>(d, 1, count, 1, count, 1, 0, d, count, nullptr, g_live,
+                                                                     g_peerwin, max_from);
+  ++g_launches;
   DLB_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -1090,7 +1222,7 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
         if (lane == 0) mbar_arrive(&empty[s]);
         if (++s == BMW_STAGES) { s = 0; ph ^= 1; }
       };
-      if (tri == 1) {
+      if (tri == 1 && NQT <= 10) {
         // C upper triangular (the dtrmm of ortho_cd, p = q <= 8 NQT): at most NQT / 2 chunks, written out
         // with the chunk index as a compile-time constant so that the tiles below the diagonal are not
         // even issued.  A predicated-off DMMA still occupies its slot of the FP64 pipe (ncu on the
@@ -1135,10 +1267,23 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
               for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * SV + a_off + r * 8];
 #pragma unroll
               for (int cc = 0; cc < NQT; ++cc) b[cc] = sCk[cc * 8 * PS + k4 * 4];
+              if (NQT <= 10 || tri != 1) {
 #pragma unroll
-              for (int r = 0; r < 2; ++r)
+                for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int cc = 0; cc < NQT; ++cc) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
+                  for (int cc = 0; cc < NQT; ++cc) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
+              } else {
+                // 128-column triangular blocks (C5): predicated tiles.  Written out per chunk like the
+                // narrower widths, this instantiation makes ptxas demote the 64 accumulators to local
+                // memory (2.4 KB stack frame, ortho phase of C5 2x slower), so it keeps the loop.
+                const int kbase = kc * BM_KC + k4 * 4;
+#pragma unroll
+                for (int cc = 0; cc < NQT; ++cc)
+                  if (kbase < (cc + 1) * 8) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) dmma884(acc[r][cc][0], acc[r][cc][1], a[r], b[cc]);
+                  }
+              }
             }
           }
           stage_release();
@@ -1368,7 +1513,7 @@ void block_mul_gram(cudaStream_t st, int num_sms, int64_t n, const double* V, in
                                                                   upper_tri ? 1 : 0, partial, g_live);
     ++g_launches;
     const int tot = q * q;
-    gram_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(partial, (int)grid, QB, QB, q, q, 1, G, ldg, nullptr, g_live);
+    gram_reduce_kernel<<<(tot + 31) / 32, GRED_SL * 32, 0, st>>>(partial, (int)grid, QB, QB, q, q, 1, G, ldg, nullptr, g_live);
     ++g_launches;
     DLB_CUDA_CHECK(cudaGetLastError());
     return;

@@ -203,9 +203,43 @@ struct Engine {
     fail(DIAGLIB_B200_ECOMM, "NCCL %s failed: %s", what, nccl.GetErrorString ? nccl.GetErrorString(r) : "?");
     return false;
   }
+  // Peer window (kernels.h): k x k all-reduces run as ONE kernel of this library over NVLink peer
+  // stores instead of ncclAllReduce, and the reduction of a Gram kernel's per-CTA partials is fused
+  // into it.  Larger messages (Davidson's lda^2 blocks beyond 128 x 128) stay with NCCL.
+  void* peer_base = nullptr;                 // own window (flags + two parity halves of slots)
+  void* peer_mapped[PEER_MAX] = {};          // cudaIpcOpenMemHandle results (to close)
+  int64_t st_peer_calls = 0;
+  bool peer_ok() const { return g_peerwin.nranks > 1; }
+  void peer_teardown() {
+    if (!peer_base) return;
+    if (st) cudaStreamSynchronize(st);
+    for (int r = 0; r < PEER_MAX; ++r)
+      if (peer_mapped[r]) { cudaIpcCloseMemHandle(peer_mapped[r]); peer_mapped[r] = nullptr; }
+    if (g_peerwin.state) cudaFree(g_peerwin.state);
+    cudaFree(peer_base);
+    peer_base = nullptr;
+    g_peerwin = PeerWin();
+  }
+  void peer_setup();
   void allreduce(double* d, size_t count, ncclRedOp_t op = ncclSum) {
     if (nranks == 1 || count == 0) return;
+    if (peer_ok() && count <= (size_t)PEER_CAP && (op == ncclSum || op == ncclMax)) {
+      ++st_peer_calls;
+      peer_allreduce(st, d, (int)count, op == ncclSum ? (1 << 30) : 0);
+      return;
+    }
     nccl_ok(nccl.AllReduce(d, d, count, ncclDouble, op, comm, st), "AllReduce");
+  }
+  // sums of squares in d[0, m), maxima in d[m, 2m): one call through the window, two with NCCL
+  void allreduce_norms(double* d, int m) {
+    if (nranks == 1 || m == 0) return;
+    if (peer_ok() && 2 * m <= PEER_CAP) {
+      ++st_peer_calls;
+      peer_allreduce(st, d, 2 * m, m);
+      return;
+    }
+    allreduce(d, m, ncclSum);
+    allreduce(d + m, m, ncclMax);
   }
 
   void ensure_small(int m, int xrows) {
@@ -241,6 +275,21 @@ struct Engine {
     if (profile) h = ph_open(PH_KGRAM);
     gram_tn(st, num_sms, n, A, lda, p, B, ldb, q, C, ldc, sym, partial.as<double>());
     if (profile) ph_close(h);
+  }
+  // Gram product + all-reduce of the result over the ranks.  With the peer window the reduction of
+  // the per-CTA partials and the all-reduce are one kernel per <= 128 x 128 block (dense.cu).
+  void kgram_ar(int64_t n, const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, double* C, int ldc,
+                bool sym) {
+    const bool fuse = peer_ok();
+    g_fuse_allreduce = fuse;
+    kgram(n, A, lda, p, B, ldb, q, C, ldc, sym);
+    g_fuse_allreduce = false;
+    if (fuse) { ++st_peer_calls; return; }
+    const int* live = g_live;
+    g_live = nullptr;   // NCCL calls are not predicated (a dead step reduces a stale matrix nobody reads)
+    if (ldc == p) allreduce(C, (size_t)p * q);
+    else for (int j = 0; j < q; ++j) allreduce(C + (size_t)j * ldc, p);
+    g_live = live;
   }
   void kbmul(int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc, int q, double alpha,
              double beta, double* Y, int64_t ldy) {
@@ -281,8 +330,7 @@ struct Engine {
       }
       ++st_cd_passes;
       if (!have_metric) {
-        kgram(n, u, ldu, m, u, ldu, m, d_metric, m, true);       // 3256
-        allreduce(d_metric, (size_t)m * m);
+        kgram_ar(n, u, ldu, m, u, ldu, m, d_metric, m, true);       // 3256
       }
       have_metric = false;
       chol_inv(st, m, d_metric, m, d_T, d_cholwork, d_cholst);   // 3261-3316
@@ -329,9 +377,8 @@ struct Engine {
   void chain_cd_passes(int64_t n, int m, double* u, int64_t ldu, int phase, bool check_vsx, bool sweep_follows) {
     for (int p = 1; p <= SPEC_PASSES; ++p) {
       g_live = &d_octl->live[cell_pass(phase, p)];
-      kgram(n, u, ldu, m, u, ldu, m, d_metric, m, true);         // 3256
+      kgram_ar(n, u, ldu, m, u, ldu, m, d_metric, m, true);         // 3256
       g_live = nullptr;
-      allreduce(d_metric, (size_t)m * m);                        // (on a stale metric when the pass is not live: unused)
       CholLink lk;
       lk.ctl = d_octl;
       lk.self = cell_pass(phase, p);
@@ -382,12 +429,10 @@ struct Engine {
     for (int j = 0; j < m; ++j) {
       double* uj = u + (int64_t)j * ldu;
       for (int pass = 0; pass < 2 && j > 0; ++pass) {
-        kgram(n, u, ldu, j, uj, ldu, 1, c, j, false);
-        allreduce(c, j);
+        kgram_ar(n, u, ldu, j, uj, ldu, 1, c, j, false);
         kbmul(n, u, ldu, j, c, j, 1, -1.0, 1.0, uj, ldu);
       }
-      kgram(n, uj, ldu, 1, uj, ldu, 1, c, 1, false);
-      allreduce(c, 1);
+      kgram_ar(n, uj, ldu, 1, uj, ldu, 1, c, 1, false);
       double nrm2;
       read_back(&nrm2, c, sizeof(double));
       const double inv = 1.0 / std::sqrt(nrm2);
@@ -402,8 +447,7 @@ struct Engine {
   // is formed once (as in ortho_cd) and both blocks are multiplied by it.  The reference does
   // not look at dpotrf's status; a metric that is not positive definite is reported instead.
   void b_ortho(int64_t n, int m, double* u, int64_t ldu, double* bu, int64_t ldbu) {
-    kgram(n, u, ldu, m, bu, ldbu, m, d_metric, m, true);     // 3124 (lower triangle, what dpotrf('l') reads)
-    allreduce(d_metric, (size_t)m * m);
+    kgram_ar(n, u, ldu, m, bu, ldbu, m, d_metric, m, true);     // 3124 (lower triangle, what dpotrf('l') reads)
     chol_inv(st, m, d_metric, m, d_T, d_cholwork, d_cholst); // 3172
     CholStatus cs;
     read_back(&cs, d_cholst, sizeof cs);
@@ -443,8 +487,7 @@ struct Engine {
     while (!done) {
       ++it;
       ++st_sweeps;
-      kgram(n, gx, ldx, m, u, ldu, k, d_xu, m, false);  // 3543 / 3632
-      allreduce(d_xu, (size_t)m * k);
+      kgram_ar(n, gx, ldx, m, u, ldu, k, d_xu, m, false);  // 3543 / 3632
       bool ok;
       if (k <= 40 && g_use_fused_gram) {
         // 3544 fused with the first metric (3256) of the ortho_cd that follows
@@ -461,7 +504,7 @@ struct Engine {
       if (status) return;
       done = sweep_verdict(n, m, k, gx, ldx, u, ldu, ok, growth);
       if (status) return;
-      if (it > maxit && !done) {                                                             // 3568
+      if (it > maxit) {   // 3568: unconditional in the reference, also when sweep maxit + 1 did converge
         fail(DIAGLIB_B200_EORTHO, " catastrophic failure of ortho_vs_x");
         return;
       }
@@ -473,8 +516,7 @@ struct Engine {
     double xu_norm;
     if (!ok) {                                                                               // 3549,3558-3560
       ortho_qr(n, k, u, ldu);
-      kgram(n, gx, ldx, m, u, ldu, k, d_xu, m, false);
-      allreduce(d_xu, (size_t)m * k);
+      kgram_ar(n, gx, ldx, m, u, ldu, k, d_xu, m, false);
       std::vector<double> h((size_t)m * k);
       read_back(h.data(), d_xu, h.size() * sizeof(double));
       double s = 0.0;
@@ -503,9 +545,8 @@ struct Engine {
     for (int sw = 1; sw <= SPEC_SWEEPS; ++sw) {
       const int* head = &d_octl->live[cell_head(sw)];
       g_live = head;
-      kgram(n, gx, ldx, m, u, ldu, k, d_xu, m, false);           // 3543 / 3632
+      kgram_ar(n, gx, ldx, m, u, ldu, k, d_xu, m, false);           // 3543 / 3632
       g_live = nullptr;
-      allreduce(d_xu, (size_t)m * k);
       g_live = head;
       project_out(n, m, k, x, ldx, u, ldu);                      // 3544
       g_live = nullptr;
@@ -571,6 +612,7 @@ struct Engine {
     st_cd_passes = st_sweeps = st_qr = st_shifts = 0;
     st_syncs = 0;
     st_eig_calls = st_eig_sweeps = st_eig_fallbacks = 0;
+    st_peer_calls = 0;
     st_launch0 = g_launches;
     for (double& t : t_acc) t = 0;
   }
@@ -588,6 +630,74 @@ struct Engine {
 };
 
 Engine g;
+
+// Peer window set-up (collective, called by comm_init after the communicator exists): allocate the
+// window, exchange cudaIpc handles with an NCCL all-gather, map every peer's window, and agree on the
+// outcome (any rank that cannot map a peer makes all ranks fall back to ncclAllReduce).
+void Engine::peer_setup() {
+  g_peerwin = PeerWin();
+  const char* ev = std::getenv("DIAGLIB_B200_PEER_REDUCE");
+  int want = !(ev && ev[0] == '0') && nranks >= 2 && nranks <= PEER_MAX;
+  const size_t flag_bytes = 256;   // PEER_MAX u64 flags, padded
+  const size_t data_bytes = (size_t)2 * nranks * PEER_CAP * sizeof(double);
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof mine);
+  PeerState* state = nullptr;
+  if (want) {
+    if (cudaMalloc(&peer_base, flag_bytes + data_bytes) != cudaSuccess || cudaMalloc(&state, sizeof(PeerState)) != cudaSuccess ||
+        cudaMemset(peer_base, 0, flag_bytes + data_bytes) != cudaSuccess || cudaMemset(state, 0, sizeof(PeerState)) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine, peer_base) != cudaSuccess) {
+      cudaGetLastError();
+      want = 0;
+    }
+  }
+  // handles of all ranks (the all-gather runs even when this rank gave up, so that nobody hangs)
+  DevBuf hb;
+  const size_t hsz = sizeof(cudaIpcMemHandle_t);
+  std::vector<char> all((size_t)nranks * hsz, 0);
+  if (!hb.ensure((size_t)nranks * hsz + 64)) { fail(DIAGLIB_B200_EALLOC, "memory allocation failed. (peer handles)"); return; }
+  char* d_h = hb.as<char>();
+  DLB_CUDA_CHECK(cudaMemcpyAsync(d_h + (size_t)rank * hsz, &mine, hsz, cudaMemcpyHostToDevice, st));
+  nccl_ok(nccl.AllGather(d_h + (size_t)rank * hsz, d_h, hsz, ncclChar, comm, st), "AllGather (peer handles)");
+  DLB_CUDA_CHECK(cudaMemcpyAsync(all.data(), d_h, all.size(), cudaMemcpyDeviceToHost, st));
+  DLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  PeerWin w;
+  w.nranks = nranks;
+  w.rank = rank;
+  w.state = state;
+  for (int r = 0; r < nranks && want; ++r) {
+    void* base = nullptr;
+    if (r == rank) {
+      base = peer_base;
+    } else {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, all.data() + (size_t)r * hsz, hsz);
+      if (cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        want = 0;
+        break;
+      }
+      peer_mapped[r] = base;
+    }
+    w.flags[r] = reinterpret_cast<unsigned long long*>(base);
+    w.data[r] = reinterpret_cast<double*>(static_cast<char*>(base) + flag_bytes);
+  }
+  // agreement: minimum of `want` over the ranks (also the barrier behind the memsets above)
+  double* d_w = reinterpret_cast<double*>(d_h);
+  const double mine_ok = want ? 1.0 : 0.0;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(d_w, &mine_ok, sizeof(double), cudaMemcpyHostToDevice, st));
+  nccl_ok(nccl.AllReduce(d_w, d_w, 1, ncclDouble, ncclMin, comm, st), "AllReduce (peer agreement)");
+  double all_ok = 0.0;
+  DLB_CUDA_CHECK(cudaMemcpyAsync(&all_ok, d_w, sizeof(double), cudaMemcpyDeviceToHost, st));
+  DLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  hb.release();
+  if (all_ok == 1.0 && status == 0) {
+    g_peerwin = w;
+  } else {
+    g_peerwin.state = state;   // so that peer_teardown frees it
+    peer_teardown();
+  }
+}
 
 bool is_device_ptr(const void* p) {
   cudaPointerAttributes at;
@@ -617,8 +727,7 @@ __global__ void set_diag_kernel(int cnt, double* a, int lda, const double* d) {
 // ---- check_guess, diaglib.f90:3734-3786 ------------------------------------------------
 void Engine::check_guess(int64_t n, int m, double* evec, int64_t ld) {
   double growth;
-  kgram(n, evec, ld, m, evec, ld, m, d_metric, m, true);  // 3762 (and 3749)
-  allreduce(d_metric, (size_t)m * m);
+  kgram_ar(n, evec, ld, m, evec, ld, m, d_metric, m, true);  // 3762 (and 3749)
   std::vector<double> ov((size_t)m * m);
   read_back(ov.data(), d_metric, ov.size() * sizeof(double));
   double tr = 0.0;
@@ -755,8 +864,7 @@ void Engine::lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, in
   }
   if (shift != 0.0) block_axpy(st, nn, n_max, shift, space, nn, aspace, nn);           // 312
   h = ph_open(PH_GRAM);
-  kgram(nn, space, nn, n_max, aspace, nn, n_max, a_red, n_max, true);  // 313
-  allreduce(a_red, (size_t)n_max * n_max);
+  kgram_ar(nn, space, nn, n_max, aspace, nn, n_max, a_red, n_max, true);  // 313
   ph_close(h);
   h = ph_open(PH_DIAG);
   sym_eig(st, n_max, a_red, n_max, false, e_red, eig_work, d_eigst);                   // 315
@@ -809,8 +917,7 @@ void Engine::lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, in
     int len_u = n_max + 2 * n_act;
     if (it == 1) len_u = 2 * n_max;
     h = ph_open(PH_GRAM);
-    kgram(nn, space, nn, len_u, aspace, nn, len_u, a_red, len_u, true);  // 403
-    allreduce(a_red, (size_t)len_u * len_u);
+    kgram_ar(nn, space, nn, len_u, aspace, nn, len_u, a_red, len_u, true);  // 403
     ph_close(h);
     h = ph_open(PH_DIAG);
     sym_eig(st, len_u, a_red, len_u, false, e_red, eig_work, d_eigst);                 // 406
@@ -829,8 +936,7 @@ void Engine::lobpcg(bool verbose, bool gen_eig, int n, int n_targ, int n_max, in
     residual_norms(st, num_sms, nn, n_max, ax_new, nn, gen_eig ? bx_new : x_new, nn, e_red, d_active, r, nn, d_norms,
                    resid_scratch.as<double>());                                        // 428-442
     ph_close(h);
-    allreduce(d_norms, n_max, ncclSum);
-    allreduce(d_norms + n_max, n_max, ncclMax);
+    allreduce_norms(d_norms, n_max);
     {
       // one read-back for eigenvalues, norms and the eigensolver status
       DLB_CUDA_CHECK(cudaMemcpyAsync(h_norms.data(), d_norms, 2 * n_max * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1037,9 +1143,13 @@ void Engine::davidson(bool verbose, bool gen, int n, int n_targ, int n_max, int 
     if (status) break;   // a callback refused its arguments
     h = ph_open(PH_GRAM);
     double* a_blk = a_red + (size_t)lda * (c1 - 1);
-    kgram(nn, space, nn, ldu, COL(aspace, c1), nn, n_act, a_blk, lda, false);  // 1691
-    // rows > ldu of these columns are zero on every rank, so the block can be reduced as one range
-    allreduce(a_blk, (size_t)(n_act - 1) * lda + ldu);
+    if (peer_ok()) {
+      kgram_ar(nn, space, nn, ldu, COL(aspace, c1), nn, n_act, a_blk, lda, false);  // 1691
+    } else {
+      kgram(nn, space, nn, ldu, COL(aspace, c1), nn, n_act, a_blk, lda, false);  // 1691
+      // rows > ldu of these columns are zero on every rank, so the block can be reduced as one range
+      allreduce(a_blk, (size_t)(n_act - 1) * lda + ldu);
+    }
     ph_close(h);
     if (restart) {                                                                      // 1696-1702
       if (n_rst > 0) { set_diag_kernel<<<(n_rst + 127) / 128, 128, 0, st>>>(n_rst, a_red, lda, e_red); ++g_launches; }
@@ -1062,8 +1172,7 @@ void Engine::davidson(bool verbose, bool gen, int n, int n_targ, int n_max, int 
     residual_norms(st, num_sms, nn, n_max, r, nn, gen ? bevec : d_evec, nn, e_red, d_active, r, nn, d_norms,
                    resid_scratch.as<double>());                                         // 1729-1731
     ph_close(h);
-    allreduce(d_norms, n_max, ncclSum);
-    allreduce(d_norms + n_max, n_max, ncclMax);
+    allreduce_norms(d_norms, n_max);
     {
       DLB_CUDA_CHECK(cudaMemcpyAsync(h_norms.data(), d_norms, 2 * n_max * sizeof(double), cudaMemcpyDeviceToHost, st));
       EigStatus es;
@@ -1264,8 +1373,7 @@ void Engine::caslr_eff(bool verbose, int n, int n2, int n_targ, int n_max, int m
     { int32_t m32 = n_act; smdmul(&n32, &m32, COL(vm, i_beg), COL(bvp, i_beg)); }         // 1285
     ph_close(h);
     h = ph_open(PH_GRAM);
-    kgram(nn, vm, nn, ldu, bvm, nn, ldu, smat, ldu, false);                              // 1293
-    allreduce(smat, (size_t)ldu * ldu);
+    kgram_ar(nn, vm, nn, ldu, bvm, nn, ldu, smat, ldu, false);                              // 1293
     ph_close(h);
     h = ph_open(PH_DIAG);
     small_ata(st, ldu, smat, ldu, s_copy, ldu);                                          // 1303
@@ -1289,10 +1397,8 @@ void Engine::caslr_eff(bool verbose, int n, int n2, int n_targ, int n_max, int m
     residual_norms(st, num_sms, nn, n_max, rm, nn, bm, nn, d_eigv, d_active, rm, nn, d_norms_m,
                    resid_scratch.as<double>());                                          // 1348
     ph_close(h);
-    allreduce(d_norms_p, n_max, ncclSum);
-    allreduce(d_norms_p + n_max, n_max, ncclMax);
-    allreduce(d_norms_m, n_max, ncclSum);
-    allreduce(d_norms_m + n_max, n_max, ncclMax);
+    allreduce_norms(d_norms_p, n_max);
+    allreduce_norms(d_norms_m, n_max);
     {
       DLB_CUDA_CHECK(cudaMemcpyAsync(h_np.data(), d_norms_p, 2 * n_max * sizeof(double), cudaMemcpyDeviceToHost, st));
       DLB_CUDA_CHECK(cudaMemcpyAsync(h_nm.data(), d_norms_m, 2 * n_max * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1605,6 +1711,7 @@ int32_t diaglib_b200_init(int32_t device) {
 void diaglib_b200_finalize(void) {
   if (!g.inited) return;
   cudaStreamSynchronize(g.st);
+  g.peer_teardown();
   if (g.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(g.comm);
   g.comm = nullptr;
   g.nranks = 1;
@@ -1980,6 +2087,7 @@ int32_t diaglib_b200_comm_init(int32_t rank, int32_t nranks, const void* uid) {
   if (!g.nccl.load()) { g.fail(DIAGLIB_B200_ECOMM, "cannot load libnccl.so.2"); return DIAGLIB_B200_ECOMM; }
   ncclUniqueId id;
   std::memcpy(&id, uid, sizeof id);
+  g.peer_teardown();
   if (g.comm_halo) { g.nccl.CommDestroy(g.comm_halo); g.comm_halo = nullptr; }
   if (g.comm) { g.nccl.CommDestroy(g.comm); g.comm = nullptr; }   // a second comm_init replaces the communicator
   if (g.nccl.CommInitRank(&g.comm, nranks, id, rank) != ncclSuccess) {
@@ -1988,6 +2096,7 @@ int32_t diaglib_b200_comm_init(int32_t rank, int32_t nranks, const void* uid) {
   }
   g.rank = rank;
   g.nranks = nranks;
+  g.peer_setup();   // k x k all-reduces through mapped peer memory (falls back to NCCL when it cannot be mapped)
   // second communicator + stream for the SpMM halo exchange (overlaps the interior rows);
   // DIAGLIB_B200_HALO_OVERLAP=0 keeps the exchange on the main stream
   const char* ov = std::getenv("DIAGLIB_B200_HALO_OVERLAP");
@@ -2005,6 +2114,16 @@ int32_t diaglib_b200_comm_init(int32_t rank, int32_t nranks, const void* uid) {
 }
 int32_t diaglib_b200_comm_rank(void) { return g.rank; }
 int32_t diaglib_b200_comm_size(void) { return g.nranks; }
+void diaglib_b200_peer_info(int64_t* out4) {
+  out4[0] = g_peerwin.nranks;
+  out4[1] = g.st_peer_calls;
+  out4[2] = out4[3] = 0;
+  if (g_peerwin.nranks > 1 && g_peerwin.state) {
+    PeerState ps;
+    cudaStreamSynchronize(g.st);
+    if (cudaMemcpy(&ps, g_peerwin.state, sizeof ps, cudaMemcpyDeviceToHost) == cudaSuccess) { out4[2] = ps.error; out4[3] = (int64_t)ps.epoch; }
+  }
+}
 
 int32_t diaglib_b200_history_len(void) { return (int32_t)g.hist.it.size(); }
 void diaglib_b200_history_get(int32_t* it, int32_t* n_act, double* eig, double* rms, double* mx, int32_t* done) {
@@ -2128,8 +2247,7 @@ int32_t diaglib_b200_k_residual(int64_t n, int32_t m, const double* ax, int64_t 
   DLB_CUDA_CHECK(cudaMemcpyAsync(d_theta, theta_host, m * sizeof(double), cudaMemcpyHostToDevice, g.st));
   DLB_CUDA_CHECK(cudaMemcpyAsync(d_act, active_host, m * sizeof(int), cudaMemcpyHostToDevice, g.st));
   residual_norms(g.st, g.num_sms, n, m, ax, ldax, x, ldx, d_theta, d_act, r, ldr, d_norms, g.resid_scratch.as<double>());
-  g.allreduce(d_norms, m, ncclSum);
-  g.allreduce(d_norms + m, m, ncclMax);
+  g.allreduce_norms(d_norms, m);
   DLB_CUDA_CHECK(cudaMemcpyAsync(norms_host, d_norms, 2 * m * sizeof(double), cudaMemcpyDeviceToHost, g.st));
   g.sync();
   tmp.release();
@@ -2258,8 +2376,7 @@ int32_t diaglib_b200_k_true_residual(int32_t n_loc, int32_t m, const double* x_d
   g.csr_matvec(m, x_dev, ax.as<double>());
   residual_norms(g.st, g.num_sms, n_loc, m, ax.as<double>(), n_loc, x_dev, n_loc, d_theta, d_act, ax.as<double>(), n_loc, d_norms,
                  g.resid_scratch.as<double>());
-  g.allreduce(d_norms, m, ncclSum);
-  g.allreduce(d_norms + m, m, ncclMax);
+  g.allreduce_norms(d_norms, m);
   DLB_CUDA_CHECK(cudaMemcpyAsync(norms_host, d_norms, 2 * m * sizeof(double), cudaMemcpyDeviceToHost, g.st));
   g.sync();
   ax.release();

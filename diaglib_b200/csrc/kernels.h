@@ -29,6 +29,32 @@ extern int g_spmm_short;
 extern int g_spmm_chunk;
 extern int g_spmm_chunk_tiled;
 
+// ---- peer window: reduction of the per-CTA partials fused with the all-reduce over NVLink ------
+// Every rank owns a window of device memory that all ranks of the node map (cudaIpc): two parity
+// halves of nranks slots of PEER_CAP doubles, plus one arrival flag per sender.  One kernel reduces
+// the local partials, stores the result into its slot of EVERY rank's window (peer stores through
+// NVSwitch), publishes an epoch number to every rank's flags, waits for the nranks flags of its own
+// window and adds the slots in rank order - so the k x k result is bit-identical on all ranks,
+// with one launch instead of gram_reduce + ncclAllReduce.  Set up by diaglib_b200_comm_init.
+constexpr int PEER_MAX = 8;
+constexpr int PEER_CAP = 16384;   // doubles per slot: a 128 x 128 block
+struct PeerState {
+  unsigned int arrive, depart;     // CTAs past the store phase / past the sum phase of the running call
+  unsigned long long epoch;        // number of completed calls (same on every rank: the calls are collective)
+  unsigned int error, pad;         // 1: a peer's flag did not arrive within the time-out
+};
+struct PeerWin {
+  int nranks = 0, rank = 0;                       // nranks == 0: not available (single rank, or set-up failed)
+  double* data[PEER_MAX] = {};                    // data[r]: window of rank r as mapped into this process
+  unsigned long long* flags[PEER_MAX] = {};       // flags[r][s]: last epoch sender s has published to rank r
+  PeerState* state = nullptr;                     // local
+};
+extern PeerWin g_peerwin;
+extern bool g_fuse_allreduce;   // gram_tn: finish every block with the peer all-reduce (set by the engine around the call)
+// in-place all-reduce of d[0, count) (count <= PEER_CAP) through the peer window: sum of the elements
+// below max_from, maximum of the others.  Collective over the ranks, predicated by g_live like gram_tn.
+void peer_allreduce(cudaStream_t st, double* d, int count, int max_from);
+
 // ---- dense.cu -------------------------------------------------------------------------
 // C(p x q, ldc) = A(n x p, lda)^T * B(n x q, ldb).  Replaces dgemm('t','n',p,q,n,...) at
 // diaglib.f90:313,403,1691,3256,3543,3762.  If sym_lower only tiles on/below the diagonal

@@ -106,7 +106,11 @@ __device__ __forceinline__ int32_t ld_nc_s32(const int32_t* p) {
 // scheme were measured and removed again (profiles/spmm_variants_r02.json, n = 2^24, m = 37, tiled
 // order): a second inlined block 4.52 ms, the same at 3 CTAs per SM 2.69 ms, a not-inlined tail
 // function 2.85 ms, against 2.57 ms with the generic tail - the extra code changes ptxas' schedule
-// of the main loop (fewer gathers in flight under the 64-register cap).
+// of the main loop (fewer gathers in flight under the 64-register cap).  Two uniform-loop forms fared
+// no better (profiles/spmm_tail_variants_r02.json): a last pass shifted back to columns [m - 8, m)
+// 2.84 ms, a last pass with the column index clamped to m - 1 (surplus gathers are L1 hits) 3.53 ms -
+// and both already lose at m = 32, where no remainder exists: any change to the pass loop costs
+// loads in flight.
 template <int JB, int KMAX>
 __global__ void __launch_bounds__(256, 4)
 spmm_csr_short_kernel(int64_t n, int64_t n_halo, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,

@@ -175,6 +175,13 @@ int32_t diaglib_b200_comm_unique_id(void* out_128_bytes);
 int32_t diaglib_b200_comm_init(int32_t rank, int32_t nranks, const void* unique_id_128_bytes);
 int32_t diaglib_b200_comm_rank(void);
 int32_t diaglib_b200_comm_size(void);
+/* How the k x k all-reduces of the drivers (diaglib.f90 has none: they replace the serial dgemm('t','n')
+ * results at 403, 1691, 3256, 3543 on a row-partitioned block) travel:
+ *   out4[0] ranks sharing the peer window (0: every all-reduce is an ncclAllReduce; the window needs
+ *           cudaIpc between the ranks of one node, DIAGLIB_B200_PEER_REDUCE=0 disables it)
+ *   out4[1] all-reduces of the last driver call that went through the window
+ *   out4[2] 1 when a peer's contribution timed out (results invalid)   out4[3] completed window calls */
+void diaglib_b200_peer_info(int64_t* out4);
 
 /* ---- introspection used by the tests and bench.py ------------------------------------- */
 

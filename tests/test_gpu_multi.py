@@ -255,3 +255,72 @@ def test_two_rank_widened_drivers(oracle, case):
         assert np.abs(eig[:n_targ] - ro["eig"][:n_targ]).max() / np.abs(ro["eig"][:n_targ]).max() < 1e-10
         assert abs(its - len(ro["it"])) <= 1
         assert np.array_equal(eig, res[0][3])
+
+
+def _peer_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    import diaglib_b200 as D
+    from diaglib_b200 import dist as DD, partition
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        D.init(rank)
+        n, n_targ = 1 << 14, 8
+        n_max = P.n_eig_rule(n_targ)
+        r0, r1 = partition.row_range(n, rank, world)
+        out = []
+        for mode in ("1", "0"):   # peer window, then ncclAllReduce (a second comm_init replaces the communicator)
+            os.environ["DIAGLIB_B200_PEER_REDUCE"] = mode
+            DD.init_comm(dist)
+            DD.install_partitioned(lambda a, b: P.toy_sparse(n, a, b), n, rank, world, dist)
+            info0 = D.peer_info()
+            for drv in ("lobpcg", "davidson"):
+                ev = np.asfortranarray(P.guess(n, n_max, r0, r1))
+                eig = np.zeros(n_max)
+                if drv == "lobpcg":
+                    ok = D.lobpcg_driver(False, False, r1 - r0, n_targ, n_max, 300, 1e-8, 0.0, None, None, None, eig, ev)
+                else:
+                    ok = D.davidson_driver(False, r1 - r0, n_targ, n_max, 300, 1e-8, 12, 0.0, None, None, eig, ev)
+                h = D.last_history(n_max)
+                out.append(dict(mode=mode, drv=drv, ok=bool(ok), eig=eig.copy(), hist_eig=np.array(h["eig"]), its=len(h["it"]),
+                                info=D.peer_info(), window=info0["window_ranks"]))
+        q.put((rank, out))
+    finally:
+        os.environ.pop("DIAGLIB_B200_PEER_REDUCE", None)
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_two_rank_peer_window_matches_nccl():
+    """The k x k all-reduces through the mapped peer windows (one kernel: reduction of the Gram kernel's
+    partials + stores into every rank's window + sum in rank order) against the same solves with
+    ncclAllReduce: on two ranks a + b is the same number in either order, so the whole iteration
+    history must agree bit for bit, for both drivers; the window must really have been used."""
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out in res:
+        by = {(o["mode"], o["drv"]): o for o in out}
+        if by[("1", "lobpcg")]["window"] == 0:
+            pytest.skip("cudaIpc mapping of the peer windows is not available on this box: NCCL path only")
+        for drv in ("lobpcg", "davidson"):
+            a, b = by[("1", drv)], by[("0", drv)]
+            assert a["ok"] and b["ok"]
+            assert a["window"] == 2 and a["info"]["calls"] > 0 and a["info"]["error"] == 0
+            assert b["window"] == 0 and b["info"]["calls"] == 0
+            assert a["its"] == b["its"]
+            assert np.array_equal(a["hist_eig"], b["hist_eig"])
+            assert np.array_equal(a["eig"], res[0][1][out.index(a)]["eig"])   # bit-identical across the ranks
