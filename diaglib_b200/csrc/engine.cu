@@ -2392,6 +2392,7 @@ int32_t diaglib_b200_k_set_tuning(const char* name, int32_t value) {
   else if (nm == "spmm_chunk") slot = &g_spmm_chunk;
   else if (nm == "eig_block") slot = &g_eig_block;
   else if (nm == "eig_mode") slot = &g_eig_mode;
+  if (nm == "chol_blocked") { set_chol_blocked(value); return 0; }
   if (!slot) return -1;
   const int prev = *slot;
   *slot = value;

@@ -20,6 +20,7 @@ extern int g_eig_mode;
 extern int g_coeffs_threads;
 extern int g_coeffs_smem;
 extern int g_eig_block;
+void set_chol_blocked(int on);   // 1 (default): blocked factor-and-invert inside chol_inv / get_coeffs; 0: column by column
 // Predicate of the dense kernels (gram_tn, block_mul, block_trmm_inplace, block_mul_gram): while it
 // points to a device int, every kernel these wrappers launch returns at once when that int is 0.
 // The engine sets it around the steps of a speculative ortho_cd / ortho_vs_x chain, whose control

@@ -21,6 +21,7 @@ namespace {
 constexpr int SM_THREADS = 1024;
 constexpr double EPS = DBL_EPSILON;       // epsilon(one)
 constexpr double TOL_ORTHO = 2.0 * EPS;   // diaglib.f90:151
+__device__ int g_chol_blocked_dev = 1;   // 0: the unblocked factor-and-invert (tuning switch chol_blocked)
 constexpr size_t CHOL_SMEM_MAX = 200 * 1024;   // factors of chol_inv stay in shared memory up to m = 112
 
 // 1/sqrt(x) for x inside the float range: FP32 hardware seed + 3 Newton steps in FP64
@@ -167,6 +168,136 @@ __device__ int cta_potrf_inv_smem(int m, double* L, double* X, double* buf) {
   return 0;
 }
 
+// Blocked form of the same factor-and-invert step: 8-column blocks.  The diagonal block (8 x 8) is
+// factored AND inverted by one warp in registers (row r in lane r, column index compile-time, the
+// pivot row travels by shuffles: no barrier inside the block); the panel below it is a product with
+// that inverse (rows independent), the trailing update a rank-8 update, and L^-1 is assembled block
+// diagonal by block diagonal from the small inverses (X_IJ = -D_I^-1 sum_K L_IK X_KJ).  3 CTA
+// barriers per 8 columns instead of 2 per column: the unblocked form spends 0.9 us per column
+// (34 us at m = 37, and ortho_cd needs it ~10 times per iteration, get_coeffs 6 more).
+// L, X: m x m in SHARED memory (ld m); the strict upper triangle of L is used as scratch.
+constexpr int CHB = 8;
+__device__ int cta_potrf_inv_blocked(int m, double* L, double* X) {
+  __shared__ int s_info;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  int rs_log = 5;
+  while ((1 << rs_log) < m) ++rs_log;
+  const int RS = 1 << rs_log, CG = nt >> rs_log;   // nt >= RS is guaranteed by the callers
+  const int row = tid & (RS - 1), kq = tid >> rs_log;
+  for (int e = tid; e < m * m; e += nt) X[e] = 0.0;
+  if (tid == 0) s_info = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < m; j0 += CHB) {
+    const int nb = min(CHB, m - j0);
+    if (warp == 0) {
+      // lanes 8..31 mirror lanes 0..7 (same values), so every shuffle source is a valid lane
+      const int r = lane & 7;
+      double d[CHB], x[CHB];
+#pragma unroll
+      for (int c = 0; c < CHB; ++c) {
+        d[c] = (r < nb && c <= r) ? L[(j0 + r) + (size_t)(j0 + c) * m] : (r == c ? 1.0 : 0.0);   // padding rows: identity
+        x[c] = (r == c) ? 1.0 : 0.0;
+      }
+      int info = 0;
+#pragma unroll
+      for (int c = 0; c < CHB; ++c) {
+        const double piv = __shfl_sync(0xffffffffu, d[c], c);
+        if (!(piv > 0.0) && info == 0) info = j0 + c + 1;   // uniform; also catches NaN like dpotrf's disnan test
+        const double rs = rsqrt(piv);
+        // column c of the factor: d[c] is 0 above the diagonal and the pivot itself on it (piv * rs = sqrt(piv))
+        const double lrc = d[c] * rs;
+        d[c] = lrc;
+        // [L | I] -> [I | L^-1]: row c of the inverse is scaled by 1 / l_cc, rows below take -l_rc times it.
+        // One formula for all rows instead of selects (the block is a single warp's instruction stream):
+        // x_new = x f - g xc with (f, g) = (0, -1) on row c, (1, l_rc) below it and (1, 0) above it
+        const double f = (r == c) ? 0.0 : 1.0, g = (r == c) ? -1.0 : lrc;
+#pragma unroll
+        for (int cc = 0; cc <= c; ++cc) {
+          const double xc = __shfl_sync(0xffffffffu, x[cc] * rs, c);
+          x[cc] = fma(-g, xc, x[cc] * f);
+        }
+        // trailing columns of the block: rows r < c2 stay 0 because l2 is masked to 0 for them
+#pragma unroll
+        for (int c2 = c + 1; c2 < CHB; ++c2) {
+          const double l2 = __shfl_sync(0xffffffffu, lrc, c2);
+          d[c2] = fma(-lrc, (r >= c2) ? l2 : 0.0, d[c2]);
+        }
+      }
+      if (info != 0) {
+        if (lane == 0) s_info = info;
+      } else if (lane < nb) {
+#pragma unroll
+        for (int c = 0; c < CHB; ++c)
+          if (c <= r) {
+            L[(j0 + r) + (size_t)(j0 + c) * m] = d[c];
+            X[(j0 + r) + (size_t)(j0 + c) * m] = x[c];
+          }
+      }
+    }
+    __syncthreads();
+    if (s_info != 0) return s_info;
+    if (j0 + nb >= m) break;
+    // panel below the block: L(i, j0 + c) = sum_{c' <= c} A(i, j0 + c') D^-1(c, c'), one thread per row
+    for (int i = j0 + nb + tid; i < m; i += nt) {
+      double a[CHB];
+#pragma unroll
+      for (int c = 0; c < CHB; ++c) a[c] = c < nb ? L[i + (size_t)(j0 + c) * m] : 0.0;
+#pragma unroll
+      for (int c = 0; c < CHB; ++c) {
+        if (c < nb) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int c1 = 0; c1 <= c; ++c1) sacc = fma(a[c1], X[(j0 + c) + (size_t)(j0 + c1) * m], sacc);
+          L[i + (size_t)(j0 + c) * m] = sacc;
+        }
+      }
+    }
+    __syncthreads();
+    // trailing update: L(i, k) -= sum_c L(i, j0 + c) L(k, j0 + c), k >= j0 + nb, i >= k
+    if (row >= j0 + nb && row < m && kq < CG) {
+      double li[CHB];
+#pragma unroll
+      for (int c = 0; c < CHB; ++c) li[c] = c < nb ? L[row + (size_t)(j0 + c) * m] : 0.0;
+      for (int k = j0 + nb + kq; k <= row; k += CG) {
+        double sacc = L[row + (size_t)k * m];
+#pragma unroll
+        for (int c = 0; c < CHB; ++c)
+          if (c < nb) sacc = fma(-li[c], L[k + (size_t)(j0 + c) * m], sacc);
+        L[row + (size_t)k * m] = sacc;
+      }
+    }
+    __syncthreads();
+  }
+  // L^-1 by block diagonals: X_IJ = -D_I^-1 S_IJ, S_IJ = sum_{K = J}^{I - 1} L_IK X_KJ  (I = J + dist).
+  // S_IJ is parked in the transposed (strictly upper, unused) position of L.
+  const int nblk = (m + CHB - 1) / CHB;
+  for (int dist = 1; dist < nblk; ++dist) {
+    const int nel = (nblk - dist) * CHB * CHB;
+    for (int e = tid; e < nel; e += nt) {
+      const int J = e >> 6, r = (e >> 3) & 7, c = e & 7;
+      const int i = (J + dist) * CHB + r, cj = J * CHB + c;
+      if (i < m) {   // cj < m follows
+        double sacc = 0.0;
+        const int t1 = (J + dist) * CHB;
+        for (int t = cj; t < t1; ++t) sacc = fma(L[i + (size_t)t * m], X[t + (size_t)cj * m], sacc);   // X(t, cj) = 0 for t < cj
+        L[cj + (size_t)i * m] = sacc;
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < nel; e += nt) {
+      const int J = e >> 6, r = (e >> 3) & 7, c = e & 7;
+      const int i0 = (J + dist) * CHB, i = i0 + r, cj = J * CHB + c;
+      if (i < m) {
+        double sacc = 0.0;
+        for (int t = 0; t <= r; ++t) sacc = fma(X[i + (size_t)(i0 + t) * m], L[cj + (size_t)(i0 + t) * m], sacc);
+        X[i + (size_t)cj * m] = -sacc;
+      }
+    }
+    __syncthreads();
+  }
+  return 0;
+}
+
 // norm_est of a lower triangular matrix in shared memory without index divisions
 __device__ double cta_norm_est_lower(int m, const double* a, double* s_red) {
   double dmax = 0.0, od = 0.0;
@@ -195,7 +326,7 @@ __device__ void cta_chol_inv_smem(int m, const double* G, int ldg, double* L, do
       if (i == j) tr += v;
     }
   const double unorm = sqrt(fmax(cta_sum(tr, s_red), 0.0));
-  int info = cta_potrf_inv_smem(m, L, Li, buf);
+  int info = g_chol_blocked_dev ? cta_potrf_inv_blocked(m, L, Li) : cta_potrf_inv_smem(m, L, Li, buf);
   const int info_first = info;
   int n_shifts = 0, hard_fail = 0;
   double shift = 0.0, alpha = 100.0;
@@ -207,7 +338,7 @@ __device__ void cta_chol_inv_smem(int m, const double* G, int ldg, double* L, do
     for (int j = warp; j < m; j += nw)
       for (int i = lane; i < m; i += 32) L[i + (size_t)j * m] = G[i + (size_t)j * ldg] + (i == j ? shift : 0.0);
     __syncthreads();
-    info = cta_potrf_inv_smem(m, L, Li, buf);
+    info = g_chol_blocked_dev ? cta_potrf_inv_blocked(m, L, Li) : cta_potrf_inv_smem(m, L, Li, buf);
     alpha *= 10.0;
   }
   double l_norm = 0.0, linv_norm = 0.0;
@@ -937,15 +1068,28 @@ sym_eig_osj_kernel(int k, int b, int nblk, double* a, int lda, int upper, double
 // get_coeffs (diaglib.f90:3686-3732) in one CTA: u_p = u_x(:,active) - e_i, then
 // ortho_vs_x(len_u, n_max, n_act, u_x, u_p) (3481-3574) with ortho_cd (3185-3341) inside.
 // ---------------------------------------------------------------------------------------
+// dot product with four independent accumulators: a single FMA chain over ~111 rows is bound by the
+// dependent-issue latency of the FP64 pipe (ncu source view: these loops were a third of get_coeffs)
+__device__ __forceinline__ double dot4(int n, const double* __restrict__ a, const double* __restrict__ b) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int r = 0;
+  for (; r + 4 <= n; r += 4) {
+    s0 = fma(a[r], b[r], s0);
+    s1 = fma(a[r + 1], b[r + 1], s1);
+    s2 = fma(a[r + 2], b[r + 2], s2);
+    s3 = fma(a[r + 3], b[r + 3], s3);
+  }
+  for (; r < n; ++r) s0 = fma(a[r], b[r], s0);
+  return (s0 + s1) + (s2 + s3);
+}
 // G(m x m) = U^T U for a small n x m block
 __device__ void cta_gram(int n, int m, const double* U, int ldu, double* G) {
   for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
     const int i = e % m, j = e / m;
     if (i < j) continue;  // lower triangle + mirror
-    double s = 0.0;
     const double* ui = U + (size_t)i * ldu;
     const double* uj = U + (size_t)j * ldu;
-    for (int r = 0; r < n; ++r) s = fma(ui[r], uj[r], s);
+    const double s = dot4(n, ui, uj);
     G[i + (size_t)j * m] = s;
     G[j + (size_t)i * m] = s;
   }
@@ -970,9 +1114,14 @@ __device__ bool cta_ortho_cd(int n, int m, double* U, int ldu, double* G, double
     // U <- U T  (T upper triangular): out of place into tmp, then copy back
     for (int e = threadIdx.x; e < n * m; e += blockDim.x) {
       const int r = e % n, j = e / n;
-      double s = 0.0;
-      for (int k = 0; k <= j; ++k) s = fma(U[r + (size_t)k * ldu], T[k + (size_t)j * m], s);
-      tmp[e] = s;
+      double s0 = 0.0, s1 = 0.0;
+      int k = 0;
+      for (; k + 1 <= j; k += 2) {
+        s0 = fma(U[r + (size_t)k * ldu], T[k + (size_t)j * m], s0);
+        s1 = fma(U[r + (size_t)(k + 1) * ldu], T[(k + 1) + (size_t)j * m], s1);
+      }
+      if (k <= j) s0 = fma(U[r + (size_t)k * ldu], T[k + (size_t)j * m], s0);
+      tmp[e] = s0 + s1;
     }
     __syncthreads();
     for (int e = threadIdx.x; e < n * m; e += blockDim.x) U[(e % n) + (size_t)(e / n) * ldu] = tmp[e];
@@ -1011,7 +1160,7 @@ get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_re
   __shared__ int s_passes;
   extern __shared__ __align__(16) double dyn[];
   const int off_x = n_max - n_act;
-  const double* u_x = a_red;  // len_u x n_max, ld len_a (eigenvectors left there by sym_eig)
+  const double* u_x = a_red;  // len_u x n_max, ld ldx = len_a (eigenvectors left there by sym_eig)
   // working set: in shared memory when it fits (the factorisations are chains of dependent steps:
   // from global memory every step pays an L2 round trip, 0.98 ms per call at 111 x 37 against
   // ~0.1 ms on chip), else in `work`
@@ -1024,11 +1173,21 @@ get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_re
   double* tmp = xu + (size_t)n_max * n_act;         // len_u x n_act
   double* u_p = in_smem ? tmp + (size_t)len_u * n_act : u_p_out;   // len_u x n_act (copied out at the end)
   double* buf = in_smem ? u_p + (size_t)len_u * n_act : nullptr;   // 2 n_act
+  int ldx = len_a;
+  if (in_smem == 2) {   // the eigenvectors too: every overlap / projection below walks them once per sweep
+    double* ux_s = buf + 2 * (size_t)n_act;   // len_u x n_max
+    for (int e = threadIdx.x; e < len_u * n_max; e += blockDim.x) {
+      const int r = e % len_u, j = e / len_u;
+      ux_s[e] = u_x[r + (size_t)j * len_a];
+    }
+    u_x = ux_s;
+    ldx = len_u;
+  }
   if (threadIdx.x == 0) s_passes = 0;
   // u_p = u_x(:,ind_x:n_max) with 1 removed from the x coefficient (3716-3722)
   for (int e = threadIdx.x; e < len_u * n_act; e += blockDim.x) {
     const int r = e % len_u, j = e / len_u;
-    double v = u_x[r + (size_t)(off_x + j) * len_a];
+    double v = a_red[r + (size_t)(off_x + j) * len_a];
     if (r == off_x + j) v -= 1.0;
     u_p[r + (size_t)j * len_u] = v;
   }
@@ -1044,18 +1203,19 @@ get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_re
     // xu = u_x^T u_p ; u_p -= u_x xu   (3543-3544)
     for (int e = threadIdx.x; e < n_max * n_act; e += blockDim.x) {
       const int i = e % n_max, j = e / n_max;
-      const double* xi = u_x + (size_t)i * len_a;
-      const double* uj = u_p + (size_t)j * len_u;
-      double s = 0.0;
-      for (int r = 0; r < len_u; ++r) s = fma(xi[r], uj[r], s);
-      xu[e] = s;
+      xu[e] = dot4(len_u, u_x + (size_t)i * ldx, u_p + (size_t)j * len_u);
     }
     __syncthreads();
     for (int e = threadIdx.x; e < len_u * n_act; e += blockDim.x) {
       const int r = e % len_u, j = e / len_u;
-      double s = u_p[r + (size_t)j * len_u];
-      for (int i = 0; i < n_max; ++i) s = fma(-u_x[r + (size_t)i * len_a], xu[i + (size_t)j * n_max], s);
-      tmp[e] = s;
+      double s0 = u_p[r + (size_t)j * len_u], s1 = 0.0;
+      int i = 0;
+      for (; i + 2 <= n_max; i += 2) {
+        s0 = fma(-u_x[r + (size_t)i * ldx], xu[i + (size_t)j * n_max], s0);
+        s1 = fma(-u_x[r + (size_t)(i + 1) * ldx], xu[(i + 1) + (size_t)j * n_max], s1);
+      }
+      if (i < n_max) s0 = fma(-u_x[r + (size_t)i * ldx], xu[i + (size_t)j * n_max], s0);
+      tmp[e] = s0 + s1;
     }
     __syncthreads();
     for (int e = threadIdx.x; e < len_u * n_act; e += blockDim.x) u_p[e] = tmp[e];
@@ -1068,10 +1228,7 @@ get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_re
       double s = 0.0;
       for (int e = threadIdx.x; e < n_max * n_act; e += blockDim.x) {
         const int i = e % n_max, j = e / n_max;
-        const double* xi = u_x + (size_t)i * len_a;
-        const double* uj = u_p + (size_t)j * len_u;
-        double d = 0.0;
-        for (int r = 0; r < len_u; ++r) d = fma(xi[r], uj[r], d);
+        const double d = dot4(len_u, u_x + (size_t)i * ldx, u_p + (size_t)j * len_u);
         s = fma(d, d, s);
       }
       xu_norm = sqrt(cta_sum(s, s_red));
@@ -1079,7 +1236,7 @@ get_coeffs_kernel(int len_a, int len_u, int n_max, int n_act, const double* a_re
       xu_norm = growth * EPS;  // 3562
     }
     done = xu_norm < TOL_ORTHO;
-    if (sweeps > 10 && !done) { fail = 1; break; }  // 3568
+    if (sweeps > 10) { fail = 1; break; }  // 3568 (unconditional in the reference)
   }
   __syncthreads();
   if (in_smem)
@@ -1212,7 +1369,10 @@ size_t coeffs_work_doubles(int len_u, int n_max, int n_act) {
   return 4 * (size_t)n_act * n_act + (size_t)n_max * n_act + (size_t)len_u * n_act + 8;
 }
 
-int g_coeffs_threads = 0;   // 0: 1024 threads; experiment switch (diaglib_b200_k_set_tuning "coeffs_threads")
+void set_chol_blocked(int on) {
+  DLB_CUDA_CHECK(cudaMemcpyToSymbol(g_chol_blocked_dev, &on, sizeof(int)));
+}
+int g_coeffs_threads = 0;   // 0: automatic (512 / 1024 threads); experiment switch (diaglib_b200_k_set_tuning "coeffs_threads")
 int g_coeffs_smem = 1;      // 0: working set of get_coeffs in global memory (round-1 behaviour)
 void get_coeffs(cudaStream_t st, int len_a, int len_u, int n_max, int n_act, const double* a_red, double* u_p,
                 double* work, CoeffStatus* status_dev) {
@@ -1221,14 +1381,19 @@ void get_coeffs(cudaStream_t st, int len_a, int len_u, int n_max, int n_act, con
     DLB_CUDA_CHECK(cudaFuncSetAttribute(get_coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  const int threads = g_coeffs_threads > 0 ? g_coeffs_threads : SM_THREADS;
+  // 512 threads up to 64 active columns (the CTA barriers of the factorisations are cheaper and every loop still has
+  // a thread per element: 511 vs 545 us at 111 x 37 x 37), 1024 beyond (C5: 20.6 vs 22.1 ms at 399 x 133 x 133)
+  const int threads = g_coeffs_threads > 0 ? g_coeffs_threads : (n_act <= 64 ? 512 : SM_THREADS);
   // G, L, Li, T, xu, tmp, u_p, buf in shared memory when they fit (and the block is wide enough for
   // the in-shared-memory factorisation: threads >= the power of two above n_act)
   const size_t need = (4 * (size_t)n_act * n_act + (size_t)n_max * n_act + 2 * (size_t)len_u * n_act + 2 * (size_t)n_act) * sizeof(double);
   int rs = 32;
   while (rs < n_act) rs <<= 1;
-  const int in_smem = (need <= 200 * 1024 && threads >= rs && g_coeffs_smem) ? 1 : 0;
-  get_coeffs_kernel<<<1, threads, in_smem ? need : 0, st>>>(len_a, len_u, n_max, n_act, a_red, u_p, work, in_smem, status_dev);
+  int in_smem = (need <= 200 * 1024 && threads >= rs && g_coeffs_smem) ? 1 : 0;
+  const size_t need_x = need + (size_t)len_u * n_max * sizeof(double);   // + the eigenvectors u_x
+  if (in_smem && need_x <= 200 * 1024) in_smem = 2;
+  get_coeffs_kernel<<<1, threads, in_smem == 2 ? need_x : (in_smem ? need : 0), st>>>(len_a, len_u, n_max, n_act, a_red, u_p, work,
+                                                                                     in_smem, status_dev);
   ++g_launches;
   DLB_CUDA_CHECK(cudaGetLastError());
 }

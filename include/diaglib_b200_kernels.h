@@ -78,7 +78,7 @@ int32_t diaglib_b200_k_sym_eig(int32_t k, double* a_host, int32_t lda, int32_t u
  * (default), 1 = two-sided only; block = columns per block of the one-sided solver (0 = automatic,
  * else 4 or 8).  Returns the previous mode. */
 int32_t diaglib_b200_k_set_eig_mode(int32_t mode, int32_t block);
-/* experiment switches by name (coeffs_threads, coeffs_smem, spmm_chunk, eig_block, eig_mode);
+/* experiment switches by name (coeffs_threads, coeffs_smem, spmm_chunk, eig_block, eig_mode, chol_blocked);
  * returns the previous value, -1 for an unknown name */
 int32_t diaglib_b200_k_set_tuning(const char* name, int32_t value);
 /* device time of the small replicated kernels, milliseconds per call over `reps` back-to-back

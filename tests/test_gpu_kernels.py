@@ -301,8 +301,14 @@ def test_sym_eig_not_positive_definite_falls_back(K):
 def test_small_kernel_timing_table(K, gpu_lib):
     """not a pass/fail test of speed: device time of the replicated single-CTA kernels (pytest -s)"""
     L = gpu_lib.lib()
-    for m in (13, 21, 37, 74, 133):
-        print(f"chol_inv m={m}: {1e3 * L.diaglib_b200_k_time_small(0, m, 0, 0, 50):.1f} us")
+    for m in (13, 21, 37, 74, 112, 133):
+        t_blk = 1e3 * L.diaglib_b200_k_time_small(0, m, 0, 0, 50)
+        L.diaglib_b200_k_set_tuning(b"chol_blocked", 0)
+        try:
+            t_col = 1e3 * L.diaglib_b200_k_time_small(0, m, 0, 0, 50)
+        finally:
+            L.diaglib_b200_k_set_tuning(b"chol_blocked", 1)
+        print(f"chol_inv m={m}: {t_blk:.1f} us blocked (8 columns per step), {t_col:.1f} us column by column")
     for len_u, n_max, n_act in ((111, 37, 37), (111, 37, 20), (74, 37, 37), (63, 21, 21), (399, 133, 133)):
         row = []
         for threads in (1024, 512, 256):
