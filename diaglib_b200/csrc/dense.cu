@@ -12,6 +12,7 @@
 #include <cuda.h>  // CUtensorMap (types only; the encoder is resolved through the runtime)
 
 #include <algorithm>
+#include <map>
 #include <vector>
 
 namespace dlb {
@@ -704,7 +705,19 @@ static void launch_gram_reduce(cudaStream_t st, const double* partial, int ncta,
 }
 
 // Build a balanced task schedule for a p x q block (tile counts ntp x ntq).
+GramSched make_sched_uncached(int ntp, int ntq, bool sym_lower, int nwarps);
+// the schedule depends on the tile counts only: built once per shape (the refinement below costs ~0.1 ms of
+// host time, a solve launches ~1500 Gram kernels)
 GramSched make_sched(int ntp, int ntq, bool sym_lower, int nwarps) {
+  static std::map<uint32_t, GramSched> cache;
+  const uint32_t key = (uint32_t)ntp | ((uint32_t)ntq << 8) | ((uint32_t)nwarps << 16) | (sym_lower ? 1u << 24 : 0u);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const GramSched s = make_sched_uncached(ntp, ntq, sym_lower, nwarps);
+  cache.emplace(key, s);
+  return s;
+}
+GramSched make_sched_uncached(int ntp, int ntq, bool sym_lower, int nwarps) {
   struct T { int ti0, tj0, nc0, nc1, cnt; };
   const int shapes[4][2] = {{2, 4}, {2, 2}, {1, 2}, {1, 1}};
   std::vector<T> tasks;
@@ -736,29 +749,74 @@ GramSched make_sched(int ntp, int ntq, bool sym_lower, int nwarps) {
       }
     if (nxt > 2 * nwarps) break;
   }
-  std::stable_sort(tasks.begin(), tasks.end(), [](const T& a, const T& b) { return a.cnt > b.cnt; });
-  GramSched s{};
-  int load_q[4] = {0, 0, 0, 0};
-  int load_w[GR_WARPS] = {0};
-  int nslot[GR_WARPS] = {0};
-  for (const T& t : tasks) {
-    // least-loaded sub-partition that still has a free slot
-    int bq = -1;
-    for (int qd = 0; qd < 4; ++qd) {
-      bool has_free = false;
-      for (int w = qd; w < nwarps; w += 4) has_free |= nslot[w] < 2;
-      if (has_free && (bq < 0 || load_q[qd] < load_q[bq])) bq = qd;
+  // LPT assignment: tasks by decreasing size onto the least-loaded SM sub-partition (the FP64 tensor pipe is
+  // per sub-partition), then onto its least-loaded warp with a free slot.  Returns false on slot overflow.
+  auto assign = [&](std::vector<T> ts, GramSched* out, int* load_q) -> bool {
+    std::stable_sort(ts.begin(), ts.end(), [](const T& a, const T& b) { return a.cnt > b.cnt; });
+    int load_w[GR_WARPS] = {0};
+    int nslot[GR_WARPS] = {0};
+    for (int qd = 0; qd < 4; ++qd) load_q[qd] = 0;
+    for (const T& t : ts) {
+      int bq = -1;
+      for (int qd = 0; qd < 4; ++qd) {
+        bool has_free = false;
+        for (int w = qd; w < nwarps; w += 4) has_free |= nslot[w] < 2;
+        if (has_free && (bq < 0 || load_q[qd] < load_q[bq])) bq = qd;
+      }
+      if (bq < 0) return false;
+      int bw = -1;
+      for (int w = bq; w < nwarps; w += 4)
+        if (nslot[w] < 2 && (bw < 0 || load_w[w] < load_w[bw])) bw = w;
+      if (out) out->t[bw][nslot[bw]] = GramTask{(uint8_t)t.ti0, (uint8_t)t.tj0, (uint8_t)t.nc0, (uint8_t)t.nc1};
+      ++nslot[bw];
+      load_w[bw] += t.cnt;
+      load_q[bq] += t.cnt;
     }
-    int bw = -1;
-    if (bq >= 0)
-    for (int w = bq; w < nwarps; w += 4)
-      if (nslot[w] < 2 && (bw < 0 || load_w[w] < load_w[bw])) bw = w;
-    if (bw < 0) { std::fprintf(stderr, "diaglib_b200: gram schedule overflow\n"); std::abort(); }
-    s.t[bw][nslot[bw]] = GramTask{(uint8_t)t.ti0, (uint8_t)t.tj0, (uint8_t)t.nc0, (uint8_t)t.nc1};
-    ++nslot[bw];
-    load_w[bw] += t.cnt;
-    load_q[bq] += t.cnt;
+    return true;
+  };
+  auto cost = [](const int* lq) {   // (largest sub-partition load, then the spread)
+    int mx = 0, sq = 0;
+    for (int qd = 0; qd < 4; ++qd) { mx = std::max(mx, lq[qd]); sq += lq[qd] * lq[qd]; }
+    return std::make_pair(mx, sq);
+  };
+  // Refinement: while slots are left, split one task (a two-row task into its rows, a one-row task into two
+  // column halves) if that lowers the largest sub-partition load.  The 74 x 37 overlap of ortho_vs_x (10 x 5
+  // tiles as 2 x 2 tasks) goes from loads 14/12/12/12 to 13/13/12/12, the 74 x 74 first-iteration Gram from
+  // 15/12/14/14 to 14/13/14/14: the kernel's DMMA pipe share follows the largest load.
+  int lq[4];
+  if (!assign(tasks, nullptr, lq)) { std::fprintf(stderr, "diaglib_b200: gram schedule overflow\n"); std::abort(); }
+  while ((int)tasks.size() < 2 * nwarps) {
+    bool improved = false;
+    std::vector<size_t> order(tasks.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tasks[a].cnt < tasks[b].cnt; });
+    for (size_t oi = 0; oi < order.size() && !improved; ++oi) {
+      const T t = tasks[order[oi]];
+      T a, b;
+      if (t.nc0 > 0 && t.nc1 > 0) {
+        a = T{t.ti0, t.tj0, t.nc0, 0, t.nc0};
+        b = T{t.ti0 + 1, t.tj0, t.nc1, 0, t.nc1};
+      } else if (t.nc1 == 0 && t.nc0 >= 2) {
+        const int h = t.nc0 / 2;
+        a = T{t.ti0, t.tj0, t.nc0 - h, 0, t.nc0 - h};
+        b = T{t.ti0, t.tj0 + (t.nc0 - h), h, 0, h};
+      } else {
+        continue;
+      }
+      std::vector<T> cand = tasks;
+      cand[order[oi]] = a;
+      cand.push_back(b);
+      int lq2[4];
+      if (assign(cand, nullptr, lq2) && cost(lq2) < cost(lq)) {
+        tasks.swap(cand);
+        for (int qd = 0; qd < 4; ++qd) lq[qd] = lq2[qd];
+        improved = true;
+      }
+    }
+    if (!improved) break;
   }
+  GramSched s{};
+  assign(tasks, &s, lq);
   return s;
 }
 
@@ -773,6 +831,24 @@ int pick_kt(int cols, int cap = 128) {
 }
 
 }  // namespace
+
+// host-side view of a schedule for the tests: cover[ti + tj * ntp] = how many tasks compute tile (ti, tj),
+// load4[q] = tiles assigned to SM sub-partition q.  Returns the number of tasks.
+int gram_schedule_cover(int ntp, int ntq, bool sym_lower, int nwarps, int* cover, int* load4) {
+  const GramSched s = make_sched(ntp, ntq, sym_lower, nwarps);
+  for (int i = 0; i < ntp * ntq; ++i) cover[i] = 0;
+  for (int q = 0; q < 4; ++q) load4[q] = 0;
+  int ntasks = 0;
+  for (int w = 0; w < nwarps; ++w)
+    for (int sl = 0; sl < 2; ++sl) {
+      const GramTask& t = s.t[w][sl];
+      if (t.nc0 + t.nc1 == 0) continue;
+      ++ntasks;
+      for (int c = 0; c < t.nc0; ++c) { ++cover[t.ti0 + (t.tj0 + c) * ntp]; ++load4[w & 3]; }
+      for (int c = 0; c < t.nc1; ++c) { ++cover[(t.ti0 + 1) + (t.tj0 + c) * ntp]; ++load4[w & 3]; }
+    }
+  return ntasks;
+}
 
 size_t gram_scratch_bytes(int p, int q, int num_sms) {
   const int pb = std::min(p, GR_MAXB), qb = std::min(q, GR_MAXB);

@@ -616,7 +616,16 @@ struct Engine {
     st_launch0 = g_launches;
     for (double& t : t_acc) t = 0;
   }
-  void end_call() { st_launches = g_launches - st_launch0; }
+  void end_call() {
+    st_launches = g_launches - st_launch0;
+    // a contribution that never arrived in the peer window (a rank died or diverged) leaves garbage in the
+    // reduced matrices: report it instead of returning a "converged" result (the stream is synchronised here)
+    if (peer_ok() && st_peer_calls > 0 && status == 0) {
+      unsigned int err = 0;
+      if (cudaMemcpy(&err, &g_peerwin.state->error, sizeof err, cudaMemcpyDeviceToHost) == cudaSuccess && err)
+        fail(DIAGLIB_B200_ECOMM, "peer-window all-reduce: a rank's contribution timed out");
+    }
+  }
   void record(int it, int n_act, int n_max, const double* eig, const double* r_norm, const int* done) {
     hist.it.push_back(it);
     hist.n_act.push_back(n_act);
@@ -2384,6 +2393,11 @@ int32_t diaglib_b200_k_true_residual(int32_t n_loc, int32_t m, const double* x_d
   return g.status;
 }
 
+int32_t diaglib_b200_k_gram_schedule(int32_t ntp, int32_t ntq, int32_t sym_lower, int32_t* cover, int32_t* load4) {
+  if (ntp < 1 || ntq < 1 || ntp > 16 || ntq > 16) return -1;
+  if (((ntp + 1) / 2) * ((ntq + 3) / 4) > 2 * GRAM_CONSUMER_WARPS) return -1;   // such blocks run on the 16-warp barrier kernel (gram_tn)
+  return gram_schedule_cover(ntp, ntq, sym_lower != 0, GRAM_CONSUMER_WARPS, cover, load4);
+}
 int32_t diaglib_b200_k_set_tuning(const char* name, int32_t value) {
   const std::string nm(name ? name : "");
   int* slot = nullptr;

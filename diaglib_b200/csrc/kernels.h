@@ -62,6 +62,9 @@ void peer_allreduce(cudaStream_t st, double* d, int count, int max_from);
 // are computed and the result is mirrored (callers consume one triangle: dsyev 'l' 406,
 // dpotrf 'l' 3261).  `partial` is scratch of at least gram_scratch_bytes(p,q,num_sms).
 size_t gram_scratch_bytes(int p, int q, int num_sms);
+// tile schedule of the Gram kernels for ntp x ntq tiles of 8 x 8 (host logic only; used by the tests)
+int gram_schedule_cover(int ntp, int ntq, bool sym_lower, int nwarps, int* cover, int* load4);
+constexpr int GRAM_CONSUMER_WARPS = 15;   // consumer warps of the TMA / bulk-copy Gram kernels
 void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t lda, int p, const double* B,
              int64_t ldb, int q, double* C, int ldc, bool sym_lower, double* partial);
 

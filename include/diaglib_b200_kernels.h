@@ -81,6 +81,10 @@ int32_t diaglib_b200_k_set_eig_mode(int32_t mode, int32_t block);
 /* experiment switches by name (coeffs_threads, coeffs_smem, spmm_chunk, eig_block, eig_mode, chol_blocked);
  * returns the previous value, -1 for an unknown name */
 int32_t diaglib_b200_k_set_tuning(const char* name, int32_t value);
+/* Tile schedule of the Gram kernels (host logic, no device needed): for a block of ntp x ntq tiles of 8 x 8
+ * (<= 16 x 16; sym_lower: tiles on/below the diagonal only) cover[ti + tj * ntp] receives the number of tasks
+ * that compute tile (ti, tj) and load4[q] the tiles given to SM sub-partition q.  Returns the task count. */
+int32_t diaglib_b200_k_gram_schedule(int32_t ntp, int32_t ntq, int32_t sym_lower, int32_t* cover, int32_t* load4);
 /* device time of the small replicated kernels, milliseconds per call over `reps` back-to-back
  * launches: which = 0 chol_inv on an a x a metric; which = 1 get_coeffs(len_u = a, n_max = b, n_act = c) */
 double diaglib_b200_k_time_small(int32_t which, int32_t a, int32_t b, int32_t c, int32_t reps);

@@ -471,6 +471,16 @@ void oracle_lobpcg_driver(const int32_t* verbose_, const int32_t* gen_eig_, cons
     int len_u = n_max + 2 * n_act;
     if (it == 1) len_u = 2 * n_max;
     dgemm('t', 'n', len_u, len_u, n, one, space.data(), n, aspace.data(), n, zero, a_red.data(), len_a);  // 403
+    if (const char* dump = std::getenv("ORACLE_DUMP_ARED")) {
+      // diagnostic: append (len_u, the len_u x len_u reduced matrix) of every iteration to a file; the
+      // reduced eigensolvers of the GPU path are studied on these (tools/eig_sweeps_study.py)
+      if (FILE* f = std::fopen(dump, "ab")) {
+        const double lu = len_u;
+        std::fwrite(&lu, sizeof(double), 1, f);
+        for (int j = 0; j < len_u; ++j) std::fwrite(&a_red[(size_t)j * len_a], sizeof(double), len_u, f);
+        std::fclose(f);
+      }
+    }
     t1 = now();
     reduced_eig(lo, len_u, a_red.data(), len_a, e_red.data(), work.data(), lwork, &info);  // 406
     t_diag += now() - t1;
