@@ -1051,7 +1051,8 @@ blockmul_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, con
         const int col = c * 8 + (lane & 3) * 2 + e;
         if (col < q) {
           double* dst = Y + row + (int64_t)col * ldy;
-          double v = alpha * acc[r][c][e];
+          double v = acc[r][c][e];
+          if (alpha != 1.0) v *= alpha;
           if (beta != 0.0) v += beta * (*dst);
           *dst = v;
         }
@@ -1167,7 +1168,8 @@ blockmul_persistent_kernel(int64_t n, const double* __restrict__ V, int64_t ldv,
             const int col = cc * 8 + (lane & 3) * 2 + e;
             if (row < n && col < q) {
               double* dst = Y + row + (int64_t)col * ldy;
-              double v = alpha * acc[r][cc][e];
+              double v = acc[r][cc][e];
+              if (alpha != 1.0) v *= alpha;
               if (beta != 0.0) v += beta * (*dst);
               *dst = v;
             }
@@ -1366,6 +1368,15 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
         }
       }
       const int64_t row0 = (blockIdx.x + ti * gridDim.x) * RT;
+      // alpha = 1 in every hot call.  Scaling is a separate, uniformly branched block: a DMUL queues for the FP64
+      // pipe behind the other warps' DMMAs (15 % of this kernel's stall samples in the ncu source view of the
+      // projection step sat on it), and a predicated-off FP64 instruction still takes its slot.
+      if (alpha != 1.0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int cc = 0; cc < NQT; ++cc) { acc[r][cc][0] *= alpha; acc[r][cc][1] *= alpha; }
+      }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int64_t row = row0 + warp * 16 + r * 8 + (lane >> 2);
@@ -1377,7 +1388,7 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
             double v = 0.0;
             if (row < n && col < q) {
               double* dst = Y + row + (int64_t)col * ldy;
-              v = alpha * acc[r][cc][e];
+              v = acc[r][cc][e];
               if (beta != 0.0) v += beta * (*dst);
               *dst = v;
             }

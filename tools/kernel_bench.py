@@ -140,6 +140,21 @@ def main():
         out["memcpy_d2d_37cols"] = dict(ms=round(ms, 4), gbs=round(16.0 * n * 37 / ms / 1e6, 1))
         print(json.dumps(dict(n=n, **out)))
         return
+    if only == "ortho":
+        # the two wide kernels of an ortho_vs_x sweep at the C3 shape: xu = x^T u (3543) and u -= x xu (3544) with
+        # x = the first 74 columns and u the 37 columns behind them, as in the solver
+        t_gram(74, 37, 0, v, w, "gram_74x37")
+        xu = K.DeviceArray.from_numpy(np.asfortranarray(np.random.default_rng(3).standard_normal((74, 37)) * 1e-3))
+        u_ptr = v.col_ptr(74)
+        lib.diaglib_b200_k_project_out(n, 74, 37, v.ptr, n, xu.ptr, u_ptr, n)
+        lib.diaglib_b200_sync()
+        K.timer_start()
+        for _ in range(reps):
+            lib.diaglib_b200_k_project_out(n, 74, 37, v.ptr, n, xu.ptr, u_ptr, n)
+        ms = K.timer_stop_ms() / reps
+        out["project_out_74_37"] = dict(ms=round(ms, 4), gbs=round(8.0 * n * (111 + 37) / ms / 1e6, 1))
+        print(json.dumps(dict(n=n, **out)))
+        return
     if only == "gram":
         t_gram(111, 111, 1, v, w, "gram_sym_111")
         t_gram(74, 37, 0, v, w, "gram_74x37")
