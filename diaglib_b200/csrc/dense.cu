@@ -696,7 +696,11 @@ gram_reduce_peer_kernel(const double* partial, int ncta, int PB, int QB, int p, 
 static void launch_gram_reduce(cudaStream_t st, const double* partial, int ncta, int PB, int QB, int pb, int qb, int sym,
                                double* C, int ldc, double* Ct) {
   const int tot = pb * qb;
-  if (g_fuse_allreduce && g_peerwin.nranks > 1 && tot <= PEER_CAP)
+  if (g_fuse_allreduce && g_peerwin.nranks > 1 && tot > PEER_CAP) {   // the engine would skip its own all-reduce
+    std::fprintf(stderr, "diaglib_b200: a %d x %d Gram block exceeds a peer-window slot\n", pb, qb);
+    std::abort();
+  }
+  if (g_fuse_allreduce && g_peerwin.nranks > 1)
     gram_reduce_peer_kernel<<<(tot + 31) / 32, GRED_SL * 32, 0, st>>>(partial, ncta, PB, QB, pb, qb, sym, C, ldc, Ct, g_live,
                                                                        g_peerwin, 1 << 30);
   else

@@ -704,6 +704,7 @@ void Engine::peer_setup() {
     g_peerwin = w;
   } else {
     g_peerwin.state = state;   // so that peer_teardown frees it
+    if (!peer_base && state) { cudaFree(state); g_peerwin = PeerWin(); }
     peer_teardown();
   }
 }
