@@ -1055,8 +1055,7 @@ blockmul_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, con
         const int col = c * 8 + (lane & 3) * 2 + e;
         if (col < q) {
           double* dst = Y + row + (int64_t)col * ldy;
-          double v = acc[r][c][e];
-          if (alpha != 1.0) v *= alpha;
+          double v = alpha * acc[r][c][e];
           if (beta != 0.0) v += beta * (*dst);
           *dst = v;
         }
@@ -1172,8 +1171,7 @@ blockmul_persistent_kernel(int64_t n, const double* __restrict__ V, int64_t ldv,
             const int col = cc * 8 + (lane & 3) * 2 + e;
             if (row < n && col < q) {
               double* dst = Y + row + (int64_t)col * ldy;
-              double v = acc[r][cc][e];
-              if (alpha != 1.0) v *= alpha;
+              double v = alpha * acc[r][cc][e];
               if (beta != 0.0) v += beta * (*dst);
               *dst = v;
             }
@@ -1340,6 +1338,36 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
                   for (int r = 0; r < 2; ++r) acc[r][cc][e] += sV[kk * SV + warp * 16 + r * 8 + (lane >> 2)];
                 }
               }
+          } else if (NQT == 5 && tri <= -2 && (kc + 1) * BM_KC > -tri - 2) {
+            // rows >= -tri - 2 of C are an upper triangular block (Y = V1 C1 + V2 T: the deferred triangular multiply of
+            // ortho_cd folded into the projection step of ortho_vs_x): a k-step whose four rows lie inside the block
+            // only needs the tiles from the one that holds its first row's diagonal on.  The skipped tiles are not
+            // issued (a branch on a warp-uniform value, not a predicate: a predicated-off DMMA keeps its pipe slot).
+            const int r0 = -tri - 2;
+            const double* sCk = sC + kc * BM_KC + b_off;
+#pragma unroll
+            for (int k4 = 0; k4 < BM_KC / 4; ++k4) {
+              const int rb = kc * BM_KC + k4 * 4 - r0;   // first row of this k-step relative to the block
+              const int ccmin = rb <= 0 ? 0 : (rb >> 3);
+              if (ccmin >= NQT) continue;                 // (rows beyond the block's columns: padding, all zero)
+              double a[2];
+#pragma unroll
+              for (int r = 0; r < 2; ++r) a[r] = sV[k4 * 4 * SV + a_off + r * 8];
+#define DLB_TILE(CC)                                                      \
+  {                                                                       \
+    const double bv = sCk[(CC) * 8 * PS + k4 * 4];                        \
+    dmma884(acc[0][CC][0], acc[0][CC][1], a[0], bv);                      \
+    dmma884(acc[1][CC][0], acc[1][CC][1], a[1], bv);                      \
+  }
+              switch (ccmin) {
+                case 0: DLB_TILE(0)   // fall through
+                case 1: DLB_TILE(1)   // fall through
+                case 2: DLB_TILE(2)   // fall through
+                case 3: DLB_TILE(3)   // fall through
+                default: DLB_TILE(4)
+              }
+#undef DLB_TILE
+            }
           } else {
             const double* sCk = sC + kc * BM_KC + b_off;
 #pragma unroll
@@ -1372,15 +1400,6 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
         }
       }
       const int64_t row0 = (blockIdx.x + ti * gridDim.x) * RT;
-      // alpha = 1 in every hot call.  Scaling is a separate, uniformly branched block: a DMUL queues for the FP64
-      // pipe behind the other warps' DMMAs (15 % of this kernel's stall samples in the ncu source view of the
-      // projection step sat on it), and a predicated-off FP64 instruction still takes its slot.
-      if (alpha != 1.0) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-          for (int cc = 0; cc < NQT; ++cc) { acc[r][cc][0] *= alpha; acc[r][cc][1] *= alpha; }
-      }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int64_t row = row0 + warp * 16 + r * 8 + (lane >> 2);
@@ -1392,7 +1411,12 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
             double v = 0.0;
             if (row < n && col < q) {
               double* dst = Y + row + (int64_t)col * ldy;
-              v = acc[r][cc][e];
+              // The multiply stays although alpha = 1 in every hot call and the DMUL queues for the FP64 pipe behind
+              // the other warps' DMMAs (15 % of the projection step's stall samples, ~1 % of its time).  Storing the
+              // accumulator registers themselves - which the next tile's DMMAs overwrite right away - made whole
+              // solves irreproducible from run to run (tools/determinism_check.py: 2-7 of 8 repetitions differed,
+              // one did not converge); with the product in a register of its own every repetition is bit-identical.
+              v = alpha * acc[r][cc][e];
               if (beta != 0.0) v += beta * (*dst);
               *dst = v;
             }
@@ -1532,7 +1556,7 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
 }  // namespace
 
 void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc, int q,
-               double alpha, double beta, double* Y, int64_t ldy, bool upper_tri, int ident_from) {
+               double alpha, double beta, double* Y, int64_t ldy, bool upper_tri, int ident_from, bool ident_is_tri) {
   if (n <= 0 || q <= 0) return;
   if (q > 128) {
     // column blocks of Y are produced one launch at a time: Y must not overlap the columns of V
@@ -1551,7 +1575,8 @@ void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, 
     double* Yb = Y + (int64_t)q0 * ldy;
     // 1: C upper triangular (first column block only); >= 2: rows >= mode - 2 of C are an identity block
     // (single column block only: the diagonal of the identity must start at column 0)
-    const int mode = (upper_tri && q0 == 0) ? 1 : ((ident_from >= 0 && q <= 128) ? 2 + ident_from : 0);
+    // <= -2: rows >= -mode - 2 of C are an upper triangular block (same restriction)
+    const int mode = (upper_tri && q0 == 0) ? 1 : ((ident_from >= 0 && q <= 128) ? (ident_is_tri ? -(2 + ident_from) : 2 + ident_from) : 0);
     if (qb <= 40)
       launch_blockmul<5>(st, n, V, ldv, p, Cb, ldc, qb, alpha, beta, Yb, ldy, mode);
     else if (qb <= 80)

@@ -27,6 +27,7 @@ namespace dlb {
 int64_t g_launches = 0;
 bool g_use_fused_gram = false;
 bool g_no_ident_proj = false;   // DIAGLIB_B200_NO_IDENT_PROJ=1: u -= x xu with beta = 1 (round-1 form)
+bool g_fold_trmm = true;        // DIAGLIB_B200_FOLD_TRMM=0: every triangular multiply of ortho_cd is applied at once
 
 namespace {
 
@@ -320,8 +321,15 @@ struct Engine {
   // Measured in round 1: the fused kernel needs 142 registers -> one CTA per SM, and these
   // HBM-bound shapes lose more from the halved occupancy (+0.40 s per solve) than the saved
   // re-read of u gains (-0.12 s), so the separate kernels stay the default.
-  bool ortho_cd_host(int64_t n, int m, double* u, int64_t ldu, double& growth, bool have_metric = false, int it_start = 0) {
+  // vsx = 0: plain ortho_cd.  vsx = 1 / 2: the initial ortho_cd of an ortho_vs_x call / the one that closes a sweep,
+  // with u foldable (right behind x): when it is done and another sweep follows - always after the initial one,
+  // after a sweep unless growth * eps < tol (3562-3566) - its last triangular multiply is NOT applied; `deferred`
+  // tells the caller, whose projection step then uses [-xu T; T] (project_out).  Same rule as chol_inv's device logic.
+  bool t_deferred = false;
+  bool ortho_cd_host(int64_t n, int m, double* u, int64_t ldu, double& growth, bool have_metric = false, int it_start = 0,
+                     int vsx = 0) {
     const int maxit = 10;
+    t_deferred = false;
     if (it_start == 0) growth = 1.0;
     for (int it = it_start + 1;; ++it) {
       if (it > maxit) {  // 3248-3254
@@ -345,7 +353,9 @@ struct Engine {
       const double rcond = cs.l_norm * cs.linv_norm;
       growth *= cs.linv_norm;                                    // 3323
       const bool macro_done = EPS * rcond * rcond < TOL_ORTHO;   // 3331-3332
-      if (macro_done || it == maxit || m > 40 || !g_use_fused_gram) {
+      if (macro_done && vsx != 0 && !g_use_fused_gram && (vsx == 1 || !(growth * EPS < TOL_ORTHO))) {
+        t_deferred = true;                                       // 3327 left to the next sweep's projection step
+      } else if (macro_done || it == maxit || m > 40 || !g_use_fused_gram) {
         ktrmm(n, u, ldu, m, d_T);                                // 3327
       } else {
         // 3327 fused with the 3256 of the next pass
@@ -374,7 +384,8 @@ struct Engine {
     DLB_CUDA_CHECK(cudaMemsetAsync(d_octl, 0, sizeof(OrthoCtl), st));
     DLB_CUDA_CHECK(cudaMemsetAsync(&d_octl->live[cell_pass(0, 1)], 1, sizeof(int), st));   // any non-zero value
   }
-  void chain_cd_passes(int64_t n, int m, double* u, int64_t ldu, int phase, bool check_vsx, bool sweep_follows) {
+  void chain_cd_passes(int64_t n, int m, double* u, int64_t ldu, int phase, bool check_vsx, bool sweep_follows,
+                       bool defer_ok = false) {
     for (int p = 1; p <= SPEC_PASSES; ++p) {
       g_live = &d_octl->live[cell_pass(phase, p)];
       kgram_ar(n, u, ldu, m, u, ldu, m, d_metric, m, true);         // 3256
@@ -389,6 +400,7 @@ struct Engine {
       lk.phase = phase;
       lk.pass = p;
       lk.check_vsx = check_vsx ? 1 : 0;
+      lk.defer_ok = defer_ok ? 1 : 0;
       chol_inv(st, m, d_metric, m, d_T, d_cholwork, d_cholst, lk);   // 3261-3316 + the decisions
       g_live = &d_octl->live[cell_trmm(phase, p)];
       ktrmm(n, u, ldu, m, d_T);                                  // 3327
@@ -464,12 +476,18 @@ struct Engine {
   // [x u] [-xu; I] -> u with beta = 0: u then streams through the TMA ring like x instead of being
   // fetched element-wise in the epilogue (6.8 -> 4.x ms at 74 + 37 columns, n = 2^24), and the tensor
   // pipe only visits the diagonal tiles of the identity block.
-  void project_out(int64_t n, int m, int k, const double* x, int64_t ldx, double* u, int64_t ldu) {
+  // fold = true: the last triangular multiply of the preceding ortho_cd was deferred (T = d_T is still the factor of
+  // that pass and xu was taken with the block before the multiply): u <- u T - x (xu T) = [x u] [-xu T; T], one
+  // kernel instead of the multiply (read + write of u) followed by the projection.
+  bool foldable(int m, int k, const double* x, int64_t ldx, const double* u, int64_t ldu) const {
+    return g_fold_trmm && u == x + (int64_t)m * ldx && ldu == ldx && k <= 40 && !g_no_ident_proj && !g_use_fused_gram;
+  }
+  void project_out(int64_t n, int m, int k, const double* x, int64_t ldx, double* u, int64_t ldu, bool fold = false) {
     if (u == x + (int64_t)m * ldx && ldu == ldx && k <= 128 && !g_no_ident_proj) {
       PhaseHandle h;
       if (profile) h = ph_open(PH_KBMUL);
-      proj_coeff(st, m, k, d_xu, m, d_cproj, m + k);
-      block_mul(st, n, x, ldx, m + k, d_cproj, m + k, k, 1.0, 0.0, u, ldu, false, m);
+      proj_coeff(st, m, k, d_xu, m, d_cproj, m + k, fold ? d_T : nullptr);
+      block_mul(st, n, x, ldx, m + k, d_cproj, m + k, k, 1.0, 0.0, u, ldu, false, m, fold);
       if (profile) ph_close(h);
     } else {
       kbmul(n, x, ldx, m, d_xu, m, k, -1.0, 1.0, u, ldu);
@@ -478,9 +496,11 @@ struct Engine {
 
   // ---- ortho_vs_x, diaglib.f90:3481-3574; with bx != nullptr b_ortho_vs_x, 3576-3663 ------
   // sweeps `it_done`+1, ... of the reference's loop, host-driven (one decision per ortho_cd pass)
+  // pending: the triangular multiply of the ortho_cd that ran last was deferred (its T is in d_T)
   void ortho_vs_x_sweeps(int64_t n, int m, int k, const double* x, int64_t ldx, double* u, int64_t ldu, const double* gx,
-                         int it_done) {
+                         int it_done, bool pending = false) {
     const int maxit = 10;
+    const bool fo = foldable(m, k, x, ldx, u, ldu);
     bool done = false;
     int it = it_done;
     double growth = 1.0;
@@ -498,8 +518,9 @@ struct Engine {
         allreduce(d_metric, (size_t)k * k);
         ok = ortho_cd_host(n, k, u, ldu, growth, true);                                      // 3548
       } else {
-        project_out(n, m, k, x, ldx, u, ldu);                                        // 3544
-        ok = ortho_cd_host(n, k, u, ldu, growth);                                            // 3548
+        project_out(n, m, k, x, ldx, u, ldu, pending);                               // 3544 (+ a deferred 3327)
+        ok = ortho_cd_host(n, k, u, ldu, growth, false, 0, fo ? 2 : 0);                      // 3548
+        pending = t_deferred;
       }
       if (status) return;
       done = sweep_verdict(n, m, k, gx, ldx, u, ldu, ok, growth);
@@ -531,26 +552,32 @@ struct Engine {
   void ortho_vs_x(int64_t n, int m, int k, const double* x, int64_t ldx, double* u, int64_t ldu,
                   const double* bx = nullptr) {
     const double* gx = bx ? bx : x;   // the overlap is taken with B x in the generalized case (3632)
+    // Deferred triangular multiply (fo): the last dtrmm (3327) of every ortho_cd that is followed by another sweep is
+    // not applied to u; the sweep takes its overlap with the block as it stands (xu' = gx^T u) and its projection step
+    // applies both at once, u <- u T - x (xu' T) (project_out).  Same arithmetic up to the order of two roundings; one
+    // read + write of u less per sweep (1.7 ms of ~13 at 37 columns, n = 2^24).  DIAGLIB_B200_FOLD_TRMM=0 disables it.
+    const bool fo = foldable(m, k, x, ldx, u, ldu);
     if (!spec_ortho || g_use_fused_gram) {
       double growth = 1.0;
-      const bool ok = ortho_cd_host(n, k, u, ldu, growth);   // 3533
+      const bool ok = ortho_cd_host(n, k, u, ldu, growth, false, 0, fo ? 1 : 0);   // 3533
+      const bool pending = t_deferred;
       if (status) return;
       if (!ok) ortho_qr(n, k, u, ldu);                       // 3534
-      ortho_vs_x_sweeps(n, m, k, x, ldx, u, ldu, gx, 0);
+      ortho_vs_x_sweeps(n, m, k, x, ldx, u, ldu, gx, 0, pending);
       return;
     }
     // speculative chain: ortho_cd (3533), then SPEC_SWEEPS x { u -= x (gx^T u) (3543-3544), ortho_cd (3548) }
     chain_begin();
-    chain_cd_passes(n, k, u, ldu, 0, false, true);
+    chain_cd_passes(n, k, u, ldu, 0, false, true, fo);
     for (int sw = 1; sw <= SPEC_SWEEPS; ++sw) {
       const int* head = &d_octl->live[cell_head(sw)];
       g_live = head;
       kgram_ar(n, gx, ldx, m, u, ldu, k, d_xu, m, false);           // 3543 / 3632
       g_live = nullptr;
       g_live = head;
-      project_out(n, m, k, x, ldx, u, ldu);                      // 3544
+      project_out(n, m, k, x, ldx, u, ldu, fo);                  // 3544; a live sweep always follows a deferring ortho_cd
       g_live = nullptr;
-      chain_cd_passes(n, k, u, ldu, sw, true, sw < SPEC_SWEEPS);
+      chain_cd_passes(n, k, u, ldu, sw, true, sw < SPEC_SWEEPS, fo);
     }
     OrthoCtl c;
     if (!chain_end(c)) return;
@@ -558,9 +585,11 @@ struct Engine {
     if (c.done_vsx) return;
     // the chain stopped short of the reference's loop: pick it up where it stands
     int sweeps_done = c.last_phase;
+    bool pending = c.deferred != 0;
     if (c.halt == 3) {   // ortho_cd number last_phase wants more passes than were enqueued
       double growth = c.growth;
-      const bool ok = ortho_cd_host(n, k, u, ldu, growth, false, SPEC_PASSES);
+      const bool ok = ortho_cd_host(n, k, u, ldu, growth, false, SPEC_PASSES, fo ? (c.last_phase == 0 ? 1 : 2) : 0);
+      pending = t_deferred;
       if (status) return;
       if (c.last_phase == 0) {
         if (!ok) ortho_qr(n, k, u, ldu);                          // 3534
@@ -569,7 +598,7 @@ struct Engine {
         if (status || done) return;
       }
     }
-    ortho_vs_x_sweeps(n, m, k, x, ldx, u, ldu, gx, sweeps_done);
+    ortho_vs_x_sweeps(n, m, k, x, ldx, u, ldu, gx, sweeps_done, pending);
   }
 
   // global row count / offset of this rank's row block
@@ -1704,6 +1733,7 @@ int32_t diaglib_b200_init(int32_t device) {
   if (const char* ev = std::getenv("DIAGLIB_B200_FUSED_GRAM")) g_use_fused_gram = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_SPEC_ORTHO")) g.spec_ortho = ev[0] != '0';
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_IDENT_PROJ")) g_no_ident_proj = ev[0] == '1';
+  if (const char* ev = std::getenv("DIAGLIB_B200_FOLD_TRMM")) g_fold_trmm = ev[0] != '0';
   if (const char* ev = std::getenv("DIAGLIB_B200_REFERENCE_RESTART")) g.reference_restart = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_TMA")) g_disable_tma = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_EIG_COOP_MIN_K")) g_eig_coop_min_k = std::atoi(ev);

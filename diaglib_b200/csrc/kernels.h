@@ -74,8 +74,10 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
 // (with C = L^-T stored as a full matrix with an explicit zero triangle).
 // ident_from >= 0 is a hint: rows [ident_from, p) of C are the q x q identity (Y = V1 C1 + V2 with
 // V2 the last q columns of V), so the tensor pipe only visits the tiles on that diagonal.
+// ident_is_tri: that block of C is upper triangular instead (Y = V1 C1 + V2 T), tiles below its diagonal are skipped.
 void block_mul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc, int q,
-               double alpha, double beta, double* Y, int64_t ldy, bool upper_tri = false, int ident_from = -1);
+               double alpha, double beta, double* Y, int64_t ldy, bool upper_tri = false, int ident_from = -1,
+               bool ident_is_tri = false);
 
 // U <- U * T, T upper triangular m x m (ld m), in place (dtrmm at diaglib.f90:3327).
 void block_trmm_inplace(cudaStream_t st, int64_t n, double* U, int64_t ldu, int m, const double* T);
@@ -156,6 +158,8 @@ struct OrthoCtl {
   int last_pass;         // its pass number (1-based)
   int passes, shifts;    // totals of the chain (statistics)
   int pdone[8];          // per ortho_cd instance: the pass that reached macro_done (0 = none yet)
+  int deferred;          // 1: the triangular multiply of the last ortho_cd that ran was NOT applied (CholLink::defer_ok):
+                         //    its T waits to be folded into the projection step of the sweep that follows
   double growth;         // of the current ortho_cd (3323)
 };
 struct CholLink {        // where a chol_inv call sits in the chain (ctl = null: plain call)
@@ -167,6 +171,8 @@ struct CholLink {        // where a chol_inv call sits in the chain (ctl = null:
   int next_first = -1;   // cell of the first pass of the ortho_cd after that sweep
   int phase = 0, pass = 1;
   int check_vsx = 0;     // this ortho_cd closes a sweep of ortho_vs_x: test xu_norm when it is done
+  int defer_ok = 0;      // inside ortho_vs_x with u right behind x: when this ortho_cd is done and another sweep follows,
+                         // leave its last triangular multiply to that sweep's projection step (engine.cu, project_out)
 };
 // metric (m x m, ldm) -> Linv_t_full (m x m, ld m): the matrix T = L^-T (upper triangular,
 // explicit zeros below) such that U_ortho = U * T.  Follows dpotrf('l') 3261, the shift loop
@@ -191,7 +197,7 @@ void get_coeffs(cudaStream_t st, int len_a, int len_u, int n_max, int n_act, con
 
 // cp ((m + k) x k, ldc) = [-xu (m x k, ldx); I_k]: coefficients that turn u <- u - x xu (3544) into one
 // product over the adjacent blocks [x u]
-void proj_coeff(cudaStream_t st, int m, int k, const double* xu, int ldx, double* cp, int ldc);
+void proj_coeff(cudaStream_t st, int m, int k, const double* xu, int ldx, double* cp, int ldc, const double* T = nullptr);
 
 // reduced problem of caslr_eff_driver: c = a^T a (1303); eig(i) = sqrt(e(k-1-i)), up(:,i) = z(:,k-1-i),
 // um(:,i) = sred up(:,i) / eig(i) (1314-1324)

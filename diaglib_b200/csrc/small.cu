@@ -435,12 +435,16 @@ chol_inv_kernel(int m, const double* G, int ldg, double* T, double* work, CholSt
     ctl->last_pass = link.pass;
     if (st->hard_fail) { ctl->halt = 2; return; }                 // 3276-3284: nothing after this runs
     ctl->live[link.trmm] = 1;                                      // 3327
+    ctl->deferred = 0;
     const double growth = (link.pass == 1 ? 1.0 : ctl->growth) * st->linv_norm;   // 3323
     ctl->growth = growth;
     const double rcond = st->l_norm * st->linv_norm;
     if (EPS * rcond * rcond < TOL_ORTHO) {                         // macro_done, 3331-3332
       ctl->pdone[link.phase] = link.pass;
       if (link.check_vsx && growth * EPS < TOL_ORTHO) { ctl->done_vsx = 1; return; }   // 3562-3566
+      // another sweep of ortho_vs_x follows (enqueued here or continued by the host): its projection step applies
+      // this T together with the projection, so the block is not rewritten now
+      if (link.defer_ok) { ctl->live[link.trmm] = 0; ctl->deferred = 1; }
       if (link.next_head >= 0) { ctl->live[link.next_head] = 1; ctl->live[link.next_first] = 1; }
     } else if (link.next_pass >= 0) {
       ctl->live[link.next_pass] = 1;
@@ -1429,16 +1433,34 @@ __global__ void lr_um_kernel(int k_, int n_max, const double* __restrict__ sred,
 }  // namespace
 
 namespace {
-// cp ((m + k) x k, ldc) = [-xu (m x k, ldx); I_k]
-__global__ void proj_coeff_kernel(int m, int k, const double* __restrict__ xu, int ldx, double* __restrict__ cp, int ldc) {
+// cp ((m + k) x k, ldc) = [-xu (m x k, ldx); I_k], or with T (k x k upper triangular, ld k) [-xu T; T]: the
+// coefficients of u <- u T - x (xu T), the projection step applied to a block whose last triangular multiply
+// was deferred (xu was taken with the block before that multiply)
+__global__ void proj_coeff_kernel(int m, int k, const double* __restrict__ xu, int ldx, const double* __restrict__ T,
+                                  double* __restrict__ cp, int ldc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i >= m + k || j >= k) return;
-  cp[i + (size_t)j * ldc] = i < m ? -xu[i + (size_t)j * ldx] : (i - m == j ? 1.0 : 0.0);
+  double v;
+  if (!T) {
+    v = i < m ? -xu[i + (size_t)j * ldx] : (i - m == j ? 1.0 : 0.0);
+  } else if (i >= m) {
+    v = (i - m <= j) ? T[(i - m) + (size_t)j * k] : 0.0;
+  } else {
+    double s0 = 0.0, s1 = 0.0;
+    int l = 0;
+    for (; l + 1 <= j; l += 2) {
+      s0 = fma(xu[i + (size_t)l * ldx], T[l + (size_t)j * k], s0);
+      s1 = fma(xu[i + (size_t)(l + 1) * ldx], T[(l + 1) + (size_t)j * k], s1);
+    }
+    if (l <= j) s0 = fma(xu[i + (size_t)l * ldx], T[l + (size_t)j * k], s0);
+    v = -(s0 + s1);
+  }
+  cp[i + (size_t)j * ldc] = v;
 }
 }  // namespace
-void proj_coeff(cudaStream_t st, int m, int k, const double* xu, int ldx, double* cp, int ldc) {
+void proj_coeff(cudaStream_t st, int m, int k, const double* xu, int ldx, double* cp, int ldc, const double* T) {
   if (k <= 0) return;
-  proj_coeff_kernel<<<dim3((m + k + 127) / 128, k), 128, 0, st>>>(m, k, xu, ldx, cp, ldc);
+  proj_coeff_kernel<<<dim3((m + k + 127) / 128, k), 128, 0, st>>>(m, k, xu, ldx, T, cp, ldc);
   ++g_launches;
 }
 

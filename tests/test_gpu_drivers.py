@@ -817,3 +817,31 @@ def test_c5_many_roots_n18_vs_oracle_fixture(gpu_lib, driver):
     assert abs(len(hg["it"]) - ref["iterations"]) <= 1
     check_solution(csr, eig, g, n_targ, tol)
     gpu_lib.lib().diaglib_b200_release_workspace()
+
+
+def test_repeated_solves_are_bit_identical(gpu_lib):
+    """Run-to-run reproducibility: the same LOBPCG solve (scaled-down benchmark workload, tiled row order, speculative
+    ortho chains with the deferred triangular multiply) four times, bit-identical eigenvalue history and vectors.
+    Guards the epilogue of the block multiply: storing its accumulator registers directly (instead of alpha * acc in a
+    register of its own) made 2-7 of 8 repetitions differ on a B200 (tools/determinism_check.py)."""
+    D = gpu_lib
+    nx, ny, nz, n_targ = 128, 128, 64, 32
+    n = nx * ny * nz
+    n_max = P.n_eig_rule(n_targ)
+    csr = P.lap3d(nx, ny, nz, delta=1.0)
+    D.set_csr(*csr)
+    D.set_csr_row_order(P.tile_order_3d(nx, ny, nz, tile=(64, 2, 2), curve="morton"))
+    try:
+        g = np.asfortranarray(P.guess_lowest_diag(csr[3], n_max) + P.guess(n, n_max) * (0.1 / np.sqrt(n / 12.0)))
+        ref = None
+        for _ in range(4):
+            ev = g.copy(order="F")
+            eig = np.zeros(n_max)
+            ok = D.lobpcg_driver(False, False, n, n_targ, n_max, 200, 1e-8, 0.0, None, None, None, eig, ev)
+            assert ok
+            got = (np.asarray(D.last_history(n_max)["eig"]).tobytes(), ev.tobytes())
+            if ref is None:
+                ref = got
+            assert got == ref
+    finally:
+        D.set_csr_row_order(None)
