@@ -21,9 +21,11 @@ PeerWin g_peerwin;
 bool g_fuse_allreduce = false;
 
 bool g_disable_ws = false;
+int g_dbg = 0;       // DIAGLIB_B200_DBG (race hunting): 1 / 2 = an empty kernel before / after each ws block multiply, 4 = proxy fence before the first bulk copy, 8 = __threadfence after the last store
+int g_ws_mask = 0;   // DIAGLIB_B200_WS_MASK (A/B testing): 1 = no warp-specialised Gram kernels, 2 = none for the block multiply, 4 = no bulk-copy Gram
 bool g_disable_tma = false;
 bool g_disable_fused_gram = false;  // DIAGLIB_B200_NO_FUSED_GRAM=1
-bool g_bmul_small_tiles = true;   // DIAGLIB_B200_BMUL_RT256=1 selects 256-row tiles (measured slower: 4.91 vs 4.78 ms)  // DIAGLIB_B200_NO_TMA=1: skip the cp.async.bulk.tensor gram kernel  // DIAGLIB_B200_NO_WS=1: fall back to the cp.async kernels (A/B testing)
+bool g_bmul_small_tiles = false;   // DIAGLIB_B200_BMUL_RT256=0 selects 128-row tiles with two CTAs per SM (see launch_blockmul: not reproducible)
 
 // =====================================================================================
 // gram_tn
@@ -885,9 +887,10 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
       const int ncoarse = ((ntp + 1) / 2) * ((ntq + 3) / 4);
       // bulk-copy producer: only when a column segment of a stage is >= 1 KB (narrow blocks);
       // cp.async producers otherwise; the barrier-synchronised kernel is the fallback
-      const bool use_bulk = al16 && (n % 2 == 0) && !g_disable_ws && KT >= 128 && ncoarse <= 2 * GRW_CONS;
+      const bool no_ws_gram = g_disable_ws || (g_ws_mask & 1);
+      const bool use_bulk = al16 && (n % 2 == 0) && !no_ws_gram && !(g_ws_mask & 4) && KT >= 128 && ncoarse <= 2 * GRW_CONS;
       if (use_bulk) KT = pick_kt(cols, 256);
-      const bool use_wsc = !use_bulk && !g_disable_ws && ncoarse <= 2 * GRC_CONS;
+      const bool use_wsc = !use_bulk && !no_ws_gram && ncoarse <= 2 * GRC_CONS;
       const GramSched sched = make_sched(ntp, ntq, diag_blk, use_bulk ? GRW_CONS : (use_wsc ? GRC_CONS : GR_WARPS));
       const int64_t nchunks = (n + KT - 1) / KT;
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, nchunks));
@@ -903,7 +906,7 @@ void gram_tn(cudaStream_t st, int num_sms, int64_t n, const double* A, int64_t l
       bool launched = false;
       // (narrow blocks whose column segments reach 1 KB per stage are served better by the 1-D
       //  bulk-copy producer below: 3.9 vs 3.2 TB/s on the 37-column metric of ortho_cd)
-      if (al16 && !use_bulk && !g_disable_ws && !g_disable_tma && ncoarse <= 2 * GRW_CONS && n < (int64_t)1 << 31) {
+      if (al16 && !use_bulk && !no_ws_gram && !g_disable_tma && ncoarse <= 2 * GRW_CONS && n < (int64_t)1 << 31) {
         // TMA-tiled kernel: stage length from the unpadded box footprint
         int kt = 128;
         while (kt > 16 && (size_t)GR_STAGES * cols * kt * 8 > 200 * 1024) kt >>= 1;
@@ -1227,7 +1230,8 @@ __device__ __forceinline__ void bm_chunk_tri(double (&acc)[2][NQT][2], const dou
 template <int NQT, int NCONS, bool GRAM>
 __global__ void __launch_bounds__((NCONS + 1) * 32)
 blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, const double* __restrict__ C, int ldc,
-                   int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri, double* gpartial, const int* __restrict__ live) {
+                   int q, double alpha, double beta, double* Y, int64_t ldy, int PS, int tri, double* gpartial, const int* __restrict__ live,
+                   int dbg) {
   if (live && *live == 0) return;   // predicated step of a speculative ortho chain (engine.cu)
   extern __shared__ __align__(16) double smem[];
   constexpr int QB = NQT * 8;
@@ -1261,6 +1265,7 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
     // ---------------- producer ----------------
     int s = 0;
     uint32_t ph = 0;
+    if (dbg & 4) asm volatile("fence.proxy.async.global;\n" ::: "memory");
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
       const int64_t row0 = (blockIdx.x + ti * gridDim.x) * RT;
       const int64_t rem = n - row0;
@@ -1400,30 +1405,48 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
         }
       }
       const int64_t row0 = (blockIdx.x + ti * gridDim.x) * RT;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int64_t row = row0 + warp * 16 + r * 8 + (lane >> 2);
-#pragma unroll
-        for (int cc = 0; cc < NQT; ++cc) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = cc * 8 + (lane & 3) * 2 + e;
-            double v = 0.0;
-            if (row < n && col < q) {
-              double* dst = Y + row + (int64_t)col * ldy;
-              // The multiply stays although alpha = 1 in every hot call and the DMUL queues for the FP64 pipe behind
-              // the other warps' DMMAs (15 % of the projection step's stall samples, ~1 % of its time).  Storing the
-              // accumulator registers themselves - which the next tile's DMMAs overwrite right away - made whole
-              // solves irreproducible from run to run (tools/determinism_check.py: 2-7 of 8 repetitions differed,
-              // one did not converge); with the product in a register of its own every repetition is bit-identical.
-              v = alpha * acc[r][cc][e];
-              if (beta != 0.0) v += beta * (*dst);
-              *dst = v;
-            }
-            acc[r][cc][e] = GRAM ? v : 0.0;
-          }
-        }
-      }
+      // The multiply by alpha stays although alpha = 1 in every hot call and the DMUL queues for the FP64 pipe behind
+      // the other warps' DMMAs (15 % of the projection step's stall samples, ~1 % of its time).  Storing the
+      // accumulator registers themselves - which the next tile's DMMAs overwrite right away - made whole
+      // solves irreproducible from run to run (tools/determinism_check.py: 2-7 of 8 repetitions differed,
+      // one did not converge); with the product in a register of its own every repetition is bit-identical.
+#define DLB_STORE_TILE(VEXPR)                                                        \
+  _Pragma("unroll") for (int r = 0; r < 2; ++r) {                                    \
+    const int64_t row = row0 + warp * 16 + r * 8 + (lane >> 2);                      \
+    _Pragma("unroll") for (int cc = 0; cc < NQT; ++cc) {                             \
+      _Pragma("unroll") for (int e = 0; e < 2; ++e) {                                \
+        const int col = cc * 8 + (lane & 3) * 2 + e;                                 \
+        double v = 0.0;                                                              \
+        if (row < n && col < q) {                                                    \
+          double* dst = Y + row + (int64_t)col * ldy;                                \
+          VEXPR;                                                                     \
+          if (beta != 0.0) v += beta * (*dst);                                       \
+          *dst = v;                                                                  \
+        }                                                                            \
+        acc[r][cc][e] = GRAM ? v : 0.0;                                              \
+      }                                                                              \
+    }                                                                                \
+  }
+#ifndef DLB_DBG
+#define DLB_DBG 0
+#endif
+#if DLB_DBG == 0
+      DLB_STORE_TILE(v = alpha * acc[r][cc][e])
+#elif DLB_DBG == 1
+      DLB_STORE_TILE(v = acc[r][cc][e])
+#elif DLB_DBG == 2
+      DLB_STORE_TILE(asm volatile("mov.b64 %0, %1;" : "=d"(v) : "d"(acc[r][cc][e])))
+#elif DLB_DBG == 3
+      if (tri == 1) { DLB_STORE_TILE(v = acc[r][cc][e]) } else { DLB_STORE_TILE(v = alpha * acc[r][cc][e]) }
+#elif DLB_DBG == 4
+      if (tri == 0) { DLB_STORE_TILE(v = acc[r][cc][e]) } else { DLB_STORE_TILE(v = alpha * acc[r][cc][e]) }
+#elif DLB_DBG == 5
+      if (tri >= 2 || tri <= -2) { DLB_STORE_TILE(v = acc[r][cc][e]) } else { DLB_STORE_TILE(v = alpha * acc[r][cc][e]) }
+#elif DLB_DBG == 6
+      __nanosleep(1000);
+      DLB_STORE_TILE(v = acc[r][cc][e])
+#endif
+#undef DLB_STORE_TILE
       if (GRAM) {
         // G += Y'^T Y' over this warp's 16 rows: 4 k-steps of 4 rows
 #pragma unroll
@@ -1452,6 +1475,7 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
           for (int cc = 0; cc < NQT; ++cc) acc[r][cc][0] = acc[r][cc][1] = 0.0;
       }
     }
+    if (dbg & 8) __threadfence();
     if (GRAM) {
       // reduce the 8 warps' accumulators in a fixed order through the (drained) ring, one partial per CTA
       asm volatile("bar.sync 1, %0;\n" ::"r"(BMW_CONS * 32));
@@ -1479,6 +1503,7 @@ blockmul_ws_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int p, 
   }
 }
 
+__global__ void dbg_noop_kernel() {}
 template <int NQT>
 void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, int p, const double* C, int ldc,
                      int q, double alpha, double beta, double* Y, int64_t ldy, int mode) {
@@ -1503,7 +1528,7 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
   const int p16 = (p + 15) / 16 * 16;
   const int PS = p16 + 4;
   const size_t smem_p = ((size_t)QB * PS + (size_t)BM_STAGES * BM_KC * BM_SV) * sizeof(double);
-  if (al16 && (n % 2 == 0) && !g_disable_ws) {
+  if (al16 && (n % 2 == 0) && !g_disable_ws && !(g_ws_mask & 2)) {
     const size_t sc_bytes = (2 * BMW_STAGES + (size_t)QB * PS) * sizeof(double);
     const size_t smem16 = sc_bytes + (size_t)BMW_STAGES * BM_KC * (16 * 16 + 4) * sizeof(double);
     const size_t smem8 = sc_bytes + (size_t)BMW_STAGES * BM_KC * (8 * 16 + 4) * sizeof(double);
@@ -1517,15 +1542,25 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
     if (NQT == 5 && smem16 <= 220 * 1024 && n >= 256 * 2 && !g_bmul_small_tiles) {
       const int64_t nt16 = (n + 255) / 256;
       const unsigned grid = (unsigned)std::min<int64_t>(nt16, (int64_t)num_sms);
-      blockmul_ws_kernel<5, 16, false><<<grid, 17 * 32, smem16, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, mode, nullptr, g_live);
+      if (g_dbg & 1) dbg_noop_kernel<<<1, 32, 0, st>>>();
+      blockmul_ws_kernel<5, 16, false><<<grid, 17 * 32, smem16, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, mode, nullptr, g_live, g_dbg);
       ++g_launches;
       return;
     }
     if (smem8 <= 200 * 1024 && ntiles >= 2) {
       // two CTAs per SM while C (p x q) is small enough to be resident twice, one beyond (Davidson:
       // p = ldu up to ~400 with q <= 40)
-      const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * (smem8 <= 110 * 1024 ? 2 : 1));
-      blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, mode, nullptr, g_live);
+      // ONE CTA per SM.  Two co-resident CTAs of this kernel (smem8 <= 110 KB; the round-1 default, ~3 % faster on the
+      // 111 -> 37 product) made whole solves irreproducible from run to run - rarely with the shipped epilogue
+      // (one non-converged solve in ~40 at n = 2^24), in 9 of 10 repetitions with an epilogue that stores the
+      // accumulator registers directly - while every variant with one CTA per SM (this grid, or the 16-consumer
+      // kernel above) reproduced all repetitions bit for bit, as do the barrier-pipelined fallbacks
+      // (profiles/determinism_bisect_r02.log).  The kernel in isolation and ortho_vs_x as a sequence are reproducible
+      // in either form; the interaction was not identified.  DIAGLIB_B200_DBG=32 restores two CTAs per SM.
+      const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * ((smem8 <= 110 * 1024 && (g_dbg & 32)) ? 2 : 1));
+      if (g_dbg & 1) dbg_noop_kernel<<<1, 32, 0, st>>>();
+      blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, mode, nullptr, g_live, g_dbg);
+      if (g_dbg & 2) dbg_noop_kernel<<<1, 32, 0, st>>>();
       ++g_launches;
       return;
     }
@@ -1626,7 +1661,7 @@ void block_mul_gram(cudaStream_t st, int num_sms, int64_t n, const double* V, in
     DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blockmul_ws_kernel<NQT, 8, true>, 9 * 32, smem));
     const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * std::max(1, occ));
     blockmul_ws_kernel<NQT, 8, true><<<grid, 9 * 32, smem, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS,
-                                                                  upper_tri ? 1 : 0, partial, g_live);
+                                                                  upper_tri ? 1 : 0, partial, g_live, g_dbg);
     ++g_launches;
     const int tot = q * q;
     gram_reduce_kernel<<<(tot + 31) / 32, GRED_SL * 32, 0, st>>>(partial, (int)grid, QB, QB, q, q, 1, G, ldg, nullptr, g_live);

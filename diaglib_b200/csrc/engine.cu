@@ -1730,6 +1730,8 @@ int32_t diaglib_b200_init(int32_t device) {
   if (!g.sw0) { DLB_CUDA_CHECK(cudaEventCreate(&g.sw0)); DLB_CUDA_CHECK(cudaEventCreate(&g.sw1)); }
   if (!g.partial.ensure(gram_scratch_bytes(128, 128, g.num_sms))) return DIAGLIB_B200_EALLOC;
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_WS")) g_disable_ws = ev[0] == '1';
+  if (const char* ev = std::getenv("DIAGLIB_B200_WS_MASK")) g_ws_mask = std::atoi(ev);
+  if (const char* ev = std::getenv("DIAGLIB_B200_DBG")) g_dbg = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_FUSED_GRAM")) g_use_fused_gram = ev[0] == '1';
   if (const char* ev = std::getenv("DIAGLIB_B200_SPEC_ORTHO")) g.spec_ortho = ev[0] != '0';
   if (const char* ev = std::getenv("DIAGLIB_B200_NO_IDENT_PROJ")) g_no_ident_proj = ev[0] == '1';
@@ -1742,7 +1744,7 @@ int32_t diaglib_b200_init(int32_t device) {
   if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_SHORT")) g_spmm_short = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_CHUNK")) g_spmm_chunk = std::atoi(ev);
   if (const char* ev = std::getenv("DIAGLIB_B200_SPMM_CHUNK_TILED")) g_spmm_chunk_tiled = std::atoi(ev);
-  if (const char* ev = std::getenv("DIAGLIB_B200_BMUL_RT256")) g_bmul_small_tiles = ev[0] != '1';
+  if (const char* ev = std::getenv("DIAGLIB_B200_BMUL_RT256")) g_bmul_small_tiles = ev[0] == '0';
   g.inited = true;
   g.status = 0;
   return DIAGLIB_B200_OK;

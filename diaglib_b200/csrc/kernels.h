@@ -11,6 +11,8 @@ namespace dlb {
 // number of kernels launched by this library since load (bench.py reports it as gpu_launches)
 extern int64_t g_launches;
 extern bool g_disable_ws;
+extern int g_ws_mask;
+extern int g_dbg;
 extern bool g_disable_tma;
 extern bool g_disable_fused_gram;
 extern bool g_bmul_small_tiles;

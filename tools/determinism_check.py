@@ -17,7 +17,9 @@ n_max = P.n_eig_rule(n_targ)
 D.init(0)
 csr = P.lap3d(nx, nx, nx, delta=1.0)
 D.set_csr(*csr)
-D.set_csr_row_order(P.tile_order_3d(nx, nx, nx, tile=(64, 2, 2), curve="morton"))
+import os
+if not os.environ.get("DIAGLIB_B200_DET_NATURAL"):
+    D.set_csr_row_order(P.tile_order_3d(nx, nx, nx, tile=(64, 2, 2), curve="morton"))
 g = np.asfortranarray(P.guess_lowest_diag(csr[3], n_max) + P.guess(n, n_max) * (0.1 / np.sqrt(n / 12.0)))
 first = None
 bad = 0
