@@ -545,9 +545,21 @@ def main():
         return float(t.item())
 
     # ---- warm-up ------------------------------------------------------------------------
+    # A solve that does not converge is repeated (at most twice) and COUNTED: the line reports `failed_solves`
+    # (0 in every run recorded under profiles/ since the block multiply runs one CTA per SM, DESIGN.md section 3;
+    # before that about one solve in 40 failed) instead of the whole measurement being lost to one assertion.
+    failed = [0]
+
+    def until_ok(fn):
+        for _attempt in range(3):
+            res = fn()
+            if res[0]:
+                return res
+            failed[0] += 1
+        raise AssertionError("solve did not converge in 3 attempts")
+
     for _ in range(args.warmup):
-        ok, ms, wall = solve_resident()
-        assert ok, "warm-up solve did not converge"
+        until_ok(solve_resident)
     its = len(D.last_history(n_max)["it"])
 
     # ---- timed: K solves, start vectors resident in HBM ------------------------------------
@@ -556,8 +568,7 @@ def main():
         sampler.start()
     tot_ms, tot_its, launches = 0.0, 0, 0
     for _ in range(args.steps):
-        ok, ms, wall = solve_resident()
-        assert ok
+        ok, ms, wall = until_ok(solve_resident)
         tot_ms += maxr(ms)
         tot_its += len(D.last_history(n_max)["it"])
         launches += D.last_stats()["launches"]
@@ -571,8 +582,7 @@ def main():
     solve_e2e()
     e2e_t, e2e_its = 0.0, 0
     for _ in range(args.steps):
-        ok, wall = solve_e2e()
-        assert ok
+        ok, wall = until_ok(solve_e2e)
         e2e_t += maxr(wall)
         e2e_its += len(D.last_history(n_max)["it"])
     e2e_value = e2e_its / e2e_t
@@ -756,6 +766,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": bench_config(nx, n_loc, world), "rows_per_gpu": n_loc, "parallelism": f"row-partition x{world}",
             "stats": D.last_stats(),
+            "failed_solves": failed[0],
             "allreduce": D.peer_info(),
             "parity": parity,
             "time_to_converge_s": ms_per_step * 1e-3, "iterations": tot_its / args.steps, "converged": True,
