@@ -1559,7 +1559,10 @@ void launch_blockmul(cudaStream_t st, int64_t n, const double* V, int64_t ldv, i
       // in either form; the interaction was not identified.  DIAGLIB_B200_DBG=32 restores two CTAs per SM.
       const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * ((smem8 <= 110 * 1024 && (g_dbg & 32)) ? 2 : 1));
       if (g_dbg & 1) dbg_noop_kernel<<<1, 32, 0, st>>>();
-      blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, smem8, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, mode, nullptr, g_live, g_dbg);
+      // the request is padded to more than half an SM's shared memory so that the block scheduler cannot place two
+      // of these CTAs on one SM even when it has SMs to spare (227 KB attribute set above)
+      const size_t smem_req = (g_dbg & 32) ? smem8 : std::max(smem8, (size_t)116 * 1024);
+      blockmul_ws_kernel<NQT, 8, false><<<grid, 9 * 32, smem_req, st>>>(n, V, ldv, p, C, ldc, q, alpha, beta, Y, ldy, PS, mode, nullptr, g_live, g_dbg);
       if (g_dbg & 2) dbg_noop_kernel<<<1, 32, 0, st>>>();
       ++g_launches;
       return;
