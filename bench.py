@@ -567,10 +567,13 @@ def main():
     if rank == 0:
         sampler.start()
     tot_ms, tot_its, launches = 0.0, 0, 0
+    sigs = set()   # the K timed solves start from the same block: their eigenvalue histories must agree bit for bit
     for _ in range(args.steps):
         ok, ms, wall = until_ok(solve_resident)
         tot_ms += maxr(ms)
-        tot_its += len(D.last_history(n_max)["it"])
+        h_ = D.last_history(n_max)
+        tot_its += len(h_["it"])
+        sigs.add(np.asarray(h_["eig"], dtype=np.float64).tobytes())
         launches += D.last_stats()["launches"]
     clocks = sampler.stop() if rank == 0 else None
     hist = D.last_history(n_max)
@@ -767,6 +770,7 @@ def main():
             "config": bench_config(nx, n_loc, world), "rows_per_gpu": n_loc, "parallelism": f"row-partition x{world}",
             "stats": D.last_stats(),
             "failed_solves": failed[0],
+            "repeat_check": {"solves": args.steps, "bit_identical_histories": len(sigs) == 1},
             "allreduce": D.peer_info(),
             "parity": parity,
             "time_to_converge_s": ms_per_step * 1e-3, "iterations": tot_its / args.steps, "converged": True,
